@@ -1,0 +1,226 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for the CPU checkers.
+
+Two interchangeable back ends with the same method surface:
+
+* ``load_oracle()``    -> oracle/libmoe_oracle.so  (plain-C restatement, always buildable; ``make -C oracle oracle``)
+* ``load_reference()`` -> oracle/_ref/libmoe_ref.so (the unmodified Cornell-MOE C++ core; ``make -C oracle ref``,
+  only buildable where /root/reference exists, but the built .so travels to the GPU box)
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this package.  The product (``cornell_moe_b200``) never does.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    if a is None:
+        return np.zeros(0, dtype=np.int32)
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class CpuGP:
+    """Handle on a CPU GaussianProcess (oracle or reference)."""
+
+    def __init__(self, backend, handle, kernel, dim, N, derivs):
+        self.b = backend
+        self.h = handle
+        self.kernel = kernel
+        self.dim = dim
+        self.N = N
+        self.derivs = derivs
+        self.g = len(derivs)
+        self.n = N * (1 + self.g)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.b._fn("gp_destroy")(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def state(self):
+        K = np.empty(self.n * self.n)
+        kinvy = np.empty(self.n)
+        mean = ctypes.c_double()
+        self.b._fn("gp_get_state")(self.h, _d(K), _d(kinvy), ctypes.byref(mean))
+        return K.reshape(self.n, self.n).T.copy(), kinvy, mean.value  # K as a proper [row, col] array
+
+    def posterior(self, pts, derivs_s=None, want=("mean", "var")):
+        """Returns dict with any of mean, grad_mean, var, chol_var, grad_var, grad_chol (raw reference layouts)."""
+        pts = _f64(pts).reshape(-1, self.dim)
+        num = pts.shape[0]
+        ds = _i32(derivs_s)
+        Q = num * (1 + len(ds))
+        out = {}
+        bufs = {
+            "mean": np.empty(Q),
+            "grad_mean": np.empty(self.dim * Q),
+            "var": np.empty(Q * Q),
+            "chol_var": np.empty(Q * Q),
+            "grad_var": np.empty(self.dim * Q * Q * num),
+            "grad_chol": np.empty(self.dim * Q * Q * num),
+        }
+        args = [(_d(bufs[k]) if k in want else None) for k in ("mean", "grad_mean", "var", "chol_var", "grad_var", "grad_chol")]
+        f = self.b._fn("gp_posterior")
+        f.restype = ctypes.c_int
+        rc = f(self.h, _d(pts), num, _i(ds), len(ds), *args)
+        out["rc"] = rc
+        for k in want:
+            out[k] = bufs[k]
+        return out
+
+    def mean_additional(self, pts):
+        pts = _f64(pts).reshape(-1, self.dim)
+        out = np.empty(pts.shape[0])
+        self.b._fn("gp_mean_additional")(self.h, _d(pts), pts.shape[0], _d(out))
+        return out
+
+    def ei(self, Xq, Xp, num_mc, best_so_far, table, grad=False):
+        Xq = _f64(Xq).reshape(-1, self.dim)
+        Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
+        table = _f64(table).ravel()
+        g = np.empty(Xq.size) if grad else None
+        f = self.b._fn("ei")
+        f.restype = ctypes.c_double
+        v = f(self.h, _d(Xq), _d(Xp), Xq.shape[0], Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far), _d(table),
+              table.size, _d(g))
+        return (v, g.reshape(Xq.shape)) if grad else v
+
+    def kg(self, Xq, Xp, num_mc, best_so_far, table, gd, inner_bounds, discrete_pts, num_fidelity=0, grad=False,
+           want_best_points=False):
+        Xq = _f64(Xq).reshape(-1, self.dim)
+        Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
+        table = _f64(table).ravel()
+        gd = _f64(gd)
+        inner_bounds = _f64(inner_bounds).ravel()
+        discrete_pts = _f64(discrete_pts).reshape(-1, self.dim - num_fidelity)
+        g = np.empty(Xq.size) if grad else None
+        bp = np.empty(num_mc * self.dim) if want_best_points else None
+        f = self.b._fn("kg")
+        f.restype = ctypes.c_double
+        v = f(self.h, int(num_fidelity), _d(gd), _d(inner_bounds), _d(discrete_pts), discrete_pts.shape[0], _d(Xq),
+              _d(Xp), Xq.shape[0], Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far), _d(table), table.size,
+              _d(g), _d(bp))
+        res = [v]
+        if grad:
+            res.append(g.reshape(Xq.shape))
+        if want_best_points:
+            res.append(bp.reshape(num_mc, self.dim))
+        return res[0] if len(res) == 1 else tuple(res)
+
+
+class CpuBackend:
+    def __init__(self, path, prefix, name):
+        self.lib = ctypes.CDLL(path)
+        self.prefix = prefix
+        self.name = name
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def covariance(self, kernel, alpha, lengths, p1, d1, p2, d2, grad=False):
+        lengths = _f64(lengths)
+        p1, p2 = _f64(p1), _f64(p2)
+        d1, d2 = _i32(d1), _i32(d2)
+        dim = p1.size
+        size = (1 + len(d1)) * (1 + len(d2)) * (dim if grad else 1)
+        out = np.empty(size)
+        self._fn("grad_covariance" if grad else "covariance")(
+            int(kernel), dim, ctypes.c_double(alpha), _d(lengths), _d(p1), _i(d1), len(d1), _d(p2), _i(d2), len(d2),
+            _d(out))
+        return out
+
+    def cholesky(self, A):
+        """A: [n, n] symmetric (row/col array). Returns (rc, L as [row, col] with the reference's untouched upper part)."""
+        A = np.array(A, dtype=np.float64)
+        n = A.shape[0]
+        buf = np.ascontiguousarray(A.T)  # column-major buffer
+        f = self._fn("cholesky")
+        f.restype = ctypes.c_int
+        rc = f(n, _d(buf))
+        return rc, buf.T.copy()
+
+    def potrs(self, L, B):
+        L = np.ascontiguousarray(np.array(L, dtype=np.float64).T)
+        B = np.array(B, dtype=np.float64)
+        B2 = B.reshape(B.shape[0], -1)
+        buf = np.ascontiguousarray(B2.T)
+        self._fn("potrs")(_d(L), L.shape[0], B2.shape[1], _d(buf))
+        return buf.T.copy().reshape(B.shape)
+
+    def limit_update(self, bounds, mrc, x, upd):
+        bounds = _f64(bounds).ravel()
+        x = _f64(x)
+        upd = np.array(upd, dtype=np.float64)
+        self._fn("limit_update")(_d(bounds), x.size, ctypes.c_double(mrc), _d(x), _d(upd))
+        return upd
+
+    def gp(self, kernel, alpha, lengths, X, y, noise, derivs=None):
+        X = _f64(X)
+        N, dim = X.shape
+        y = _f64(y).ravel()
+        derivs = _i32(derivs)
+        noise = _f64(noise).ravel()
+        lengths = _f64(lengths)
+        assert y.size == N * (1 + len(derivs)) and noise.size == 1 + len(derivs) and lengths.size == dim
+        lm = ctypes.c_int(0)
+        f = self._fn("gp_create")
+        f.restype = ctypes.c_void_p
+        h = f(int(kernel), ctypes.c_double(alpha), _d(lengths), _d(X), _d(y), _d(noise), _i(derivs), len(derivs), dim,
+              N, ctypes.byref(lm))
+        if not h:
+            return None, lm.value
+        return CpuGP(self, ctypes.c_void_p(h), kernel, dim, N, derivs), 0
+
+    def max_threads(self):
+        f = self._fn("max_threads")
+        f.restype = ctypes.c_int
+        return f()
+
+
+def oracle_path():
+    return os.path.join(_HERE, "libmoe_oracle.so")
+
+
+def reference_path():
+    return os.path.join(_HERE, "_ref", "libmoe_ref.so")
+
+
+def load_oracle():
+    return CpuBackend(oracle_path(), "oracle_", "port")
+
+
+def load_reference():
+    return CpuBackend(reference_path(), "ref_", "reference")
+
+
+def have_reference():
+    return os.path.exists(reference_path())
+
+
+def philox_normals(seed, first_draw, num_draws, per_draw):
+    """Host restatement of the CUDA path's Philox4x32-10 + Box-Muller stream: [num_draws, per_draw]."""
+    lib = ctypes.CDLL(oracle_path())
+    out = np.empty(num_draws * per_draw)
+    lib.oracle_philox_normals(ctypes.c_uint64(seed), ctypes.c_uint64(first_draw), int(num_draws), int(per_draw), _d(out))
+    return out.reshape(num_draws, per_draw)

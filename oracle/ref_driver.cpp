@@ -1,0 +1,263 @@
+// TEST INFRASTRUCTURE — not product code.
+//
+// Thin extern "C" driver around the UNMODIFIED Cornell-MOE C++ core, compiled where it lies under
+// /root/reference by oracle/Makefile into oracle/_ref/libmoe_ref.so.  It exists so that
+//   (1) the plain-C restatement in oracle/moe_oracle.c can be pinned against the real reference, and
+//   (2) tests / bench.py --impl reference can time the reference's own OpenMP path on host cores.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+//
+// Every entry point here just marshals plain pointers into the reference's classes:
+//   GaussianProcess                      moe/optimal_learning/cpp/gpp_math.hpp:275
+//   ExpectedImprovementEvaluator/State   gpp_math.hpp:1001 / :1149
+//   KnowledgeGradientEvaluator/State     gpp_knowledge_gradient_optimization.hpp:152 / :310
+//   NormalRNGSimulator (table replay)    gpp_random.hpp:314
+//   EvaluateKGAtPointList                gpp_knowledge_gradient_optimization.hpp:972
+//   EvaluateEIAtPointList                gpp_math.cpp:2305
+#include <omp.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+// K_chol_ has no public accessor in the reference; the parity tests need the factor itself.
+#define private public
+#include "gpp_math.hpp"
+#undef private
+#include "gpp_covariance.hpp"
+#include "gpp_domain.hpp"
+#include "gpp_exception.hpp"
+#include "gpp_knowledge_gradient_optimization.hpp"
+#include "gpp_linear_algebra.hpp"
+#include "gpp_optimization.hpp"
+#include "gpp_optimizer_parameters.hpp"
+#include "gpp_random.hpp"
+
+using namespace optimal_learning;  // NOLINT
+
+namespace {
+
+std::unique_ptr<CovarianceInterface> MakeCovariance(int kernel, int dim, double alpha, const double* lengths) {
+  if (kernel == 0) {
+    return std::unique_ptr<CovarianceInterface>(new SquareExponential(dim, alpha, lengths));
+  }
+  return std::unique_ptr<CovarianceInterface>(new MaternNu2p5(dim, alpha, lengths));
+}
+
+TensorProductDomain MakeDomain(const double* bounds, int dim) {
+  std::vector<ClosedInterval> iv(dim);
+  for (int i = 0; i < dim; ++i) {
+    iv[i] = ClosedInterval(bounds[2 * i], bounds[2 * i + 1]);
+  }
+  return TensorProductDomain(iv.data(), dim);
+}
+
+GradientDescentParameters MakeGD(const double* p) {
+  // p = {num_multistarts, max_num_steps, max_num_restarts, num_steps_averaged, gamma, pre_mult, max_relative_change, tolerance}
+  return GradientDescentParameters(static_cast<int>(p[0]), static_cast<int>(p[1]), static_cast<int>(p[2]),
+                                   static_cast<int>(p[3]), p[4], p[5], p[6], p[7]);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- covariance (gpp_covariance.cpp:121-234, 339-459) ----
+void ref_covariance(int kernel, int dim, double alpha, const double* lengths, const double* p1, const int* d1, int g1,
+                    const double* p2, const int* d2, int g2, double* cov) {
+  auto c = MakeCovariance(kernel, dim, alpha, lengths);
+  c->Covariance(p1, d1, g1, p2, d2, g2, cov);
+}
+
+void ref_grad_covariance(int kernel, int dim, double alpha, const double* lengths, const double* p1, const int* d1,
+                         int g1, const double* p2, const int* d2, int g2, double* grad_cov) {
+  auto c = MakeCovariance(kernel, dim, alpha, lengths);
+  c->GradCovariance(p1, d1, g1, p2, d2, g2, grad_cov);
+}
+
+// ---- linear algebra (gpp_linear_algebra.cpp:109-208) ----
+int ref_cholesky(int n, double* a) { return ComputeCholeskyFactorL(n, a); }
+void ref_trsv(const double* a, int trans, int n, int lda, double* x) {
+  TriangularMatrixVectorSolve(a, trans ? 'T' : 'N', n, lda, x);
+}
+void ref_potrs(const double* a, int n, int nrhs, double* x) { CholeskyFactorLMatrixMatrixSolve(a, n, nrhs, x); }
+
+// ---- GP (gpp_math.cpp:553-573) ----
+void* ref_gp_create(int kernel, double alpha, const double* lengths, const double* X, const double* y,
+                    const double* noise, const int* derivs, int g, int dim, int N, int* leading_minor) {
+  *leading_minor = 0;
+  auto c = MakeCovariance(kernel, dim, alpha, lengths);
+  try {
+    return new GaussianProcess(*c, X, y, noise, derivs, g, dim, N);
+  } catch (const SingularMatrixException& e) {
+    *leading_minor = e.leading_minor_index();
+    return nullptr;
+  }
+}
+
+void ref_gp_destroy(void* h) { delete static_cast<GaussianProcess*>(h); }
+
+void ref_gp_get_state(void* h, double* K_chol, double* K_inv_y, double* mean) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  if (K_chol) std::copy(gp->K_chol_.begin(), gp->K_chol_.end(), K_chol);
+  if (K_inv_y) std::copy(gp->K_inv_y_.begin(), gp->K_inv_y_.end(), K_inv_y);
+  if (mean) *mean = gp->mean_;
+}
+
+// Posterior queries at `num` points carrying the derivative rows `derivs_s[g_s]`
+// (gpp_math.cpp:662,721,924,1366,1466; Python boundary gpp_python_gaussian_process.cpp:64-236).
+// Any output pointer may be NULL.  Returns the leading-minor index if chol(var) fails, else 0.
+int ref_gp_posterior(void* h, const double* pts, int num, const int* derivs_s, int g_s, double* mean, double* grad_mean,
+                     double* var, double* chol_var, double* grad_var, double* grad_chol) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  const int Q = num * (1 + g_s);
+  const bool need_grad = (grad_mean || grad_var || grad_chol);
+  GaussianProcess::StateType st(*gp, pts, num, derivs_s, g_s, need_grad ? num : 0);
+  if (mean) gp->ComputeMeanOfPoints(st, mean);
+  if (grad_mean) gp->ComputeGradMeanOfPoints(st, grad_mean);
+  std::vector<double> v(static_cast<size_t>(Q) * Q);
+  gp->ComputeVarianceOfPoints(&st, derivs_s, g_s, v.data());
+  if (var) std::copy(v.begin(), v.end(), var);
+  if (grad_var) gp->ComputeGradVarianceOfPoints(&st, grad_var);
+  if (chol_var || grad_chol) {
+    int lm = ComputeCholeskyFactorL(Q, v.data());
+    if (lm != 0) return lm;
+    if (chol_var) std::copy(v.begin(), v.end(), chol_var);
+    if (grad_chol) gp->ComputeGradCholeskyVarianceOfPoints(&st, v.data(), grad_chol);
+  }
+  return 0;
+}
+
+void ref_gp_mean_additional(void* h, const double* pts, int num, double* mean) {
+  static_cast<GaussianProcess*>(h)->ComputeMeanOfAdditionalPoints(pts, num, nullptr, 0, mean);
+}
+
+// ---- q-EI (gpp_math.cpp:1991-2126) with table-fed normals ----
+// table holds (q+p) normals per MC iteration, iteration-major.  grad may be NULL.
+double ref_ei(void* h, const double* Xq, const double* Xp, int q, int p, int num_mc, double best_so_far,
+              const double* table, int table_len, double* grad) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  std::vector<double> tab(table, table + table_len);
+  NormalRNGSimulator rng(tab);
+  ExpectedImprovementEvaluator ev(*gp, num_mc, best_so_far);
+  ExpectedImprovementEvaluator::StateType st(ev, Xq, Xp, q, p, grad != nullptr, &rng);
+  double v = ev.ComputeExpectedImprovement(&st);
+  if (grad) ev.ComputeGradExpectedImprovement(&st, grad);
+  return v;
+}
+
+// ---- q-KG / d-KG (gpp_knowledge_gradient_optimization.cpp:69-227) with table-fed normals ----
+// table holds (q+p)(1+g) normals per EVEN iteration (odd iterations are antithetic).
+// gd = 8 inner GradientDescentParameters; inner_bounds[2*(dim-num_fidelity)].
+// best_points (may be NULL) receives the per-sample minimisers x*_i [num_mc][dim].
+double ref_kg(void* h, int num_fidelity, const double* gd, const double* inner_bounds, const double* discrete_pts,
+              int num_pts, const double* Xq, const double* Xp, int q, int p, int num_mc, double best_so_far,
+              const double* table, int table_len, double* grad, double* best_points) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  std::vector<double> tab(table, table + table_len);
+  NormalRNGSimulator rng(tab);
+  TensorProductDomain dom = MakeDomain(inner_bounds, gp->dim() - num_fidelity);
+  GradientDescentParameters inner = MakeGD(gd);
+  KnowledgeGradientEvaluator<TensorProductDomain> ev(*gp, num_fidelity, discrete_pts, num_pts, num_mc, dom, inner,
+                                                     best_so_far);
+  std::vector<int> derivs(gp->derivatives());
+  KnowledgeGradientEvaluator<TensorProductDomain>::StateType st(ev, Xq, Xp, q, p, num_mc, derivs.data(),
+                                                                gp->num_derivatives(), grad != nullptr, &rng);
+  double v;
+  if (grad) {
+    v = ev.ComputeGradKnowledgeGradient(&st, grad);
+  } else {
+    v = ev.ComputeKnowledgeGradient(&st);
+  }
+  if (best_points) std::copy(st.best_point.begin(), st.best_point.end(), best_points);
+  return v;
+}
+
+// ---- the reference's own parallel path, for CPU baselines ----
+// EvaluateKGAtPointList (NullOptimizer + OpenMP static schedule), one NormalRNG per thread seeded seed+t.
+void ref_evaluate_kg_at_point_list(void* h, int num_fidelity, const double* gd, const double* bounds,
+                                   const double* inner_bounds, const double* discrete_pts, int num_pts,
+                                   const double* candidates, const double* Xp, int num_candidates, int q, int p,
+                                   int num_mc, double best_so_far, int num_threads, unsigned seed, double* values,
+                                   double* best_point) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  TensorProductDomain dom = MakeDomain(bounds, gp->dim());
+  TensorProductDomain inner_dom = MakeDomain(inner_bounds, gp->dim() - num_fidelity);
+  GradientDescentParameters inner = MakeGD(gd);
+  std::vector<NormalRNG> rngs(num_threads);
+  for (int t = 0; t < num_threads; ++t) rngs[t].SetExplicitSeed(seed + t);
+  ThreadSchedule sched(num_threads, omp_sched_static);
+  bool found = false;
+  std::vector<double> bp(static_cast<size_t>(q) * gp->dim());
+  EvaluateKGAtPointList(*gp, num_fidelity, inner, dom, inner_dom, sched, candidates, Xp, discrete_pts,
+                        num_candidates, q, p, num_pts, best_so_far, num_mc, &found, rngs.data(), values, bp.data());
+  if (best_point) std::copy(bp.begin(), bp.end(), best_point);
+}
+
+// Value AND gradient for a list of candidates, OpenMP over candidates (the work one outer-GD step does).
+void ref_kg_grad_at_point_list(void* h, int num_fidelity, const double* gd, const double* inner_bounds,
+                               const double* discrete_pts, int num_pts, const double* candidates, const double* Xp,
+                               int num_candidates, int q, int p, int num_mc, double best_so_far, int num_threads,
+                               unsigned seed, double* values, double* grads) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  const int dim = gp->dim();
+  TensorProductDomain inner_dom = MakeDomain(inner_bounds, dim - num_fidelity);
+  GradientDescentParameters inner = MakeGD(gd);
+  KnowledgeGradientEvaluator<TensorProductDomain> ev(*gp, num_fidelity, discrete_pts, num_pts, num_mc, inner_dom,
+                                                     inner, best_so_far);
+  std::vector<int> derivs(gp->derivatives());
+#pragma omp parallel num_threads(num_threads)
+  {
+    NormalRNG rng(seed + omp_get_thread_num());
+#pragma omp for schedule(static)
+    for (int c = 0; c < num_candidates; ++c) {
+      KnowledgeGradientEvaluator<TensorProductDomain>::StateType st(
+          ev, candidates + static_cast<size_t>(c) * q * dim, Xp, q, p, num_mc, derivs.data(), gp->num_derivatives(),
+          true, &rng);
+      values[c] = ev.ComputeGradKnowledgeGradient(&st, grads + static_cast<size_t>(c) * q * dim);
+    }
+  }
+}
+
+void ref_evaluate_ei_at_point_list(void* h, const double* candidates, const double* Xp, int num_candidates, int q,
+                                   int p, int num_mc, double best_so_far, int num_threads, unsigned seed,
+                                   double* values) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  std::vector<NormalRNG> rngs(num_threads);
+  for (int t = 0; t < num_threads; ++t) rngs[t].SetExplicitSeed(seed + t);
+  ThreadSchedule sched(num_threads, omp_sched_static);
+  bool found = false;
+  std::vector<double> bp(static_cast<size_t>(q) * gp->dim());
+  EvaluateEIAtPointList(*gp, sched, candidates, Xp, num_candidates, q, p, best_so_far, num_mc, &found, rngs.data(),
+                        values, bp.data());
+}
+
+void ref_ei_grad_at_point_list(void* h, const double* candidates, const double* Xp, int num_candidates, int q, int p,
+                               int num_mc, double best_so_far, int num_threads, unsigned seed, double* values,
+                               double* grads) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  const int dim = gp->dim();
+  ExpectedImprovementEvaluator ev(*gp, num_mc, best_so_far);
+#pragma omp parallel num_threads(num_threads)
+  {
+    NormalRNG rng(seed + omp_get_thread_num());
+#pragma omp for schedule(static)
+    for (int c = 0; c < num_candidates; ++c) {
+      ExpectedImprovementEvaluator::StateType st(ev, candidates + static_cast<size_t>(c) * q * dim, Xp, q, p, true,
+                                                 &rng);
+      values[c] = ev.ComputeExpectedImprovement(&st);
+      ev.ComputeGradExpectedImprovement(&st, grads + static_cast<size_t>(c) * q * dim);
+    }
+  }
+}
+
+// LimitUpdate (gpp_domain.cpp:64-104) for pinning the restatement.
+void ref_limit_update(const double* bounds, int dim, double max_relative_change, const double* current_point,
+                      double* update) {
+  TensorProductDomain dom = MakeDomain(bounds, dim);
+  dom.LimitUpdate(max_relative_change, current_point, update);
+}
+
+int ref_max_threads() { return omp_get_max_threads(); }
+
+}  // extern "C"

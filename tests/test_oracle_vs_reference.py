@@ -1,0 +1,164 @@
+"""Pins the plain-C oracle (oracle/moe_oracle.c) against the UNMODIFIED reference compiled into
+oracle/_ref/libmoe_ref.so.  Skipped where the reference .so is absent (it is built from /root/reference by
+`make -C oracle ref`, in the build container, and travels with the snapshot)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from synth import DISCRETE_ONLY_GD, EXAMPLE_INNER_GD, make_problem, unit_bounds
+
+pytestmark = pytest.mark.skipif(not orc.have_reference(), reason="oracle/_ref/libmoe_ref.so not built")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return orc.load_oracle(), orc.load_reference()
+
+
+def _gp_pair(libs, kernel, prob):
+    out = []
+    for b in libs:
+        gp, lm = b.gp(kernel, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+        assert lm == 0
+        out.append(gp)
+    return out
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("g1,g2", [((), ()), ((0, 2), ()), ((), (1,)), ((0, 1, 2), (0, 2)), ((1,), (1,))])
+def test_covariance_blocks(libs, kernel, g1, g2):
+    rng = np.random.default_rng(5)
+    o, r = libs
+    for _ in range(5):
+        p1, p2 = rng.uniform(size=3), rng.uniform(size=3)
+        ls = rng.uniform(0.5, 2.5, size=3)
+        for grad in (False, True):
+            a = o.covariance(kernel, 2.80723, ls, p1, g1, p2, g2, grad=grad)
+            b = r.covariance(kernel, 2.80723, ls, p1, g1, p2, g2, grad=grad)
+            np.testing.assert_allclose(a, b, rtol=1e-14, atol=1e-15)
+    # coincident points (Matern grad of the Hessian block is zeroed at r = 0)
+    p = rng.uniform(size=3)
+    a = o.covariance(kernel, 1.3, [1.0, 0.7, 2.0], p, g1, p, g2, grad=True)
+    b = r.covariance(kernel, 1.3, [1.0, 0.7, 2.0], p, g1, p, g2, grad=True)
+    np.testing.assert_allclose(a, b, rtol=1e-14, atol=1e-15)
+
+
+def test_cholesky_and_solve(libs):
+    o, r = libs
+    rng = np.random.default_rng(34187)
+    for n in (1, 5, 11, 20, 63):
+        A = rng.standard_normal((n, n))
+        A = A @ A.T + n * np.eye(n)
+        rc_o, Lo = o.cholesky(A)
+        rc_r, Lr = r.cholesky(A)
+        assert rc_o == rc_r == 0
+        np.testing.assert_allclose(np.tril(Lo), np.tril(Lr), rtol=1e-13, atol=1e-14)  # FMA contraction differs
+        B = rng.standard_normal((n, 3))
+        np.testing.assert_allclose(o.potrs(Lo, B), r.potrs(Lr, B), rtol=1e-11, atol=1e-13)
+    # exactly singular (integer arithmetic stays exact): pivot 3 is 0 -> both return 3
+    L0 = np.array([[2.0, 0, 0, 0], [1, 3, 0, 0], [4, 1, 0, 0], [2, 2, 1, 5]])
+    A = L0 @ L0.T
+    assert o.cholesky(A)[0] == r.cholesky(A)[0] == 3
+    # known-answer cases from the reference's own tests (gpp_linear_algebra_test.cpp:238-262, 358-368)
+    W = np.array([[4.0, 12, -16], [12, 37, -43], [-16, -43, 98]])
+    for b in (o, r):
+        rc, L = b.cholesky(W)
+        assert rc == 0
+        np.testing.assert_array_equal(np.tril(L), np.array([[2.0, 0, 0], [6, 1, 0], [-8, 5, 3]]))
+
+
+def test_limit_update(libs):
+    o, r = libs
+    rng = np.random.default_rng(3)
+    b = np.array([0.0, 1.0, -2.0, 3.0, 0.5, 0.6])
+    for _ in range(200):
+        x = np.array([rng.uniform(0, 1), rng.uniform(-2, 3), rng.uniform(0.5, 0.6)])
+        u = rng.standard_normal(3) * rng.choice([1e-3, 0.1, 1.0, 10.0])
+        np.testing.assert_allclose(o.limit_update(b, 0.3, x, u), r.limit_update(b, 0.3, x, u), rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("g_idx", [(), (0, 2)])
+def test_gp_fit_and_posterior(libs, kernel, g_idx):
+    prob = make_problem(24, 3, g_idx=g_idx, seed=11)
+    go, gr = _gp_pair(libs, kernel, prob)
+    Ko, bo, mo = go.state()
+    Kr, br, mr = gr.state()
+    np.testing.assert_allclose(np.tril(Ko), np.tril(Kr), rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(bo, br, rtol=1e-10, atol=1e-12)
+    assert mo == mr
+    pts = np.random.default_rng(2).uniform(size=(4, 3))
+    want = ("mean", "grad_mean", "var", "chol_var", "grad_var", "grad_chol")
+    for ds in ((), g_idx):
+        po = go.posterior(pts, ds, want)
+        pr = gr.posterior(pts, ds, want)
+        assert po["rc"] == pr["rc"] == 0
+        Q = 4 * (1 + len(ds))
+        for k in want:
+            a, b = po[k], pr[k]
+            if k in ("var", "chol_var"):
+                # only the lower triangle is defined by the reference
+                a = np.tril(a.reshape(Q, Q).T)
+                b = np.tril(b.reshape(Q, Q).T)
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11, err_msg=k)
+
+
+def test_gp_singular(libs):
+    prob = make_problem(10, 2, seed=1)
+    prob["X"][1] = prob["X"][0]  # K[:2,:2] = [[1,1],[1,1]] -> second pivot is exactly 0
+    prob["noise"][:] = 0.0
+    res = [b.gp(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"]) for b in libs]
+    assert res[0][0] is None and res[1][0] is None
+    assert res[0][1] == res[1][1] == 2
+
+
+@pytest.mark.parametrize("q,p", [(1, 0), (1, 5), (3, 2), (10, 0)])
+def test_ei_table_fed(libs, q, p):
+    prob = make_problem(30, 3, seed=4)
+    go, gr = _gp_pair(libs, 0, prob)
+    rng = np.random.default_rng(3141)
+    Xq, Xp = rng.uniform(size=(q, 3)), rng.uniform(size=(p, 3))
+    mc = 64
+    table = rng.standard_normal(mc * (q + p))
+    best = float(prob["y"].min()) + 0.3
+    vo, gradо = go.ei(Xq, Xp, mc, best, table, grad=True)
+    vr, gradr = gr.ei(Xq, Xp, mc, best, table, grad=True)
+    assert vr > 0
+    np.testing.assert_allclose(vo, vr, rtol=1e-11)
+    np.testing.assert_allclose(gradо, gradr, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("gd", [DISCRETE_ONLY_GD, EXAMPLE_INNER_GD, [1, 20, 3, 3, 0.7, 1.0, 0.2, 1e-7]])
+@pytest.mark.parametrize("q,p,g_idx", [(1, 0, ()), (2, 0, ()), (1, 2, ()), (3, 2, ()), (2, 1, (0, 1))])
+def test_kg_table_fed(libs, gd, q, p, g_idx):
+    prob = make_problem(16, 3, g_idx=g_idx, seed=9, noise=0.1)
+    go, gr = _gp_pair(libs, 0, prob)
+    rng = np.random.default_rng(27)
+    Xq, Xp = rng.uniform(size=(q, 3)), rng.uniform(size=(p, 3))
+    disc = rng.uniform(size=(5, 3))
+    mc = 16
+    Q = (q + p) * (1 + len(g_idx))
+    table = rng.standard_normal((mc // 2) * Q)
+    best = float(go.mean_additional(disc).min())
+    vo, gradо, bpo = go.kg(Xq, Xp, mc, best, table, gd, unit_bounds(3), disc, grad=True, want_best_points=True)
+    vr, gradr, bpr = gr.kg(Xq, Xp, mc, best, table, gd, unit_bounds(3), disc, grad=True, want_best_points=True)
+    np.testing.assert_allclose(bpo, bpr, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(vo, vr, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gradо, gradr, rtol=1e-6, atol=1e-9)
+    # value-only entry point agrees with the value returned by the gradient entry point
+    np.testing.assert_allclose(gr.kg(Xq, Xp, mc, best, table, gd, unit_bounds(3), disc), vr, rtol=1e-12)
+    np.testing.assert_allclose(go.kg(Xq, Xp, mc, best, table, gd, unit_bounds(3), disc), vo, rtol=1e-12)
+
+
+def test_kg_fidelity_dim(libs):
+    prob = make_problem(14, 3, seed=21, noise=0.1)
+    go, gr = _gp_pair(libs, 1, prob)
+    rng = np.random.default_rng(8)
+    Xq = rng.uniform(size=(2, 3))
+    disc = rng.uniform(size=(6, 2))
+    table = rng.standard_normal(8 * 2)
+    args = (Xq, None, 16, 0.1, table, EXAMPLE_INNER_GD, unit_bounds(2), disc)
+    vo, go_ = go.kg(*args, num_fidelity=1, grad=True)
+    vr, gr_ = gr.kg(*args, num_fidelity=1, grad=True)
+    np.testing.assert_allclose(vo, vr, rtol=1e-9)
+    np.testing.assert_allclose(go_, gr_, rtol=1e-6, atol=1e-9)
