@@ -1,0 +1,268 @@
+"""ctypes binding of the C ABI declared in include/cmoe_b200.h.
+
+This is the thinnest possible host layer: numpy arrays in, numpy arrays out, every call goes straight to
+libcornell_moe_b200.so (hand-written sm_100a kernels).  If the library is missing or no CUDA device is visible the
+calls raise — there is deliberately no fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcornell_moe_b200.so")
+
+OK, ERR_SINGULAR, ERR_BOUNDS, ERR_INVALID_VALUE, ERR_RUNTIME, ERR_NO_DEVICE = range(6)
+SQUARE_EXPONENTIAL, MATERN_NU_2P5 = 0, 1
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+class CmoeError(RuntimeError):
+    """Base error (reference: OptimalLearningException)."""
+
+    def __init__(self, code, msg, info=0):
+        super().__init__(msg)
+        self.code = code
+        self.info = info
+
+
+class SingularMatrixError(CmoeError):
+    """reference: SingularMatrixException; ``info`` = leading minor index."""
+
+
+class BoundsError(CmoeError):
+    """reference: BoundsException."""
+
+
+class InvalidValueError(CmoeError):
+    """reference: InvalidValueException."""
+
+
+class NoDeviceError(CmoeError):
+    """No CUDA device: the product has no CPU path."""
+
+
+_ERRS = {ERR_SINGULAR: SingularMatrixError, ERR_BOUNDS: BoundsError, ERR_INVALID_VALUE: InvalidValueError,
+         ERR_RUNTIME: CmoeError, ERR_NO_DEVICE: NoDeviceError}
+
+
+class GDParams(ctypes.Structure):
+    """GradientDescentParameters (gpp_optimizer_parameters.hpp:81)."""
+    _fields_ = [("num_multistarts", ctypes.c_int), ("max_num_steps", ctypes.c_int), ("max_num_restarts", ctypes.c_int),
+                ("num_steps_averaged", ctypes.c_int), ("gamma", ctypes.c_double), ("pre_mult", ctypes.c_double),
+                ("max_relative_change", ctypes.c_double), ("tolerance", ctypes.c_double)]
+
+    @classmethod
+    def from_seq(cls, p):
+        if isinstance(p, cls):
+            return p
+        return cls(int(p[0]), int(p[1]), int(p[2]), int(p[3]), float(p[4]), float(p[5]), float(p[6]), float(p[7]))
+
+
+class KGStats(ctypes.Structure):
+    _fields_ = [("mc_samples", ctypes.c_uint64), ("posterior_evals", ctypes.c_uint64),
+                ("line_search_steps", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libcornell_moe_b200.so (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `make -C cornell-moe_b200` (or __graft_entry__.build()); "
+                "there is no fallback implementation")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.cmoe_last_error.restype = ctypes.c_char_p
+        _lib.cmoe_version.restype = ctypes.c_char_p
+    return _lib
+
+
+def _check(rc, info=0):
+    if rc != OK:
+        msg = lib().cmoe_last_error().decode()
+        raise _ERRS.get(rc, CmoeError)(rc, msg, info)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.zeros(0, dtype=np.int32) if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def device_count():
+    return lib().cmoe_device_count()
+
+
+def version():
+    return lib().cmoe_version().decode()
+
+
+def cholesky(A, device=0):
+    """Lower Cholesky of a symmetric [n, n] array through the device path; returns L as [row, col] array."""
+    A = np.array(A, dtype=np.float64)
+    n = A.shape[0]
+    buf = np.ascontiguousarray(A.T)
+    info = ctypes.c_int(0)
+    rc = lib().cmoe_cholesky(n, _d(buf), int(device), ctypes.byref(info))
+    _check(rc, info.value)
+    return buf.T.copy()
+
+
+def potrs(L, B, device=0):
+    Lc = np.ascontiguousarray(np.array(L, dtype=np.float64).T)
+    B = np.array(B, dtype=np.float64)
+    B2 = B.reshape(B.shape[0], -1)
+    buf = np.ascontiguousarray(B2.T)
+    _check(lib().cmoe_potrs(Lc.shape[0], B2.shape[1], _d(Lc), _d(buf), int(device)))
+    return buf.T.copy().reshape(B.shape)
+
+
+def philox_normals(seed, first_draw, num_draws, per_draw, device=0):
+    out = np.empty(num_draws * per_draw)
+    _check(lib().cmoe_philox_normals(ctypes.c_uint64(seed), ctypes.c_uint64(first_draw), int(num_draws),
+                                     int(per_draw), _d(out), int(device)))
+    return out.reshape(num_draws, per_draw)
+
+
+class GaussianProcess:
+    """Device-resident GP (reference: optimal_learning::GaussianProcess, gpp_math.hpp:275)."""
+
+    def __init__(self, kernel, alpha, lengths, X, y, noise, derivs=None, device=0):
+        X = _f64(X)
+        self.N, self.dim = X.shape
+        self.derivs = _i32(derivs)
+        self.g = len(self.derivs)
+        self.n = self.N * (1 + self.g)
+        y = _f64(y).ravel()
+        noise = _f64(noise).ravel()
+        lengths = _f64(lengths).ravel()
+        assert y.size == self.n and noise.size == 1 + self.g and lengths.size == self.dim
+        self.kernel = kernel
+        self.device = device
+        h = ctypes.c_void_p()
+        info = ctypes.c_int(0)
+        rc = lib().cmoe_gp_create(int(kernel), ctypes.c_double(alpha), _d(lengths), _d(X), _d(y), _d(noise),
+                                  _i(self.derivs), self.g, self.dim, self.N, int(device), ctypes.byref(h),
+                                  ctypes.byref(info))
+        self.h = None
+        _check(rc, info.value)
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().cmoe_gp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def state(self):
+        K = np.empty(self.n * self.n)
+        kinvy = np.empty(self.n)
+        mean = ctypes.c_double()
+        _check(lib().cmoe_gp_get_state(self.h, _d(K), _d(kinvy), ctypes.byref(mean)))
+        return K.reshape(self.n, self.n).T.copy(), kinvy, mean.value
+
+    def fit_timings_usec(self):
+        t = np.zeros(3)
+        lib().cmoe_gp_fit_timings(self.h, _d(t))
+        return t
+
+    def add_sampled_points(self, pts, vals):
+        pts = _f64(pts).reshape(-1, self.dim)
+        vals = _f64(vals).ravel()
+        info = ctypes.c_int(0)
+        rc = lib().cmoe_gp_add_sampled_points(self.h, _d(pts), _d(vals), pts.shape[0], ctypes.byref(info))
+        _check(rc, info.value)
+        self.N += pts.shape[0]
+        self.n = self.N * (1 + self.g)
+
+    def bench_cov_build(self, repeats=10):
+        t = ctypes.c_double()
+        _check(lib().cmoe_bench_cov_build(self.h, int(repeats), ctypes.byref(t)))
+        return t.value
+
+    def bench_cholesky(self, repeats=3):
+        t = ctypes.c_double()
+        _check(lib().cmoe_bench_cholesky(self.h, int(repeats), ctypes.byref(t)))
+        return t.value
+
+    def posterior(self, sets, derivs_s=None, want=("mean", "var")):
+        """sets: [num_sets, num_pts, dim].  Returns dict of arrays with a leading num_sets axis (reference layouts)."""
+        sets = _f64(sets)
+        if sets.ndim == 2:
+            sets = sets[None]
+        ns, num, _ = sets.shape
+        ds = _i32(derivs_s)
+        Q = num * (1 + len(ds))
+        shapes = {"mean": (ns, Q), "grad_mean": (ns, Q * self.dim), "var": (ns, Q * Q), "chol_var": (ns, Q * Q),
+                  "grad_var": (ns, num * Q * Q * self.dim), "grad_chol": (ns, num * Q * Q * self.dim)}
+        bufs = {k: (np.empty(shapes[k]) if k in want else None) for k in shapes}
+        info = ctypes.c_int(0)
+        rc = lib().cmoe_gp_posterior(self.h, _d(sets), ns, num, _i(ds), len(ds), _d(bufs["mean"]),
+                                     _d(bufs["grad_mean"]), _d(bufs["var"]), _d(bufs["chol_var"]),
+                                     _d(bufs["grad_var"]), _d(bufs["grad_chol"]), ctypes.byref(info))
+        _check(rc, info.value)
+        return {k: v for k, v in bufs.items() if v is not None}
+
+    def ei(self, candidates, Xp, num_mc, best_so_far, seed=0, table=None, grad=False):
+        cand = _f64(candidates)
+        if cand.ndim == 2:
+            cand = cand[None]
+        nc, q, _ = cand.shape
+        Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
+        table = _f64(table).ravel() if table is not None else None
+        if table is not None:
+            assert table.size >= num_mc * (q + Xp.shape[0])
+        ei = np.empty(nc)
+        g = np.empty((nc, q, self.dim)) if grad else None
+        info = ctypes.c_int(0)
+        rc = lib().cmoe_ei_eval(self.h, _d(cand), nc, q, _d(Xp), Xp.shape[0], int(num_mc),
+                                ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(table), _d(ei), _d(g),
+                                ctypes.byref(info))
+        _check(rc, info.value)
+        return (ei, g) if grad else ei
+
+    def kg(self, candidates, Xp, num_mc, best_so_far, inner, inner_bounds, discrete_pts, num_fidelity=0, seed=0,
+           table=None, grad=False, stats=False):
+        cand = _f64(candidates)
+        if cand.ndim == 2:
+            cand = cand[None]
+        nc, q, _ = cand.shape
+        Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
+        table = _f64(table).ravel() if table is not None else None
+        inner = GDParams.from_seq(inner)
+        inner_bounds = _f64(inner_bounds).ravel()
+        disc = _f64(discrete_pts).reshape(-1, self.dim - num_fidelity)
+        kg = np.empty(nc)
+        g = np.empty((nc, q, self.dim)) if grad else None
+        st = KGStats()
+        info = ctypes.c_int(0)
+        rc = lib().cmoe_kg_eval(self.h, int(num_fidelity), ctypes.byref(inner), _d(inner_bounds), _d(disc),
+                                disc.shape[0], _d(cand), nc, q, _d(Xp), Xp.shape[0], int(num_mc),
+                                ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(table), _d(kg), _d(g),
+                                ctypes.byref(st), ctypes.byref(info))
+        _check(rc, info.value)
+        res = [kg]
+        if grad:
+            res.append(g)
+        if stats:
+            res.append({"mc_samples": st.mc_samples, "posterior_evals": st.posterior_evals,
+                        "line_search_steps": st.line_search_steps})
+        return res[0] if len(res) == 1 else tuple(res)

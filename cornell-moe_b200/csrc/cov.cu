@@ -1,0 +1,171 @@
+// Covariance-matrix builders (HBM-write-bound kernels).
+//
+// Replaces (reference, moe/optimal_learning/cpp/):
+//   BuildCovarianceMatrixWithNoiseVariance   gpp_math.cpp:426-455   (lower triangle + noise by observation type)
+//   BuildMixCovarianceMatrix                 gpp_math.cpp:309-335
+//   SquareExponential / MaternNu2p5 ::Covariance   gpp_covariance.cpp:121-164, 339-387
+//
+// Tiling: one CTA per 128x32 block of point pairs in the lower-triangular tile grid; the two point slabs are staged
+// through shared memory once and every thread produces 4 consecutive rows of a column, so each warp store instruction
+// writes 1 KB contiguous (coalesced 32 B per lane).  Only lower-triangular tiles are visited: the algorithmic traffic
+// is 4*n*(n+1) bytes written + 8*N*dim read.
+#include "device_math.cuh"
+#include "internal.cuh"
+
+namespace cmoe {
+
+namespace {
+
+constexpr int TR = 128;  // point rows per tile
+constexpr int TC = 32;   // point cols per tile
+
+// g == 0 fast path: K[i + j*n] for i >= j (tile granularity), noise[0] on the diagonal
+__global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant__ KernelSpec spec,
+                                                           const double* __restrict__ X, int N,
+                                                           const double* __restrict__ noise, double* __restrict__ K) {
+  extern __shared__ double sm[];
+  const int dim = spec.dim;
+  double* Xr = sm;               // [TR][dim]
+  double* Xc = sm + TR * dim;    // [TC][dim]
+  // map linear block -> (tile row, tile col) with tile_row*TR + TR > tile_col*TC (lower triangle incl. diagonal tiles)
+  const int tcols = (N + TC - 1) / TC;
+  const int tr = blockIdx.y, tc = blockIdx.x;
+  if (tc >= tcols) return;
+  const int row0 = tr * TR, col0 = tc * TC;
+  if (col0 > row0 + TR - 1) return;  // tile entirely above the diagonal
+  for (int e = threadIdx.x; e < TR * dim; e += blockDim.x) {
+    const int r = row0 + e / dim;
+    Xr[e] = (r < N) ? X[static_cast<size_t>(r) * dim + e % dim] : 0.0;
+  }
+  for (int e = threadIdx.x; e < TC * dim; e += blockDim.x) {
+    const int c = col0 + e / dim;
+    Xc[e] = (c < N) ? X[static_cast<size_t>(c) * dim + e % dim] : 0.0;
+  }
+  __syncthreads();
+  const int rg = threadIdx.x & 31;  // rows rg*4 .. rg*4+3
+  const int cg = threadIdx.x >> 5;  // cols cg*4 .. cg*4+3
+  const double nz = noise[0];
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = cg * 4 + cc;
+    const int gc = col0 + c;
+    if (gc >= N) continue;
+    double v[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = rg * 4 + rr;
+      // point one = row point, point two = column point (gpp_math.cpp:434-436)
+      const KParts kp = kernel_parts(spec, weighted_sqdist(spec, Xr + r * dim, Xc + c * dim));
+      v[rr] = kp.A;
+      if (row0 + r == gc) v[rr] += nz;
+    }
+    const int gr = row0 + rg * 4;
+    double* dst = K + static_cast<size_t>(gc) * N + gr;
+    if (gr + 3 < N && (N % 2 == 0)) {
+      // 16-byte aligned when N is even (gr is a multiple of 4)
+      reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
+      reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        if (gr + rr < N) dst[rr] = v[rr];
+    }
+  }
+}
+
+// generic path (derivative observations): one thread per point pair, writes the (1+g)x(1+g) block
+__global__ void __launch_bounds__(256) cov_build_generic_kernel(const __grid_constant__ KernelSpec spec,
+                                                                const double* __restrict__ X, int N,
+                                                                const double* __restrict__ noise,
+                                                                double* __restrict__ K) {
+  const int dim = spec.dim, b = 1 + spec.g, n = N * b;
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);  // row point (fast)
+  const int j = blockIdx.y * 8 + (threadIdx.x >> 5);   // col point
+  if (i >= N || j >= N || i < j) return;
+  const double* p1 = X + static_cast<size_t>(i) * dim;
+  const double* p2 = X + static_cast<size_t>(j) * dim;
+  const KParts kp = kernel_parts(spec, weighted_sqdist(spec, p1, p2));
+  for (int cn = 0; cn < b; ++cn) {
+    const int a2 = cn ? spec.derivs[cn - 1] : -1;
+    for (int m = 0; m < b; ++m) {
+      const int a1 = m ? spec.derivs[m - 1] : -1;
+      const int row = i * b + m, col = j * b + cn;
+      if (row >= col) {
+        double v = cov_entry(spec, kp, p1, p2, a1, a2);
+        if (row == col) v += noise[m];
+        K[static_cast<size_t>(col) * n + row] = v;
+      }
+    }
+  }
+}
+
+// K(X, P): thread per (sampled point i, P point j), writes the (1+g)x(1+gs) block; rows fastest.
+__global__ void __launch_bounds__(256) mix_cov_kernel(const __grid_constant__ KernelSpec spec,
+                                                      const double* __restrict__ X, int N,
+                                                      const double* __restrict__ P, int num,
+                                                      const int* __restrict__ dPs, int gs,
+                                                      double* __restrict__ out) {
+  const int dim = spec.dim, b = 1 + spec.g, bs = 1 + gs, n = N * b;
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int j = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (i >= N || j >= num) return;
+  const double* p1 = X + static_cast<size_t>(i) * dim;
+  const double* p2 = P + static_cast<size_t>(j) * dim;
+  const KParts kp = kernel_parts(spec, weighted_sqdist(spec, p1, p2));
+  for (int cn = 0; cn < bs; ++cn) {
+    const int a2 = cn ? dPs[cn - 1] : -1;
+    for (int m = 0; m < b; ++m) {
+      const int a1 = m ? spec.derivs[m - 1] : -1;
+      out[static_cast<size_t>(j * bs + cn) * n + i * b + m] = cov_entry(spec, kp, p1, p2, a1, a2);
+    }
+  }
+}
+
+__global__ void philox_table_kernel(uint64_t seed, uint64_t first_draw, int num_draws, int per_draw,
+                                    double* __restrict__ out) {
+  const int pairs = (per_draw + 1) / 2;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(num_draws) * pairs) return;
+  const int i = static_cast<int>(idx / pairs), k = static_cast<int>(idx % pairs);
+  double a, b;
+  philox_normal_pair(seed, first_draw + i, k, a, b);
+  out[static_cast<size_t>(i) * per_draw + 2 * k] = a;
+  if (2 * k + 1 < per_draw) out[static_cast<size_t>(i) * per_draw + 2 * k + 1] = b;
+}
+
+}  // namespace
+
+void build_covariance(const KernelSpec& spec, const double* X, int N, const double* noise, double* K,
+                      cudaStream_t s) {
+  if (spec.g == 0) {
+    dim3 grid((N + TC - 1) / TC, (N + TR - 1) / TR);
+    const size_t smem = static_cast<size_t>(TR + TC) * spec.dim * sizeof(double);
+    cov_build_g0_kernel<<<grid, 256, smem, s>>>(spec, X, N, noise, K);
+  } else {
+    dim3 grid((N + 31) / 32, (N + 7) / 8);
+    cov_build_generic_kernel<<<grid, 256, 0, s>>>(spec, X, N, noise, K);
+  }
+  count_launch();
+  CMOE_CUDA(cudaGetLastError());
+}
+
+void build_mix_covariance(const KernelSpec& spec, const double* X, int N, const double* P, int num, const int* dPs,
+                          int gs, double* out, cudaStream_t s) {
+  if (num == 0 || N == 0) return;
+  dim3 grid((N + 31) / 32, (num + 7) / 8);
+  mix_cov_kernel<<<grid, 256, 0, s>>>(spec, X, N, P, num, dPs, gs, out);
+  count_launch();
+  CMOE_CUDA(cudaGetLastError());
+}
+
+void philox_normals_device(uint64_t seed, uint64_t first_draw, int num_draws, int per_draw, double* out,
+                           cudaStream_t s) {
+  const size_t total = static_cast<size_t>(num_draws) * ((per_draw + 1) / 2);
+  if (!total) return;
+  philox_table_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(seed, first_draw, num_draws, per_draw,
+                                                                               out);
+  count_launch();
+  CMOE_CUDA(cudaGetLastError());
+}
+
+}  // namespace cmoe

@@ -1,0 +1,295 @@
+// GaussianProcess handle: covariance build -> blocked Cholesky -> K^-1 (y - mean), all on the device.
+// Replaces GaussianProcess::GaussianProcess / RecomputeDerivedVariables / AddPointsToGP
+// (reference gpp_math.cpp:553-573, 481-511, 1699-1718).
+#include <algorithm>
+#include <cmath>
+
+#include "device_math.cuh"
+#include "internal.cuh"
+
+namespace cmoe {
+
+namespace {
+thread_local std::string g_last_error;
+
+__global__ void center_values_kernel(const double* __restrict__ y, int N, int b, double mean,
+                                     double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N * b) return;
+  out[r] = y[r] - ((r % b == 0) ? mean : 0.0);  // only function-value rows carry the constant prior mean
+}
+
+__global__ void scale_points_kernel(const __grid_constant__ KernelSpec spec, const double* __restrict__ X, int N,
+                                    double* __restrict__ Xs) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * spec.dim) return;
+  Xs[e] = X[e] * spec.inv_len[e % spec.dim];
+}
+}  // namespace
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+void require_device(int device) {
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    throw Error(CMOE_ERR_NO_DEVICE,
+                "cornell-moe_b200: no CUDA device visible; this library has no CPU compute path");
+  }
+  if (device < 0 || device >= count) throw Error(CMOE_ERR_BOUNDS, "device ordinal out of range");
+  CMOE_CUDA(cudaSetDevice(device));
+}
+
+void fit_gp(cmoe_gp* gp, bool mean_change) {
+  const KernelSpec& spec = gp->spec;
+  const int N = gp->N, b = 1 + spec.g, n = N * b;
+  gp->n = n;
+  cudaStream_t s = gp->stream;
+  gp->dX.upload(gp->hX.data(), gp->hX.size(), s);
+  gp->dy.upload(gp->hy.data(), gp->hy.size(), s);
+  gp->dnoise.upload(gp->hnoise.data(), gp->hnoise.size(), s);
+  gp->dK.ensure(static_cast<size_t>(n) * n);
+  gp->dKinvY.ensure(n);
+  gp->dXs.ensure(static_cast<size_t>(N) * spec.dim);
+  if (gp->dFlag.count == 0) gp->dFlag.alloc(1);
+
+  EventTimer t0, t1, t2;
+  t0.start(s);
+  if (spec.g > 0) CMOE_CUDA(cudaMemsetAsync(gp->dK.p, 0, static_cast<size_t>(n) * n * sizeof(double), s));
+  build_covariance(spec, gp->dX.p, N, gp->dnoise.p, gp->dK.p, s);
+  t0.stop(s);
+  t1.start(s);
+  potrf_lower(gp->dK.p, n, gp->dFlag.p, s);
+  t1.stop(s);
+  int flag = 0;
+  CMOE_CUDA(cudaMemcpyAsync(&flag, gp->dFlag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaStreamSynchronize(s));
+  if (flag != 0) {
+    throw Error(CMOE_ERR_SINGULAR,
+                "Covariance matrix (K) singular. Check for duplicate points_sampled (with 0 noise) and/or extreme "
+                "hyperparameter values.",
+                flag);
+  }
+  if (mean_change) {
+    // mean_ = average of the function values (gpp_math.cpp:498-504); same summation order as the reference
+    double m = 0.0;
+    for (int i = 0; i < N; ++i) m += gp->hy[static_cast<size_t>(i) * b];
+    gp->mean = m / N;
+  }
+  t2.start(s);
+  center_values_kernel<<<(n + 255) / 256, 256, 0, s>>>(gp->dy.p, N, b, gp->mean, gp->dKinvY.p);
+  count_launch();
+  potrs_lower(gp->dK.p, n, gp->dKinvY.p, n, 1, s);
+  scale_points_kernel<<<(N * spec.dim + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, N, gp->dXs.p);
+  count_launch();
+  t2.stop(s);
+  CMOE_CUDA(cudaGetLastError());
+  CMOE_CUDA(cudaStreamSynchronize(s));
+  gp->fit_usec[0] = t0.ms() * 1e3;
+  gp->fit_usec[1] = t1.ms() * 1e3;
+  gp->fit_usec[2] = t2.ms() * 1e3;
+}
+
+}  // namespace cmoe
+
+cmoe_gp::~cmoe_gp() {
+  if (stream) {
+    cudaSetDevice(device);
+    cudaStreamDestroy(stream);
+  }
+}
+
+using namespace cmoe;  // NOLINT
+
+extern "C" {
+
+const char* cmoe_last_error(void) { return g_last_error.c_str(); }
+const char* cmoe_version(void) { return "cornell-moe_b200 0.1 (sm_100a)"; }
+
+int cmoe_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+int cmoe_gp_create(int kernel, double alpha, const double* lengths, const double* points_sampled,
+                   const double* points_sampled_value, const double* noise_variance, const int* derivatives,
+                   int num_derivatives, int dim, int num_sampled, int device, cmoe_gp** gp_out, int* info) {
+  if (gp_out) *gp_out = nullptr;
+  return guarded(info, [&] {
+    CMOE_REQUIRE(gp_out != nullptr, CMOE_ERR_INVALID_VALUE, "gp_out is NULL");
+    CMOE_REQUIRE(kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL || kernel == CMOE_KERNEL_MATERN_NU_2P5,
+                 CMOE_ERR_INVALID_VALUE, "unknown covariance kernel id");
+    CMOE_REQUIRE(dim >= 1 && dim <= CMOE_MAX_DIM, CMOE_ERR_BOUNDS, "dim must be in [1, CMOE_MAX_DIM]");
+    CMOE_REQUIRE(num_sampled >= 1, CMOE_ERR_BOUNDS, "num_sampled must be >= 1");
+    CMOE_REQUIRE(num_derivatives >= 0 && num_derivatives <= dim, CMOE_ERR_BOUNDS, "num_derivatives out of range");
+    // hyperparameter validation as InitializeCovariance, gpp_covariance.cpp:74-98
+    CMOE_REQUIRE(alpha > 0.0, CMOE_ERR_BOUNDS, "Invalid hyperparameter (alpha).");
+    for (int k = 0; k < dim; ++k) CMOE_REQUIRE(lengths[k] > 0.0, CMOE_ERR_BOUNDS, "Invalid hyperparameter (length).");
+    for (int k = 0; k < num_derivatives; ++k)
+      CMOE_REQUIRE(derivatives[k] >= 0 && derivatives[k] < dim, CMOE_ERR_BOUNDS, "derivative index out of range");
+    require_device(device);
+    std::unique_ptr<cmoe_gp> gp(new cmoe_gp());
+    gp->device = device;
+    KernelSpec& s = gp->spec;
+    s.kernel = kernel;
+    s.dim = dim;
+    s.g = num_derivatives;
+    s.alpha = alpha;
+    for (int k = 0; k < CMOE_MAX_DIM; ++k) {
+      s.lsq[k] = 1.0;
+      s.inv_len[k] = 0.0;
+      s.derivs[k] = 0;
+    }
+    for (int k = 0; k < dim; ++k) {
+      s.lsq[k] = lengths[k] * lengths[k];
+      s.inv_len[k] = 1.0 / lengths[k];
+    }
+    for (int k = 0; k < num_derivatives; ++k) s.derivs[k] = derivatives[k];
+    gp->N = num_sampled;
+    gp->hX.assign(points_sampled, points_sampled + static_cast<size_t>(num_sampled) * dim);
+    gp->hy.assign(points_sampled_value,
+                  points_sampled_value + static_cast<size_t>(num_sampled) * (1 + num_derivatives));
+    gp->hnoise.assign(noise_variance, noise_variance + 1 + num_derivatives);
+    CMOE_CUDA(cudaStreamCreateWithFlags(&gp->stream, cudaStreamNonBlocking));
+    fit_gp(gp.get(), true);
+    *gp_out = gp.release();
+  });
+}
+
+void cmoe_gp_destroy(cmoe_gp* gp) {
+  if (!gp) return;
+  cudaSetDevice(gp->device);
+  delete gp;
+}
+
+int cmoe_gp_dim(const cmoe_gp* gp) { return gp->spec.dim; }
+int cmoe_gp_num_sampled(const cmoe_gp* gp) { return gp->N; }
+int cmoe_gp_num_derivatives(const cmoe_gp* gp) { return gp->spec.g; }
+
+int cmoe_gp_get_state(const cmoe_gp* gp, double* K_chol, double* K_inv_y, double* mean) {
+  return guarded(nullptr, [&] {
+    require_device(gp->device);
+    const int n = gp->n;
+    if (K_chol) {
+      gp->dK.download(K_chol, static_cast<size_t>(n) * n, gp->stream);
+      CMOE_CUDA(cudaStreamSynchronize(gp->stream));
+      for (int j = 1; j < n; ++j)  // strictly-upper part is undefined on the device (never written): report zeros
+        std::fill(K_chol + static_cast<size_t>(j) * n, K_chol + static_cast<size_t>(j) * n + j, 0.0);
+    }
+    if (K_inv_y) {
+      gp->dKinvY.download(K_inv_y, n, gp->stream);
+      CMOE_CUDA(cudaStreamSynchronize(gp->stream));
+    }
+    if (mean) *mean = gp->mean;
+  });
+}
+
+int cmoe_gp_add_sampled_points(cmoe_gp* gp, const double* new_points, const double* new_points_value,
+                               int num_new_points, int* info) {
+  return guarded(info, [&] {
+    CMOE_REQUIRE(num_new_points >= 0, CMOE_ERR_BOUNDS, "num_new_points must be >= 0");
+    require_device(gp->device);
+    const int dim = gp->spec.dim, b = 1 + gp->spec.g;
+    gp->hX.insert(gp->hX.end(), new_points, new_points + static_cast<size_t>(num_new_points) * dim);
+    gp->hy.insert(gp->hy.end(), new_points_value, new_points_value + static_cast<size_t>(num_new_points) * b);
+    gp->N += num_new_points;
+    fit_gp(gp, true);
+  });
+}
+
+int cmoe_gp_fit_timings(const cmoe_gp* gp, double* usec3) {
+  for (int i = 0; i < 3; ++i) usec3[i] = gp->fit_usec[i];
+  return CMOE_OK;
+}
+
+int cmoe_bench_cov_build(const cmoe_gp* gp, int repeats, double* usec_per_build) {
+  return guarded(nullptr, [&] {
+    require_device(gp->device);
+    DevBuf<double> scratch(static_cast<size_t>(gp->n) * gp->n);
+    cudaStream_t s = gp->stream;
+    build_covariance(gp->spec, gp->dX.p, gp->N, gp->dnoise.p, scratch.p, s);  // warm-up
+    EventTimer t;
+    t.start(s);
+    for (int r = 0; r < repeats; ++r) build_covariance(gp->spec, gp->dX.p, gp->N, gp->dnoise.p, scratch.p, s);
+    t.stop(s);
+    *usec_per_build = t.ms() * 1e3 / repeats;
+  });
+}
+
+int cmoe_bench_cholesky(const cmoe_gp* gp, int repeats, double* usec_per_factor) {
+  return guarded(nullptr, [&] {
+    require_device(gp->device);
+    const size_t nn = static_cast<size_t>(gp->n) * gp->n;
+    DevBuf<double> K0(nn), work(nn);
+    DevBuf<int> flag(1);
+    cudaStream_t s = gp->stream;
+    if (gp->spec.g > 0) K0.zero(s);
+    build_covariance(gp->spec, gp->dX.p, gp->N, gp->dnoise.p, K0.p, s);
+    double total = 0.0;
+    for (int r = 0; r < repeats + 1; ++r) {
+      CMOE_CUDA(cudaMemcpyAsync(work.p, K0.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      EventTimer t;
+      t.start(s);
+      potrf_lower(work.p, gp->n, flag.p, s);
+      t.stop(s);
+      if (r > 0) total += t.ms();
+    }
+    *usec_per_factor = total * 1e3 / repeats;
+  });
+}
+
+int cmoe_cholesky(int n, double* a, int device, int* info) {
+  return guarded(info, [&] {
+    CMOE_REQUIRE(n >= 1, CMOE_ERR_BOUNDS, "n must be >= 1");
+    require_device(device);
+    cudaStream_t s;
+    CMOE_CUDA(cudaStreamCreate(&s));
+    const size_t nn = static_cast<size_t>(n) * n;
+    DevBuf<double> A(nn);
+    DevBuf<int> flag(1);
+    A.upload(a, nn, s);
+    potrf_lower(A.p, n, flag.p, s);
+    int f = 0;
+    CMOE_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // copy back only the lower triangle; like the reference the strictly-upper part keeps the caller's input
+    std::vector<double> tmp(nn);
+    A.download(tmp.data(), nn, s);
+    CMOE_CUDA(cudaStreamSynchronize(s));
+    cudaStreamDestroy(s);
+    if (f != 0) throw Error(CMOE_ERR_SINGULAR, "cholesky matrix singular", f);
+    for (int j = 0; j < n; ++j)
+      for (int i = j; i < n; ++i) a[static_cast<size_t>(j) * n + i] = tmp[static_cast<size_t>(j) * n + i];
+  });
+}
+
+int cmoe_potrs(int n, int nrhs, const double* chol, double* x, int device) {
+  return guarded(nullptr, [&] {
+    CMOE_REQUIRE(n >= 1 && nrhs >= 0, CMOE_ERR_BOUNDS, "bad sizes");
+    require_device(device);
+    cudaStream_t s;
+    CMOE_CUDA(cudaStreamCreate(&s));
+    DevBuf<double> L(static_cast<size_t>(n) * n), X(static_cast<size_t>(n) * nrhs);
+    L.upload(chol, static_cast<size_t>(n) * n, s);
+    X.upload(x, static_cast<size_t>(n) * nrhs, s);
+    potrs_lower(L.p, n, X.p, n, nrhs, s);
+    X.download(x, static_cast<size_t>(n) * nrhs, s);
+    CMOE_CUDA(cudaStreamSynchronize(s));
+    cudaStreamDestroy(s);
+  });
+}
+
+int cmoe_philox_normals(uint64_t seed, uint64_t first_draw, int num_draws, int per_draw, double* out, int device) {
+  return guarded(nullptr, [&] {
+    require_device(device);
+    DevBuf<double> d(static_cast<size_t>(num_draws) * per_draw);
+    philox_normals_device(seed, first_draw, num_draws, per_draw, d.p, 0);
+    CMOE_CUDA(cudaMemcpy(out, d.p, d.count * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+// Dense FP64 linear algebra on sm_100a: blocked right-looking Cholesky with the trailing-panel SYRK/GEMM on the
+// FP64 tensor pipe (mma.sync m8n8k4 DMMA — tcgen05 has no f64 kind), and blocked triangular solves.
+//
+// Replaces (reference, moe/optimal_learning/cpp/):
+//   ComputeCholeskyFactorL              gpp_linear_algebra.cpp:109-148  (pivot test `> 1e-16`, returns k+1 on failure)
+//   TriangularMatrixVectorSolve         gpp_linear_algebra.cpp:160-193
+//   TriangularMatrixMatrixSolve         gpp_linear_algebra.cpp:203-208
+//   CholeskyFactorLMatrix{Vector,Matrix}Solve  gpp_linear_algebra.hpp:220,247
+//
+// Layout: column-major, only the lower triangle of the factor is defined (as in the reference).
+#include "device_math.cuh"
+#include "internal.cuh"
+
+namespace cmoe {
+
+namespace {
+
+constexpr int NB = 64;        // Cholesky block size == K depth of one DMMA tile product
+constexpr int LDT = NB + 4;   // smem leading dimension: 68 = 4 (mod 16) makes the DMMA fragment loads conflict-free
+constexpr double kPivotTol = 1.0e-16;  // gpp_linear_algebra.cpp:118
+
+// --------------------------------------------------------------------------------------------------------------
+// potf2: factor one nb x nb diagonal block in shared memory (single CTA), and emit inv(L_kk) for the panel update.
+// --------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int lda, int k0, int nb,
+                                                    double* __restrict__ invL, int* __restrict__ flag) {
+  extern __shared__ double dyn_smem[];
+  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
+  double (*V)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  __shared__ int failed;
+  if (*flag != 0) return;
+  const int tid = threadIdx.x;
+  double* Ab = A + static_cast<size_t>(k0) * lda + k0;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e % NB, j = e / NB;
+    S[i][j] = (i < nb && j < nb && i >= j) ? Ab[static_cast<size_t>(j) * lda + i] : 0.0;
+  }
+  if (tid == 0) failed = 0;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (tid == 0) {
+      const double piv = S[j][j];
+      if (piv > kPivotTol) {
+        S[j][j] = sqrt(piv);
+      } else {
+        failed = k0 + j + 1;
+      }
+    }
+    __syncthreads();
+    if (failed) break;
+    const double ljj = S[j][j];
+    for (int i = j + 1 + tid; i < nb; i += blockDim.x) S[i][j] /= ljj;
+    __syncthreads();
+    // trailing update of the lower triangle: S[i][c] -= S[i][j] * S[c][j], c in (j, nb), i in [c, nb)
+    const int m = nb - j - 1;
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      const int c = j + 1 + e / m, i = j + 1 + e % m;
+      if (i >= c) S[i][c] = S[i][c] - S[i][j] * S[c][j];
+    }
+    __syncthreads();
+  }
+  if (failed) {
+    if (tid == 0) *flag = failed;
+    return;
+  }
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int i = e % NB, j = e / NB;
+    if (i < nb && j < nb && i >= j) Ab[static_cast<size_t>(j) * lda + i] = S[i][j];
+  }
+  // inv(L_kk): thread c solves L x = e_c by forward substitution; result column-major nb x nb with ld NB.
+  if (invL != nullptr) {
+    if (tid < NB) {
+      const int c = tid;
+      for (int i = 0; i < NB; ++i) {
+        double v = 0.0;
+        if (i < nb && c < nb && i >= c) {
+          double acc = (i == c) ? 1.0 : 0.0;
+          for (int m2 = c; m2 < i; ++m2) acc -= S[i][m2] * V[m2][c];
+          v = acc / S[i][i];
+        }
+        V[i][c] = v;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += blockDim.x) invL[e] = V[e % NB][e / NB];
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// DMMA tile product:  C(64x64) = alpha * A(64xNB) * B(64xNB)^T + beta * C  with A, B, C blocks of one matrix.
+//   mode 0 (panel):  C = A_ik <- A_ik * inv(L_kk)^T            (B = invL scratch, beta = 0, in place)
+//   mode 1 (syrk):   C = A_ij <- A_ij - A_ik * A_jk^T, i >= j  (lower-triangular tile grid)
+// 4 warps, each owning a 32x32 sub-tile = 4x4 m8n8k4 fragments.
+// --------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// loads a (rows x NB) block whose (r, c) element sits at src[c*ld + r] into smem T[c*LDT + r], zero padded
+__device__ __forceinline__ void load_tile(double* __restrict__ T, const double* __restrict__ src, int ld, int rows,
+                                          int cols) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e % NB, c = e / NB;
+    T[c * LDT + r] = (r < rows && c < cols) ? src[static_cast<size_t>(c) * ld + r] : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                        const double* __restrict__ invL, int mode,
+                                                        const int* __restrict__ flag) {
+  extern __shared__ double smem[];
+  if (*flag != 0) return;
+  double* As = smem;
+  double* Bs = smem + NB * LDT;
+  const int t0 = k0 + nb;  // first row/col of the trailing matrix
+  int ti, tj;
+  if (mode == 0) {
+    ti = blockIdx.x;
+    tj = 0;
+  } else {
+    // linear index -> (ti >= tj) of the lower-triangular tile grid
+    const int b = blockIdx.x;
+    ti = static_cast<int>((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+    while (ti * (ti + 1) / 2 > b) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
+    tj = b - ti * (ti + 1) / 2;
+  }
+  const int row0 = t0 + ti * NB;
+  const int rows = min(NB, n - row0);
+  const double* Asrc = A + static_cast<size_t>(k0) * lda + row0;
+  load_tile(As, Asrc, lda, rows, nb);
+  int col0 = 0, cols = 0;
+  if (mode == 0) {
+    load_tile(Bs, invL, NB, nb, nb);  // B(n, k) = invL(n, k): C = A * invL^T
+    cols = nb;
+  } else {
+    col0 = t0 + tj * NB;
+    cols = min(NB, n - col0);
+    load_tile(Bs, A + static_cast<size_t>(k0) * lda + col0, lda, cols, nb);
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll 4
+  for (int kk = 0; kk < NB; kk += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = As[(kk + lc) * LDT + wm + i * 8 + lr];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + lc) * LDT + wn + j * 8 + lr];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+
+  // epilogue
+  double* Cdst;
+  int ldc = lda;
+  if (mode == 0) {
+    Cdst = A + static_cast<size_t>(k0) * lda + row0;  // overwrite A_ik (whole tile already staged in smem)
+  } else {
+    Cdst = A + static_cast<size_t>(col0) * lda + row0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm + i * 8 + lr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = wn + j * 8 + lc * 2 + h;
+        if (r < rows && c < cols) {
+          double* dst = Cdst + static_cast<size_t>(c) * ldc + r;
+          if (mode == 0) {
+            *dst = acc[i][j][h];
+          } else {
+            *dst = *dst - acc[i][j][h];
+          }
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Blocked triangular solve, one CTA per slab of 32 right-hand sides.
+//   TRANS = false: X <- L^-1 X (block rows top-down);  TRANS = true: X <- L^-T X (bottom-up).
+// Per block row: acc = sum_j Ltile(k,j) * X_j via 32x32x32 shared-memory products, then the 32x32 diagonal block is
+// solved by column-oriented substitution (the operation order of the reference's TriangularMatrixVectorSolve, so
+// small integer systems come out exact), one barrier per eliminated unknown.
+// --------------------------------------------------------------------------------------------------------------
+template <bool TRANS>
+__global__ void __launch_bounds__(256) trsm_kernel(const double* __restrict__ L, int n, double* __restrict__ X,
+                                                   int ldx, int nrhs) {
+  constexpr int T = kTrsmNB;
+  __shared__ double Ls[T][T + 1];
+  __shared__ double Xs[T][T + 1];
+  __shared__ double Ys[2][T];
+  const int col0 = blockIdx.x * T;
+  const int tid = threadIdx.x;
+  const int c = tid & 31, rg = tid >> 5;  // output column, row group (rows rg + 8*i)
+  const int lm = tid & 31, lq = tid >> 5; // load mapping: fast index, slow index (+8*i)
+  const int nbk = (n + T - 1) / T;
+  const bool col_ok = (col0 + c) < nrhs;
+
+  for (int step = 0; step < nbk; ++step) {
+    const int k = TRANS ? (nbk - 1 - step) : step;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int jbeg = TRANS ? (k + 1) : 0, jend = TRANS ? nbk : k;
+    for (int j = jbeg; j < jend; ++j) {
+      // Ls[r][m] = (op(L))(k*T + r, j*T + m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int slow = lq + 8 * i;
+        if (!TRANS) {
+          const int r = k * T + lm, m = j * T + slow;  // L(r, m), contiguous in r
+          Ls[lm][slow] = (r < n && m < n) ? L[static_cast<size_t>(m) * n + r] : 0.0;
+        } else {
+          const int m = j * T + lm, r = k * T + slow;  // L(m, r), contiguous in m
+          Ls[slow][lm] = (r < n && m < n) ? L[static_cast<size_t>(r) * n + m] : 0.0;
+        }
+        const int xr = j * T + lm, xc = col0 + slow;
+        Xs[lm][slow] = (xr < n && xc < nrhs) ? X[static_cast<size_t>(xc) * ldx + xr] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int m = 0; m < T; ++m) {
+        const double xv = Xs[m][c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += Ls[rg + 8 * i][m] * xv;
+      }
+      __syncthreads();
+    }
+    // diagonal block L_kk -> Ls (lower part; identity on the padding), right-hand side minus products -> registers
+    double val[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg + 8 * i;
+      const int xr = k * T + r;
+      const double bval = (xr < n && col_ok) ? X[static_cast<size_t>(col0 + c) * ldx + xr] : 0.0;
+      val[i] = bval - acc[i];
+      const int slow = lq + 8 * i;  // column of the block
+      const int gr = k * T + lm, gc = k * T + slow;
+      double lv = 0.0;
+      if (gr < n && gc < n) {
+        if (lm >= slow) lv = L[static_cast<size_t>(gc) * n + gr];
+      } else if (lm == slow) {
+        lv = 1.0;
+      }
+      Ls[lm][slow] = lv;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < T; ++rr) {
+      const int r = TRANS ? (T - 1 - rr) : rr;
+      if (rg == (r & 7)) {
+        const int i = r >> 3;
+        double y = 0.0;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+          if (ii == i) {
+            y = val[ii] / Ls[r][r];
+            val[ii] = y;
+          }
+        Ys[rr & 1][c] = y;
+      }
+      __syncthreads();
+      const double y = Ys[rr & 1][c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = rg + 8 * i;
+        if (!TRANS) {
+          if (row > r) val[i] = val[i] - y * Ls[row][r];
+        } else {
+          if (row < r) val[i] = val[i] - Ls[r][row] * y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xr = k * T + rg + 8 * i;
+      if (xr < n && col_ok) X[static_cast<size_t>(col0 + c) * ldx + xr] = val[i];
+    }
+    __syncthreads();  // make this block row visible to the next iterations of this CTA
+  }
+}
+
+int g_launches = 0;
+
+}  // namespace
+
+int launches_issued() { return g_launches; }
+void count_launch(int n) { g_launches += n; }
+
+void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
+  const size_t smem = 2 * NB * LDT * sizeof(double);
+  CMOE_CUDA(cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  const size_t smem_potf2 = 2 * NB * (NB + 1) * sizeof(double);
+  CMOE_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem_potf2)));
+  CMOE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  DevBuf<double> invL(NB * NB);
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int nb = min(NB, n - k0);
+    const int rem = n - k0 - nb;
+    potf2_kernel<<<1, 256, smem_potf2, s>>>(A, n, k0, nb, rem > 0 ? invL.p : nullptr, flag);
+    count_launch();
+    if (rem > 0) {
+      const int tiles = (rem + NB - 1) / NB;
+      dmma_tile_kernel<<<tiles, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 0, flag);
+      dmma_tile_kernel<<<tiles * (tiles + 1) / 2, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 1, flag);
+      count_launch(2);
+    }
+  }
+  CMOE_CUDA(cudaGetLastError());
+  CMOE_CUDA(cudaStreamSynchronize(s));  // invL scratch is freed on return
+}
+
+void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s) {
+  if (n == 0 || nrhs == 0) return;
+  const int grid = (nrhs + kTrsmNB - 1) / kTrsmNB;
+  if (trans) {
+    trsm_kernel<true><<<grid, 256, 0, s>>>(L, n, X, ldx, nrhs);
+  } else {
+    trsm_kernel<false><<<grid, 256, 0, s>>>(L, n, X, ldx, nrhs);
+  }
+  count_launch();
+  CMOE_CUDA(cudaGetLastError());
+}
+
+void potrs_lower(const double* L, int n, double* X, int ldx, int nrhs, cudaStream_t s) {
+  trsm_lower(L, n, X, ldx, nrhs, false, s);
+  trsm_lower(L, n, X, ldx, nrhs, true, s);
+}
+
+}  // namespace cmoe

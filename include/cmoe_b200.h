@@ -1,0 +1,194 @@
+/* cornell-moe_b200 — C ABI of the B200-native GP-posterior + Monte-Carlo acquisition path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types.  Every entry point
+ * states which interface of the reference (wujian16/Cornell-MOE, paths relative to
+ * moe/optimal_learning/cpp/) it replaces.  The pybind11 module `GPP` in cornell-moe_b200/csrc/gpp_module.cpp
+ * re-exports the reference's `moe.build.GPP` names on top of exactly these calls; INTEGRATION.md shows the
+ * binding a reference maintainer would add.
+ *
+ * Conventions are the reference's own (gpp_common.hpp:29,390; gpp_math.hpp:301-305):
+ *   - all reals are IEEE double, all matrices column-major, point sets are [num_points][dim];
+ *   - observations are interleaved per point: (value, d/dx_{derivatives[0]}, ...);
+ *   - noise_variance has 1+num_derivatives entries and is indexed by observation TYPE, not by point
+ *     (gpp_math.cpp:447-449);
+ *   - host pointers in, host pointers out, no ownership transfer (gpp_python_common.cpp:37, 79-128).
+ *
+ * Errors: every function returns a status code; CMOE_ERR_* map 1:1 onto the reference's exception
+ * classes (gpp_exception.hpp:170-509, gpp_python.cpp:189-206).  `info` receives the payload
+ * (leading-minor index k+1 for CMOE_ERR_SINGULAR, exactly as gpp_linear_algebra.cpp:141-142 returns it).
+ * There is NO CPU fallback: without a CUDA device every compute call returns CMOE_ERR_NO_DEVICE.
+ */
+#ifndef CMOE_B200_H_
+#define CMOE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMOE_OK 0
+#define CMOE_ERR_SINGULAR 1      /* SingularMatrixException   (gpp_exception.hpp:465) */
+#define CMOE_ERR_BOUNDS 2        /* BoundsException           (gpp_exception.hpp:243) */
+#define CMOE_ERR_INVALID_VALUE 3 /* InvalidValueException     (gpp_exception.hpp:382) */
+#define CMOE_ERR_RUNTIME 4       /* OptimalLearningException  (gpp_exception.hpp:170): CUDA / internal failure */
+#define CMOE_ERR_NO_DEVICE 5     /* OptimalLearningException: no CUDA device; there is no CPU path */
+
+#define CMOE_KERNEL_SQUARE_EXPONENTIAL 0 /* gpp_covariance.hpp:195 */
+#define CMOE_KERNEL_MATERN_NU_2P5 1      /* gpp_covariance.hpp:313 */
+
+#define CMOE_MAX_DIM 32
+
+typedef struct cmoe_gp cmoe_gp; /* opaque; replaces optimal_learning::GaussianProcess (gpp_math.hpp:275) */
+
+/* GradientDescentParameters, gpp_optimizer_parameters.hpp:81-135 (same field order as its constructor) */
+typedef struct cmoe_gd_params {
+  int num_multistarts;
+  int max_num_steps;
+  int max_num_restarts;
+  int num_steps_averaged;
+  double gamma;
+  double pre_mult;
+  double max_relative_change;
+  double tolerance;
+} cmoe_gd_params;
+
+/* Work counters reported by the fused q-KG kernel (it counts what it actually executed). */
+typedef struct cmoe_kg_stats {
+  uint64_t mc_samples;         /* candidates * num_mc */
+  uint64_t posterior_evals;    /* posterior-mean (+gradient) evaluations inside the per-sample line search */
+  uint64_t line_search_steps;  /* accepted inner gradient steps */
+} cmoe_kg_stats;
+
+/* Human-readable description of the last error on the calling thread. */
+const char* cmoe_last_error(void);
+const char* cmoe_version(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int cmoe_device_count(void);
+
+/* ---- GaussianProcess --------------------------------------------------------------------------------------
+ * cmoe_gp_create  replaces GaussianProcess::GaussianProcess (gpp_math.cpp:553-573) == covariance build
+ *   (gpp_math.cpp:426-455) + Cholesky (gpp_linear_algebra.cpp:109-148) + K^-1 (y - mean) (gpp_math.cpp:481-511);
+ *   Python boundary: make_gaussian_process, gpp_python_gaussian_process.cpp:42-62.
+ *   hyperparameters = (alpha, lengths[dim]).  device = CUDA ordinal (the reference's dead `which_gpu`).
+ *   On a singular K: returns CMOE_ERR_SINGULAR, *info = leading minor index, *gp_out = NULL. */
+int cmoe_gp_create(int kernel, double alpha, const double* lengths, const double* points_sampled,
+                   const double* points_sampled_value, const double* noise_variance, const int* derivatives,
+                   int num_derivatives, int dim, int num_sampled, int device, cmoe_gp** gp_out, int* info);
+void cmoe_gp_destroy(cmoe_gp* gp);
+int cmoe_gp_dim(const cmoe_gp* gp);
+int cmoe_gp_num_sampled(const cmoe_gp* gp);
+int cmoe_gp_num_derivatives(const cmoe_gp* gp);
+/* Copies out K_chol_ (n*n, lower triangle valid), K_inv_y_ (n) and mean_ (gpp_math.hpp:838-867); any may be NULL. */
+int cmoe_gp_get_state(const cmoe_gp* gp, double* K_chol, double* K_inv_y, double* mean);
+/* GaussianProcess::AddPointsToGP (gpp_math.cpp:1699-1718): append and refit. */
+int cmoe_gp_add_sampled_points(cmoe_gp* gp, const double* new_points, const double* new_points_value,
+                               int num_new_points, int* info);
+/* Timings of the last fit, microseconds of device time: {covariance build, Cholesky, K^-1 y solve}. */
+int cmoe_gp_fit_timings(const cmoe_gp* gp, double* usec3);
+
+/* ---- posterior queries, batched over point sets -------------------------------------------------------------
+ * Replaces ComputeMeanOfPoints (gpp_math.cpp:662), ComputeGradMeanOfPoints (:721), ComputeVarianceOfPoints (:924),
+ * ComputeGradVarianceOfPoints (:1366), ComputeGradCholeskyVarianceOfPoints (:1466) and the q*q Cholesky; Python
+ * boundary gpp_python_gaussian_process.cpp:64-236.  `sets` = [num_sets][num_pts][dim]; each point carries the
+ * derivative rows derivs_s[g_s] (Q = num_pts*(1+g_s)).  Outputs per set, reference layouts:
+ *   mean[Q]; grad_mean[Q][dim] (d fastest); var[Q*Q] col-major (full symmetric); chol_var[Q*Q] (lower, upper zeroed);
+ *   grad_var / grad_chol [num_pts][Q][Q][dim] (d fastest; grad_chol in the reference's transposed storage,
+ *   gpp_math.cpp:1416-1417).  Any output may be NULL.  chol failure -> CMOE_ERR_SINGULAR, *info = index. */
+int cmoe_gp_posterior(const cmoe_gp* gp, const double* sets, int num_sets, int num_pts, const int* derivs_s, int g_s,
+                      double* mean, double* grad_mean, double* var, double* chol_var, double* grad_var,
+                      double* grad_chol, int* info);
+
+/* ---- q-EI Monte Carlo, batched over candidates ----------------------------------------------------------------
+ * Replaces ExpectedImprovementEvaluator::ComputeExpectedImprovement / ComputeGradExpectedImprovement
+ * (gpp_math.cpp:1991-2126); Python boundary compute_expected_improvement / compute_grad_expected_improvement /
+ * evaluate_EI_at_point_list (gpp_python_expected_improvement.cpp:44-109, 401-441).
+ * candidates = [num_candidates][q][dim]; points_being_sampled = [p][dim] shared by all candidates.
+ * Normals: Philox4x32-10 + Box-Muller keyed by `seed` (same stream for every candidate = common random numbers,
+ * the device analogue of ResetToMostRecentSeed, gpp_random.cpp:130-135), or, if normals_table != NULL, the table
+ * is replayed exactly like NormalRNGSimulator (gpp_random.hpp:314): (q+p) normals per iteration.
+ * ei[num_candidates]; grad_ei[num_candidates][q][dim] or NULL. */
+int cmoe_ei_eval(const cmoe_gp* gp, const double* candidates, int num_candidates, int q,
+                 const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                 const double* normals_table, double* ei, double* grad_ei, int* info);
+
+/* ---- q-KG / d-KG Monte Carlo, batched over candidates -----------------------------------------------------------
+ * Replaces KnowledgeGradientEvaluator::ComputeKnowledgeGradient / ComputeGradKnowledgeGradient
+ * (gpp_knowledge_gradient_optimization.cpp:69-227) including KnowledgeGradientState::PreCompute (:292-317),
+ * ComputeOptimalPosteriorMean (:420-472), the line-search gradient descent (gpp_optimization.hpp:708-828) and
+ * TensorProductDomain::LimitUpdate (gpp_domain.cpp:64-104); Python boundary compute_knowledge_gradient /
+ * compute_grad_knowledge_gradient / evaluate_KG_at_point_list (gpp_python_knowledge_gradient.cpp:77-154, 352-397).
+ * inner_bounds = [dim-num_fidelity][2]; discrete_pts = [num_pts][dim-num_fidelity].
+ * Normals as for EI but (q+p)(1+g) per EVEN iteration; odd iterations are antithetic (:88-97).
+ * kg[num_candidates]; grad_kg[num_candidates][q][dim] or NULL; stats may be NULL. */
+int cmoe_kg_eval(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* inner, const double* inner_bounds,
+                 const double* discrete_pts, int num_pts, const double* candidates, int num_candidates, int q,
+                 const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                 const double* normals_table, double* kg, double* grad_kg, cmoe_kg_stats* stats, int* info);
+
+/* ---- device-resident plan for the q-KG path (what bench.py times as `value`) ------------------------------------
+ * Same computation as cmoe_kg_eval, split so that inputs can be made resident in HBM before the timed region:
+ *   create -> upload (H2D of candidates) -> run (kernels only, asynchronous on the plan's stream) -> download (D2H).
+ * cmoe_kg_plan_elapsed_ms returns CUDA-event time of the last run; cmoe_kg_plan_kernel_ms the time spent in the
+ * fused MC kernel alone (events recorded around it on the launching stream); *_launches the kernel launches issued. */
+typedef struct cmoe_kg_plan cmoe_kg_plan;
+int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* inner, const double* inner_bounds,
+                        const double* discrete_pts, int num_pts, int max_candidates, int q,
+                        const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                        int want_grad, cmoe_kg_plan** plan_out);
+void cmoe_kg_plan_destroy(cmoe_kg_plan* plan);
+int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_candidates);
+int cmoe_kg_plan_run(cmoe_kg_plan* plan);
+int cmoe_kg_plan_sync(cmoe_kg_plan* plan, int* info);
+int cmoe_kg_plan_download(cmoe_kg_plan* plan, double* kg, double* grad_kg, cmoe_kg_stats* stats);
+int cmoe_kg_plan_timings(const cmoe_kg_plan* plan, double* total_ms, double* mc_kernel_ms, int* launches);
+
+/* ---- multistart optimisation (the data-parallel axis) -------------------------------------------------------------
+ * Replaces ComputeKGOptimalPointsToSampleViaMultistartGradientDescent (gpp_knowledge_gradient_optimization.hpp:859-935):
+ * KG at every start -> keep the best 20 (hard-coded `k = 20`, :901) -> restarted gradient descent with LimitUpdate on
+ * each (gpp_optimization.hpp:620-705, 1144-1185) -> strict-> argmax (gpp_optimization.hpp:1511, 1540).
+ * Python boundary multistart_knowledge_gradient_optimization (gpp_python_knowledge_gradient.cpp:243-304).
+ * shard_rank / shard_count select this process's share of the starts (candidate c belongs to rank c % count); the caller
+ * (one process per GPU) exchanges the per-start values with one collective — see cornell_moe_b200/multigpu.py.
+ * start_values (may be NULL) receives KG at every start owned by this shard (others untouched).
+ * best_value / best_point[q*dim] / found_flag follow OptimizationIOContainer (gpp_optimization.hpp:511). */
+int cmoe_multistart_kg(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
+                       const double* domain_bounds, const double* inner_bounds, const double* discrete_pts, int num_pts,
+                       const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
+                       int num_mc, double best_so_far, uint64_t seed, double* start_values, double* best_point,
+                       double* best_value, int* found_flag, int* info);
+/* EI twin: ComputeOptimalPointsToSampleViaMultistartGradientDescent (gpp_math.hpp:1683-1802);
+ * Python boundary multistart_expected_improvement_optimization (gpp_python_expected_improvement.cpp:221-276). */
+int cmoe_multistart_ei(const cmoe_gp* gp, const cmoe_gd_params* outer, const double* domain_bounds,
+                       const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
+                       int num_mc, double best_so_far, uint64_t seed, double* start_values, double* best_point,
+                       double* best_value, int* found_flag, int* info);
+
+/* Restarted gradient descent from given starts only (the second half of the multistart drivers); used by the
+ * multi-GPU host layer after the global top-20 has been agreed on.  values_out[num_starts], points_out[num_starts][q*dim]. */
+int cmoe_kg_gradient_descent(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,
+                             const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                             const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                             const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                             double* values_out, double* points_out, int* info);
+int cmoe_ei_gradient_descent(const cmoe_gp* gp, const cmoe_gd_params* outer, const double* domain_bounds,
+                             const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
+                             int num_mc, double best_so_far, uint64_t seed, double* values_out, double* points_out,
+                             int* info);
+
+/* ---- building blocks exposed for parity tests and micro-benchmarks ------------------------------------------------ */
+/* Covariance build alone on device-resident inputs: returns device time (usec) of `repeats` builds of the n*n matrix. */
+int cmoe_bench_cov_build(const cmoe_gp* gp, int repeats, double* usec_per_build);
+/* Blocked Cholesky alone (re-factors a fresh copy of K each repeat). */
+int cmoe_bench_cholesky(const cmoe_gp* gp, int repeats, double* usec_per_factor);
+/* In-place lower Cholesky of a host matrix through the device path (ComputeCholeskyFactorL, gpp_linear_algebra.cpp:109). */
+int cmoe_cholesky(int n, double* a, int device, int* info);
+/* Solve (L L^T) X = B for nrhs right-hand sides (CholeskyFactorLMatrixMatrixSolve, gpp_linear_algebra.hpp:247). */
+int cmoe_potrs(int n, int nrhs, const double* chol, double* x, int device);
+/* Philox4x32-10 + Box-Muller normals exactly as the kernels draw them: out[num_draws][per_draw]. */
+int cmoe_philox_normals(uint64_t seed, uint64_t first_draw, int num_draws, int per_draw, double* out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMOE_B200_H_ */

@@ -1,0 +1,108 @@
+"""GPU parity: covariance build, blocked Cholesky, triangular solves, GP fit — CUDA path (through the C ABI) vs the
+CPU checker on identical inputs."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from gpu_util import checker, tril_close
+from synth import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from cornell_moe_b200 import capi as c
+    assert c.device_count() > 0, "needs a CUDA device"
+    return c
+
+
+def test_cholesky_known_answers(capi):
+    # reference KATs: gpp_linear_algebra_test.cpp:238-262 (integer matrices, exact factors) and :358-368
+    A = np.array([[81.0, 27, 0, 90], [27, 13, 8, 44], [0, 8, 52, 40], [90, 44, 40, 217]])
+    L = capi.cholesky(A)
+    np.testing.assert_array_equal(np.tril(L), np.array([[9.0, 0, 0, 0], [3, 2, 0, 0], [0, 4, 6, 0], [10, 7, 2, 8]]))
+    B = np.array([[25.0, 15, -5], [15, 18, 0], [-5, 0, 11]])
+    np.testing.assert_array_equal(np.tril(capi.cholesky(B)), np.array([[5.0, 0, 0], [3, 3, 0], [-1, 1, 3]]))
+    W = np.array([[4.0, 12, -16], [12, 37, -43], [-16, -43, 98]])
+    Lw = capi.cholesky(W)
+    np.testing.assert_array_equal(np.tril(Lw), np.array([[2.0, 0, 0], [6, 1, 0], [-8, 5, 3]]))
+    x = capi.potrs(np.tril(Lw), np.array([-20.0, -43.0, 192.0]))
+    np.testing.assert_allclose(x, [1.0, 2.0, 3.0], rtol=1e-14)
+
+
+@pytest.mark.parametrize("n", [1, 5, 11, 20, 63, 64, 65, 130, 257, 500])
+def test_cholesky_random_spd(capi, n):
+    rng = np.random.default_rng(34187 + n)
+    A = rng.standard_normal((n, n))
+    A = A @ A.T + n * np.eye(n)
+    L = np.tril(capi.cholesky(A))
+    rc, Lref = checker().cholesky(A)
+    assert rc == 0
+    tril_close(L, Lref, rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(L @ L.T, A, rtol=1e-12, atol=1e-11 * n)
+    B = rng.standard_normal((n, 37))
+    X = capi.potrs(L, B)
+    np.testing.assert_allclose(A @ X, B, rtol=1e-9, atol=1e-9)
+
+
+def test_cholesky_failure_index(capi):
+    # exactly singular in integer arithmetic: pivot 3 is 0 -> k+1 = 3, as gpp_linear_algebra.cpp:141-142
+    L0 = np.array([[2.0, 0, 0, 0], [1, 3, 0, 0], [4, 1, 0, 0], [2, 2, 1, 5]])
+    with pytest.raises(capi.SingularMatrixError) as e:
+        capi.cholesky(L0 @ L0.T)
+    assert e.value.info == 3
+    # failure in a later block of the blocked algorithm
+    n = 150
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((n, n))
+    A = A @ A.T + n * np.eye(n)
+    A[100, :] = 0.0
+    A[:, 100] = 0.0
+    with pytest.raises(capi.SingularMatrixError) as e:
+        capi.cholesky(A)
+    assert e.value.info == 101
+
+
+def test_philox_stream_matches_host(capi):
+    dev = capi.philox_normals(0xC0FFEE, 5, 300, 7)
+    host = orc.philox_normals(0xC0FFEE, 5, 300, 7)
+    np.testing.assert_allclose(dev, host, rtol=1e-12, atol=1e-14)
+    assert abs(dev.mean()) < 0.1 and abs(dev.std() - 1.0) < 0.1
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("N,dim,g_idx", [(50, 2, ()), (24, 3, (0, 2)), (200, 6, ()), (300, 4, (0, 1, 2, 3)), (500, 8, ())])
+def test_gp_fit_matches_checker(capi, kernel, N, dim, g_idx):
+    prob = make_problem(N, dim, g_idx=g_idx, seed=N + dim)
+    gp = capi.GaussianProcess(kernel, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"],
+                              prob["derivs"])
+    ref, lm = checker().gp(kernel, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    assert lm == 0
+    K, kinvy, mean = gp.state()
+    Kr, kr, mr = ref.state()
+    assert mean == mr
+    tril_close(K, Kr, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(kinvy, kr, rtol=1e-7, atol=1e-8)
+
+
+def test_gp_singular_reports_leading_minor(capi):
+    prob = make_problem(10, 2, seed=1)
+    prob["X"][1] = prob["X"][0]
+    prob["noise"][:] = 0.0
+    with pytest.raises(capi.SingularMatrixError) as e:
+        capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    assert e.value.info == 2
+
+
+def test_gp_large_fit_residual(capi):
+    # size-independent property at a config-5-like size: L L^T reproduces K and K (K^-1 y) reproduces y - mean
+    prob = make_problem(2000, 10, seed=5, length=0.5)
+    gp = capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    L, kinvy, mean = gp.state()
+    L = np.tril(L)
+    X = prob["X"] / prob["lengths"]
+    d2 = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+    K = np.exp(-0.5 * d2) + prob["noise"][0] * np.eye(2000)
+    np.testing.assert_allclose(L @ L.T, K, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(K @ kinvy, prob["y"] - mean, rtol=0, atol=1e-8)
