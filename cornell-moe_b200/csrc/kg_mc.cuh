@@ -1,0 +1,522 @@
+// Fused q-KG Monte-Carlo kernels (the north-star hot path).
+//
+// One MC sample-evaluation of the reference = fantasise y = mu + L z at the q candidate points, re-solve K^-1 y on the
+// (N+q) system, scan the discretisation set for the arg-min of the new posterior mean and run a line-search gradient
+// descent from it (gpp_knowledge_gradient_optimization.cpp:87-113, 420-472; gpp_optimization.hpp:708-828).
+// Here the re-solve is replaced by the algebraically identical rank-q update
+//     mu+(x) = m + sum_j (beta_j - B_j . c) k(x, X_j) + sum_u c_u k(x, Xu_u),      c = L^-T z,  B = K^-1 K*
+// so a sample touches no HBM at all: the per-candidate operands (scaled X, beta, B) are staged once per CTA into shared
+// memory with TMA bulk copies and every lane runs one sample's whole inner optimisation out of registers.
+//
+// Mapping: one thread per MC sample; grid = (sample chunks, candidates).  Lanes that finish fetch the next sample of
+// the chunk from a shared counter, so a warp only idles at the very end of a chunk although the line search has
+// data-dependent trip counts.  The line search is a per-lane state machine whose only expensive transition is
+// "evaluate mu+ and its gradient at my query point" — that evaluation is warp-uniform code.
+#pragma once
+
+#include "device_math.cuh"
+#include "internal.cuh"
+
+namespace cmoe {
+
+struct KgMcParams {
+  int N;        // training points
+  int U;        // union points (= rows, g == 0)
+  int ps;       // free coordinates (dim - num_fidelity)
+  int dim;
+  int M;        // discretisation set size (U + num_pts)
+  int num_mc;
+  int chunk;    // samples per CTA
+  int use_smem;
+  int max_steps, max_restarts;
+  double mean, mrc, tol, step_tol, alpha;
+  const double* Xt;      // [N][DIM] scaled training points (zero padded)
+  const double* Pk;      // [nc][N][QP+2]  (e_j, beta_j, B_j[0..QP))
+  const double* Xu;      // [nc][U][DIM+2] (scaled union point, e_u, pad)
+  const double* A;       // [nc][M][DIM]   unscaled start points (fidelity coords = 1, padding = 0)
+  const double* recC;    // [nc][num_mc][QP]
+  const int* recStart;   // [nc][num_mc]
+  const double* alpha0;  // [max_steps]  pre_mult * (i+1)^-gamma
+  double* outVal;        // [nc][num_mc]   -mu+(x*)  (the reference's best_function_value)
+  double* outX;          // [nc][num_mc][DIM] scaled minimiser
+  unsigned long long* stats;  // [2]: posterior evaluations, accepted steps
+  double lo[CMOE_MAX_DIM], hi[CMOE_MAX_DIM], inv_len[CMOE_MAX_DIM], len[CMOE_MAX_DIM];
+};
+
+struct KgAccParams {
+  int N, U, dim, num_mc;
+  double alpha;
+  const double* Xt;     // [N][DIM]
+  const double* Xu;     // [nc][U][DIM+2]
+  const double* recC;   // [nc][num_mc][QP]
+  const double* outX;   // [nc][num_mc][DIM]
+  double* R;            // [nc][QP][N+U]   R[a][row] = sum_i c_ia k(row, x*_i)
+  double* Gu;           // [nc][U][DIM]    sum_i c_iu Bpart(Xu_u, x*_i) x~*_i
+  double* GkB;          // [nc][U]         sum_i c_iu Bpart(Xu_u, x*_i)
+};
+
+// ---- small PTX helpers: mbarrier + TMA bulk copy (global -> shared) ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Kernel-specific pieces.  pk0 holds e_j = ln(alpha) - |x~_j|^2/2 for SE and |x~_j|^2 for Matern.
+// Returns the value weight kv (k(x, X_j)) and the gradient weight kb (d k / d x_d = kb * (x~_jd - x~_d) / l_d).
+template <int KERNEL>
+__device__ __forceinline__ void kernel_pair(double dot, double pk0, double nq, double alpha, double& kv, double& kb) {
+  if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
+    kv = exp(dot + pk0 - 0.5 * nq);
+    kb = kv;
+  } else {
+    const double r2 = fmax(0.0, nq + pk0 - 2.0 * dot);
+    const double ar = kSqrt5 * sqrt(r2);
+    const double ee = alpha * exp(-ar);
+    kv = ee * (1.0 + ar + (5.0 / 3.0) * r2);
+    kb = (5.0 / 3.0) * ee * (1.0 + ar);
+  }
+}
+
+// mu+(xq) - m  and  the scaled-gradient accumulators, for one query point (scaled coordinates xq).
+template <int KERNEL, int DIM, int QP>
+__device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, const double* __restrict__ Pk,
+                                               const double* __restrict__ Xu, int N, int U, double alpha,
+                                               const double (&xq)[DIM], const double (&c)[QP], double& S0, double& SB,
+                                               double (&s)[DIM]) {
+  double nq = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) nq = fma(xq[d], xq[d], nq);
+  S0 = 0.0;
+  SB = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) s[d] = 0.0;
+#pragma unroll 2
+  for (int j = 0; j < N; ++j) {
+    const double* xj = Xt + j * DIM;
+    const double* pk = Pk + j * (QP + 2);
+    double dot = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xj[d], dot);
+    double a = pk[1];
+#pragma unroll
+    for (int u = 0; u < QP; ++u) a = fma(-pk[2 + u], c[u], a);
+    double kv, kb;
+    kernel_pair<KERNEL>(dot, pk[0], nq, alpha, kv, kb);
+    S0 = fma(a, kv, S0);
+    const double wb = a * kb;
+    if (KERNEL != CMOE_KERNEL_SQUARE_EXPONENTIAL) SB += wb;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xj[d], s[d]);
+  }
+  for (int u = 0; u < U; ++u) {
+    const double* xu = Xu + u * (DIM + 2);
+    double dot = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xu[d], dot);
+    double kv, kb;
+    kernel_pair<KERNEL>(dot, xu[DIM], nq, alpha, kv, kb);
+    double cu = 0.0;
+#pragma unroll
+    for (int v = 0; v < QP; ++v)
+      if (v == u) cu = c[v];
+    S0 = fma(cu, kv, S0);
+    const double wb = cu * kb;
+    if (KERNEL != CMOE_KERNEL_SQUARE_EXPONENTIAL) SB += wb;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xu[d], s[d]);
+  }
+  if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) SB = S0;
+}
+
+// TensorProductDomain::LimitUpdate, gpp_domain.cpp:64-104, for one coordinate
+__device__ __forceinline__ double limit_step(double step, double x, double lo, double hi, double mrc) {
+  double dist = fmin(x - lo, hi - x);
+  if (fabs(step) > mrc * dist) step = copysign(mrc * dist, step);
+  const double next = x + step;
+  if (next < lo || next > hi) {
+    if (next < lo) {
+      dist = lo - x;
+      step = (x + step * 0.5 < lo) ? dist * 0.5 : step * 0.5;
+    } else {
+      dist = hi - x;
+      step = (x + step * 0.5 > hi) ? dist * 0.5 : step * 0.5;
+    }
+  }
+  return step;
+}
+
+enum : int { ST_FETCH = 0, ST_INIT = 1, ST_TRIAL = 2, ST_LIMIT = 3, ST_DONE = 4 };
+
+template <int KERNEL, int DIM, int QP>
+__global__ void __launch_bounds__(256, 2) kg_mc_kernel(const __grid_constant__ KgMcParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t mbar;
+  __shared__ int next_sample;
+  const int cand = blockIdx.y;
+  const int N = prm.N, U = prm.U;
+  const int s_begin = blockIdx.x * prm.chunk;
+  const int s_end = min(prm.num_mc, s_begin + prm.chunk);
+  const double* Xt = prm.Xt;
+  const double* Pk = prm.Pk + static_cast<size_t>(cand) * N * (QP + 2);
+  const double* Xu = prm.Xu + static_cast<size_t>(cand) * U * (DIM + 2);
+  if (prm.use_smem) {
+    // stage the per-candidate operands with TMA bulk copies (UBLKCP) signalled through an mbarrier
+    double* sXt = reinterpret_cast<double*>(smem_raw);
+    double* sPk = sXt + static_cast<size_t>(N) * DIM;
+    double* sXu = sPk + static_cast<size_t>(N) * (QP + 2);
+    const uint32_t bX = static_cast<uint32_t>(N) * DIM * 8u, bP = static_cast<uint32_t>(N) * (QP + 2) * 8u,
+                   bU = static_cast<uint32_t>(U) * (DIM + 2) * 8u;
+    if (threadIdx.x == 0) {
+      mbar_init(&mbar, 1);
+      next_sample = s_begin + blockDim.x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&mbar, bX + bP + bU);
+      tma_bulk_g2s(sXt, Xt, bX, &mbar);
+      tma_bulk_g2s(sPk, Pk, bP, &mbar);
+      tma_bulk_g2s(sXu, Xu, bU, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    Xt = sXt;
+    Pk = sPk;
+    Xu = sXu;
+  } else {
+    if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
+    __syncthreads();
+  }
+
+  const double* A = prm.A + static_cast<size_t>(cand) * prm.M * DIM;
+  const double* recC = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
+  const int* recStart = prm.recStart + static_cast<size_t>(cand) * prm.num_mc;
+  double* outVal = prm.outVal + static_cast<size_t>(cand) * prm.num_mc;
+  double* outX = prm.outX + static_cast<size_t>(cand) * prm.num_mc * DIM;
+
+  // per-lane state
+  int state = ST_FETCH;
+  int sample = s_begin + threadIdx.x;
+  double c[QP];
+  double xb[DIM], gb[DIM];   // base point (unscaled) and gradient of f = -mu+ there
+  double run0[DIM];          // start of the current restart run
+  double fb = 0.0, alpha_n = 0.0, gnorm = 0.0, f_trial = 0.0;
+  double g_trial[DIM];
+  int step_i = 0, restart_i = 0, search = 0;
+  unsigned long long n_evals = 0, n_steps = 0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) xb[d] = gb[d] = run0[d] = g_trial[d] = 0.0;
+#pragma unroll
+  for (int u = 0; u < QP; ++u) c[u] = 0.0;
+
+  while (true) {
+    if (state == ST_FETCH) {
+      if (sample < s_end) {
+#pragma unroll
+        for (int u = 0; u < QP; ++u) c[u] = recC[static_cast<size_t>(sample) * QP + u];
+        const double* a0 = A + static_cast<size_t>(recStart[sample]) * DIM;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          xb[d] = a0[d];
+          run0[d] = a0[d];
+        }
+        step_i = 0;
+        restart_i = 0;
+        state = (prm.max_restarts > 0) ? ST_INIT : ST_DONE;
+        if (state == ST_DONE) {
+          // ComputeOptimalPosteriorMean returns without touching its outputs (...optimization.cpp:424-426):
+          // best_function_value stays 0 and the best point stays at its fill value 1.0
+          outVal[sample] = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = 1.0 * prm.inv_len[d];
+          sample = atomicAdd(&next_sample, 1);
+          state = ST_FETCH;
+          continue;
+        }
+      } else {
+        state = ST_DONE;
+      }
+    }
+    if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+
+    // ---- query point of this lane ----
+    double xq[DIM];
+    double stepv[DIM];
+    if (state == ST_TRIAL) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) stepv[d] = alpha_n * gb[d];
+    } else if (state != ST_LIMIT) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) stepv[d] = 0.0;
+    } else {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) stepv[d] = g_trial[d];  // ST_LIMIT: g_trial temporarily holds the limited step
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) xq[d] = (xb[d] + stepv[d]) * prm.inv_len[d];
+
+    // ---- the expensive, warp-uniform part ----
+    double S0, SB, s[DIM];
+    eval_posterior<KERNEL, DIM, QP>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
+    if (state != ST_DONE) n_evals += 1;
+    const double fq = -(prm.mean + S0);
+    double gq[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gq[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
+
+    // ---- per-lane transitions (cheap) ----
+    bool finish_run = false;
+    if (state == ST_INIT) {
+      fb = fq;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gb[d] = gq[d];
+      finish_run = (prm.max_steps <= 0);
+      if (!finish_run) {
+        alpha_n = prm.alpha0[0];
+        search = 0;
+        gnorm = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
+        state = ST_TRIAL;
+      }
+    } else if (state == ST_TRIAL || state == ST_LIMIT) {
+      bool have_limit_eval = false;
+      double f_lim = 0.0;
+      if (state == ST_TRIAL) {
+        // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
+        const bool ok = (fq - fb) > 0.5 * alpha_n * gnorm;
+        if (!ok) {
+          alpha_n *= 0.5;
+          search += 1;
+        }
+        if (ok || search >= 30) {
+          if (search >= 30) {
+            // line search exhausted: the reference rejects the step and stops this run (:778-781)
+            finish_run = true;
+          } else {
+            // limit the accepted step to the domain; if unchanged, the trial evaluation IS the final evaluation
+            bool same = true;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+              const double raw = alpha_n * gb[d];
+              const double lim = (d < prm.ps) ? limit_step(raw, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+              same = same && (lim == raw);
+              stepv[d] = lim;
+            }
+            if (same) {
+              have_limit_eval = true;
+              f_lim = fq;
+            } else {
+              // need one more evaluation at the limited point: park the step in g_trial
+              f_trial = fq;
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) g_trial[d] = stepv[d];
+              state = ST_LIMIT;
+            }
+          }
+        }
+      } else {
+        have_limit_eval = true;
+        f_lim = fq;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) stepv[d] = g_trial[d];
+      }
+      if (have_limit_eval) {
+        if (f_lim <= fb) {
+          finish_run = true;  // no increase: restore the base point and stop (:778-781)
+        } else {
+          double ns = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            xb[d] += stepv[d];
+            gb[d] = gq[d];
+            ns = fma(stepv[d], stepv[d], ns);
+          }
+          fb = f_lim;
+          n_steps += 1;
+          step_i += 1;
+          if (sqrt(ns) < prm.step_tol || step_i >= prm.max_steps) {
+            finish_run = true;
+          } else {
+            alpha_n = prm.alpha0[step_i];
+            search = 0;
+            gnorm = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
+            state = ST_TRIAL;
+          }
+        }
+      }
+    }
+    if (finish_run) {
+      // restart logic of GradientDescentOptimizerLineSearch::Optimize (gpp_optimization.hpp:1255-1273)
+      double nd2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const double df = run0[d] - xb[d];
+        nd2 = fma(df, df, nd2);
+      }
+      restart_i += 1;
+      if (sqrt(nd2) <= prm.tol || restart_i >= prm.max_restarts || prm.max_steps <= 0) {
+        outVal[sample] = fb;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = xb[d] * prm.inv_len[d];
+        sample = atomicAdd(&next_sample, 1);
+        state = ST_FETCH;
+      } else {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) run0[d] = xb[d];
+        step_i = 0;
+        alpha_n = prm.alpha0[0];
+        search = 0;
+        gnorm = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
+        state = ST_TRIAL;
+      }
+    }
+  }
+  // integer counters: atomics keep the totals deterministic
+  n_evals = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(n_evals));
+  n_steps = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(n_steps));
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(prm.stats + 0, n_evals);
+    atomicAdd(prm.stats + 1, n_steps);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase 2: per-candidate accumulations over the samples' minimisers for the envelope-theorem gradient
+//   R[a][row] = sum_i c_ia k(row, x*_i)   (rows = training points then union points; fixed sample order)
+//   Gu[u][d]  = sum_i c_iu kb(Xu_u, x*_i) x~*_id ,  GkB[u] = sum_i c_iu kb(Xu_u, x*_i)
+// grid (row blocks, candidates); one thread per row.
+// ---------------------------------------------------------------------------------------------------------------
+template <int KERNEL, int DIM, int QP>
+__global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgAccParams prm) {
+  const int cand = blockIdx.y;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = prm.N, U = prm.U;
+  const bool active = row < N + U;
+  const bool is_u = row >= N;
+  double xr[DIM];
+  double pk0 = 0.0;
+  if (active) {
+    const double* src = is_u ? (prm.Xu + (static_cast<size_t>(cand) * U + (row - N)) * (DIM + 2))
+                             : (prm.Xt + static_cast<size_t>(row) * DIM);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) xr[d] = src[d];
+    if (is_u) {
+      pk0 = src[DIM];
+    } else {
+      double nrm = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) nrm = fma(xr[d], xr[d], nrm);
+      pk0 = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) ? (log(prm.alpha) - 0.5 * nrm) : nrm;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) xr[d] = 0.0;
+  }
+  double acc[QP];
+#pragma unroll
+  for (int a = 0; a < QP; ++a) acc[a] = 0.0;
+  double gu[DIM], gkb = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) gu[d] = 0.0;
+  const double* xs = prm.outX + static_cast<size_t>(cand) * prm.num_mc * DIM;
+  const double* cs = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
+  const int uu = is_u ? (row - N) : 0;
+  for (int i = 0; i < prm.num_mc; ++i) {
+    const double* xi = xs + static_cast<size_t>(i) * DIM;
+    const double* ci = cs + static_cast<size_t>(i) * QP;
+    double dot = 0.0, nq = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const double v = xi[d];
+      dot = fma(v, xr[d], dot);
+      nq = fma(v, v, nq);
+    }
+    double kv, kb;
+    kernel_pair<KERNEL>(dot, pk0, nq, prm.alpha, kv, kb);
+#pragma unroll
+    for (int a = 0; a < QP; ++a) acc[a] = fma(ci[a], kv, acc[a]);
+    if (is_u) {
+      double cu = 0.0;
+#pragma unroll
+      for (int a = 0; a < QP; ++a)
+        if (a == uu) cu = ci[a];
+      const double w = cu * kb;
+      gkb += w;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) gu[d] = fma(w, xi[d], gu[d]);
+    }
+  }
+  if (!active) return;
+  double* R = prm.R + static_cast<size_t>(cand) * QP * (N + U);
+#pragma unroll
+  for (int a = 0; a < QP; ++a) R[static_cast<size_t>(a) * (N + U) + row] = acc[a];
+  if (is_u) {
+    prm.GkB[static_cast<size_t>(cand) * U + uu] = gkb;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) prm.Gu[(static_cast<size_t>(cand) * U + uu) * DIM + d] = gu[d];
+  }
+}
+
+// launchers instantiated per (DIM) translation unit
+using KgMcLaunch = void (*)(const KgMcParams&, dim3 grid, size_t smem, cudaStream_t s);
+using KgAccLaunch = void (*)(const KgAccParams&, dim3 grid, cudaStream_t s);
+struct KgDispatchEntry {
+  int kernel, dim, qp;
+  KgMcLaunch mc;
+  KgAccLaunch acc;
+  size_t (*smem_bytes)(int N, int U);
+};
+void register_kg_entries(const KgDispatchEntry* entries, int count);
+const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q);
+
+template <int KERNEL, int DIM, int QP>
+void launch_kg_mc(const KgMcParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(kg_mc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  kg_mc_kernel<KERNEL, DIM, QP><<<grid, 256, smem, s>>>(p);
+}
+template <int KERNEL, int DIM, int QP>
+void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {
+  kg_acc_kernel<KERNEL, DIM, QP><<<grid, 128, 0, s>>>(p);
+}
+template <int DIM, int QP>
+size_t kg_smem_bytes(int N, int U) {
+  return (static_cast<size_t>(N) * (DIM + QP + 2) + static_cast<size_t>(U) * (DIM + 2)) * sizeof(double);
+}
+
+#define CMOE_KG_ENTRY(K, D, Q) \
+  { K, D, Q, &launch_kg_mc<K, D, Q>, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
+#define CMOE_KG_ENTRIES_FOR_DIM(D)                                                                              \
+  CMOE_KG_ENTRY(0, D, 2), CMOE_KG_ENTRY(0, D, 4), CMOE_KG_ENTRY(0, D, 8), CMOE_KG_ENTRY(0, D, 16),               \
+      CMOE_KG_ENTRY(1, D, 2), CMOE_KG_ENTRY(1, D, 4), CMOE_KG_ENTRY(1, D, 8), CMOE_KG_ENTRY(1, D, 16)
+
+}  // namespace cmoe
