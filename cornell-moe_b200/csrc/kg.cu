@@ -1,0 +1,728 @@
+// q-KG evaluation (value + envelope-theorem gradient), batched over candidates: host orchestration and the small
+// per-candidate kernels around the fused Monte-Carlo kernel of kg_mc.cuh.
+//
+// Replaces (reference, moe/optimal_learning/cpp/gpp_knowledge_gradient_optimization.{hpp,cpp}):
+//   KnowledgeGradientState ctor / PreCompute          .cpp:246-317
+//   KnowledgeGradientEvaluator::ComputeKnowledgeGradient      .cpp:69-115
+//   KnowledgeGradientEvaluator::ComputeGradKnowledgeGradient  .cpp:130-227
+//   EvaluateKGAtPointList                              .hpp:972-1013
+//
+// Pipeline per batch of candidates (everything asynchronous on one stream, inputs resident in HBM):
+//   posterior set-up (posterior.cu) -> discretisation-set statistics W = L^-1 Cov_n(Xu, A), mu_n(A)
+//   -> per-sample prep (normals, c = L^-T z, arg-min over the discretisation set)
+//   -> fused MC kernel (inner line-search optimisation of every sample)
+//   -> [gradient] accumulate R = sum_i k(X, x*_i) c_i^T, K^-1 R, contraction with dK*, dL  -> KG, grad KG.
+#include <algorithm>
+#include <cmath>
+
+#include "kg_mc.cuh"
+
+namespace cmoe {
+
+namespace {
+
+std::vector<KgDispatchEntry>& kg_table() {
+  static std::vector<KgDispatchEntry> t;
+  return t;
+}
+
+__device__ __forceinline__ int row_type(int local, const int* derivs) { return local ? derivs[local - 1] : -1; }
+
+// union sets on the device: P[c] = [candidate c ; points being sampled]
+__global__ void build_union_kernel(const double* __restrict__ cand, const double* __restrict__ Xp, int nc, int q, int p,
+                                   int dim, double* __restrict__ P) {
+  const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t per = static_cast<size_t>(q + p) * dim;
+  if (e >= per * nc) return;
+  const size_t c = e / per, r = e % per;
+  P[e] = (r < static_cast<size_t>(q) * dim) ? cand[c * q * dim + r] : Xp[r - static_cast<size_t>(q) * dim];
+}
+
+// scaled + zero-padded training points [N][DIMP]
+__global__ void pack_xt_kernel(const __grid_constant__ KernelSpec spec, const double* __restrict__ X, int N, int DIMP,
+                               double* __restrict__ Xt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * DIMP) return;
+  const int j = e / DIMP, d = e % DIMP;
+  Xt[e] = (d < spec.dim) ? X[static_cast<size_t>(j) * spec.dim + d] * spec.inv_len[d] : 0.0;
+}
+
+// per-candidate operand packs for the MC kernel (g == 0: rows == training points, Q == U)
+__global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int ps,
+                                                      int num_pts, int DIMP, int QP, const double* __restrict__ Xt,
+                                                      const double* __restrict__ beta, const double* __restrict__ B,
+                                                      const double* __restrict__ P, const double* __restrict__ D,
+                                                      double* __restrict__ Pk, double* __restrict__ Xu,
+                                                      double* __restrict__ A, double* __restrict__ Afull) {
+  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim;
+  const bool se = spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL;
+  const double lna = log(spec.alpha);
+  double* pk = Pk + static_cast<size_t>(c) * N * (QP + 2);
+  const double* Bc = B + static_cast<size_t>(c) * U * N;
+  for (int j = tid; j < N; j += blockDim.x) {
+    double nrm = 0.0;
+    for (int d = 0; d < DIMP; ++d) nrm = fma(Xt[j * DIMP + d], Xt[j * DIMP + d], nrm);
+    double* o = pk + static_cast<size_t>(j) * (QP + 2);
+    o[0] = se ? (lna - 0.5 * nrm) : nrm;
+    o[1] = beta[j];
+    for (int u = 0; u < QP; ++u) o[2 + u] = (u < U) ? Bc[static_cast<size_t>(u) * N + j] : 0.0;
+  }
+  const double* Pc = P + static_cast<size_t>(c) * U * dim;
+  double* xu = Xu + static_cast<size_t>(c) * U * (DIMP + 2);
+  for (int u = tid; u < U; u += blockDim.x) {
+    double nrm = 0.0;
+    for (int d = 0; d < DIMP; ++d) {
+      const double v = (d < dim) ? Pc[u * dim + d] * spec.inv_len[d] : 0.0;
+      xu[u * (DIMP + 2) + d] = v;
+      nrm = fma(v, v, nrm);
+    }
+    xu[u * (DIMP + 2) + DIMP] = se ? (lna - 0.5 * nrm) : nrm;
+    xu[u * (DIMP + 2) + DIMP + 1] = 0.0;
+  }
+  // discretisation set: [union (free coords) ; discrete_pts], fidelity coordinates pinned to 1.0 (...cpp:259-261, 365)
+  const int M = U + num_pts;
+  double* Ac = A + static_cast<size_t>(c) * M * DIMP;
+  double* Af = Afull + static_cast<size_t>(c) * U * dim;
+  for (int e = tid; e < M * DIMP; e += blockDim.x) {
+    const int j = e / DIMP, d = e % DIMP;
+    double v = 0.0;
+    if (d < ps) {
+      v = (j < U) ? Pc[j * dim + d] : D[static_cast<size_t>(j - U) * dim + d];
+    } else if (d < dim) {
+      v = 1.0;
+    }
+    Ac[e] = v;
+    if (j < U && d < dim) Af[j * dim + d] = v;
+  }
+}
+
+// W = L^-1 Cov_n(Xu, A), mu_n(A), best_posterior and its arg-min, one CTA per candidate.
+// KAu = K(X, A_union part) [n][nc*U], KD = K(X, D) [n][num_pts] (shared by all candidates), muD = mu_n(D).
+__global__ void __launch_bounds__(256) kg_discrete_kernel(const __grid_constant__ KernelSpec spec, int n, int U,
+                                                          int num_pts, int QP, double mean, double best_so_far,
+                                                          const double* __restrict__ beta,
+                                                          const double* __restrict__ P,
+                                                          const double* __restrict__ Afull,
+                                                          const double* __restrict__ D,
+                                                          const double* __restrict__ KAu,
+                                                          const double* __restrict__ KD,
+                                                          const double* __restrict__ muD,
+                                                          const double* __restrict__ B,
+                                                          const double* __restrict__ mu,
+                                                          const double* __restrict__ chol,
+                                                          const int* __restrict__ fail, double* __restrict__ W,
+                                                          double* __restrict__ muA, double* __restrict__ best_post,
+                                                          int* __restrict__ winner) {
+  extern __shared__ double sm[];
+  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, M = U + num_pts;
+  if (fail[c] != 0) return;
+  double* Ls = sm;  // [U][U] column-major
+  for (int e = tid; e < U * U; e += blockDim.x) Ls[e] = chol[static_cast<size_t>(c) * U * U + e];
+  __syncthreads();
+  const double* Pc = P + static_cast<size_t>(c) * U * dim;
+  const double* Bc = B + static_cast<size_t>(c) * U * n;
+  double* Wc = W + static_cast<size_t>(c) * M * QP;
+  for (int j = tid; j < M; j += blockDim.x) {
+    const double* kcol = (j < U) ? (KAu + (static_cast<size_t>(c) * U + j) * n) : (KD + static_cast<size_t>(j - U) * n);
+    const double* aj = (j < U) ? (Afull + (static_cast<size_t>(c) * U + j) * dim) : (D + static_cast<size_t>(j - U) * dim);
+    double m;
+    if (j < U) {
+      m = 0.0;
+      for (int r = 0; r < n; ++r) m += kcol[r] * beta[r];
+      m += mean;
+    } else {
+      m = muD[j - U];
+    }
+    muA[static_cast<size_t>(c) * M + j] = m;
+    double v[kMaxQ];
+    for (int a = 0; a < U; ++a) {
+      const double* ba = Bc + static_cast<size_t>(a) * n;
+      double t = 0.0;
+      for (int r = 0; r < n; ++r) t += ba[r] * kcol[r];
+      const double* pa = Pc + a * dim;
+      const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pa, aj));
+      v[a] = kp.A - t;
+    }
+    // forward substitution  L w = v
+    for (int a = 0; a < U; ++a) {
+      double t = v[a];
+      for (int b = 0; b < a; ++b) t -= Ls[a + b * U] * v[b];
+      v[a] = t / Ls[a + a * U];
+    }
+    for (int a = 0; a < QP; ++a) Wc[static_cast<size_t>(j) * QP + a] = (a < U) ? v[a] : 0.0;
+  }
+  if (tid == 0) {
+    // best_posterior = min(best_so_far, min_j mu_j) with the first strict minimiser (...cpp:146-153)
+    double bp = best_so_far;
+    int w = -1;
+    for (int j = 0; j < U; ++j) {
+      const double m = mu[static_cast<size_t>(c) * U + j];
+      if (m < bp) {
+        bp = m;
+        w = j;
+      }
+    }
+    best_post[c] = bp;
+    winner[c] = w;
+  }
+}
+
+// per sample: normals (antithetic pairs), c = L^-T z, arg-min of mu_n(A_j) + W_j . z over the discretisation set
+__global__ void __launch_bounds__(256) kg_prep_kernel(int U, int M, int QP, int num_mc, uint64_t seed,
+                                                      const double* __restrict__ table,
+                                                      const double* __restrict__ chol, const double* __restrict__ W,
+                                                      const double* __restrict__ muA, const int* __restrict__ fail,
+                                                      int w_in_smem, double* __restrict__ recC,
+                                                      int* __restrict__ recStart) {
+  extern __shared__ double sm[];
+  const int c = blockIdx.y;
+  if (fail[c] != 0) return;
+  double* Ls = sm;
+  double* Ws = sm + U * U;
+  double* ms = Ws + (w_in_smem ? static_cast<size_t>(M) * QP : 0);
+  for (int e = threadIdx.x; e < U * U; e += blockDim.x) Ls[e] = chol[static_cast<size_t>(c) * U * U + e];
+  const double* Wc = W + static_cast<size_t>(c) * M * QP;
+  const double* mc_ = muA + static_cast<size_t>(c) * M;
+  if (w_in_smem) {
+    for (int e = threadIdx.x; e < M * QP; e += blockDim.x) Ws[e] = Wc[e];
+    for (int e = threadIdx.x; e < M; e += blockDim.x) ms[e] = mc_[e];
+  }
+  __syncthreads();
+  const double* Wp = w_in_smem ? Ws : Wc;
+  const double* mp = w_in_smem ? ms : mc_;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= num_mc) return;
+  const int pair = s >> 1;
+  const double sign = (s & 1) ? -1.0 : 1.0;  // odd iterations reuse -z of the previous one (...cpp:88-97)
+  double z[kMaxQ];
+  if (table != nullptr) {
+    for (int i = 0; i < U; ++i) z[i] = sign * table[static_cast<size_t>(pair) * U + i];
+  } else {
+    for (int k = 0; 2 * k < U; ++k) {
+      double a, b;
+      philox_normal_pair(seed, static_cast<uint64_t>(pair), k, a, b);
+      z[2 * k] = sign * a;
+      if (2 * k + 1 < U) z[2 * k + 1] = sign * b;
+    }
+  }
+  // arg-min over the discretisation set (first strict minimiser, ...cpp:436-449)
+  int arg = 0;
+  double best = 0.0;
+  for (int j = 0; j < M; ++j) {
+    double v = mp[j];
+    for (int a = 0; a < U; ++a) v = fma(Wp[static_cast<size_t>(j) * QP + a], z[a], v);
+    if (j == 0 || best > v) {
+      best = v;
+      arg = j;
+    }
+  }
+  recStart[static_cast<size_t>(c) * num_mc + s] = arg;
+  // c = L^-T z (back substitution)
+  for (int a = U - 1; a >= 0; --a) {
+    double t = z[a];
+    for (int b = a + 1; b < U; ++b) t -= Ls[b + a * U] * z[b];
+    z[a] = t / Ls[a + a * U];
+  }
+  double* out = recC + (static_cast<size_t>(c) * num_mc + s) * QP;
+  for (int a = 0; a < QP; ++a) out[a] = (a < U) ? z[a] : 0.0;
+}
+
+// KG[c] = best_posterior + mean_i best_function_value_i ; fixed-order reduction
+__global__ void __launch_bounds__(256) kg_value_kernel(int num_mc, const double* __restrict__ outVal,
+                                                       const double* __restrict__ best_post,
+                                                       const int* __restrict__ fail, double* __restrict__ kg) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  if (fail[c] != 0) {
+    if (threadIdx.x == 0) kg[c] = nan("");
+    return;
+  }
+  const double* v = outVal + static_cast<size_t>(c) * num_mc;
+  double part = 0.0;
+  for (int s = threadIdx.x; s < num_mc; s += blockDim.x) part += v[s];
+  const double total = block_sum(part, red);
+  if (threadIdx.x == 0) kg[c] = best_post[c] + total / static_cast<double>(num_mc);
+}
+
+// T' [a', a] = R[a'][N + a] - sum_j R[a'][j] B[j, a]   (must run BEFORE R is overwritten by K^-1 R)
+__global__ void __launch_bounds__(256) kg_tprime_kernel(int N, int U, int QP, const double* __restrict__ R,
+                                                        const double* __restrict__ B, double* __restrict__ Tp) {
+  const int c = blockIdx.x;
+  const double* Rc = R + static_cast<size_t>(c) * QP * (N + U);
+  const double* Bc = B + static_cast<size_t>(c) * U * N;
+  for (int o = threadIdx.x; o < U * U; o += blockDim.x) {
+    const int ap = o / U, a = o % U;
+    const double* r = Rc + static_cast<size_t>(ap) * (N + U);
+    const double* b = Bc + static_cast<size_t>(a) * N;
+    double t = 0.0;
+    for (int j = 0; j < N; ++j) t += r[j] * b[j];
+    Tp[static_cast<size_t>(c) * U * U + o] = r[N + a] - t;
+  }
+}
+
+// grad KG[c][p][d] = [p == winner] dmu_p[d] - (1/mc) ( G1 - sum_j dK*[d,j,p] (K^-1 R)[j,p] - <dL_pd, T> )
+__global__ void __launch_bounds__(128) kg_grad_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int q,
+                                                      int QP, int DIMP, int num_mc, const double* __restrict__ X,
+                                                      const double* __restrict__ P, const double* __restrict__ Xu,
+                                                      const double* __restrict__ R, const double* __restrict__ Tp,
+                                                      const double* __restrict__ Gu, const double* __restrict__ GkB,
+                                                      const double* __restrict__ chol,
+                                                      const double* __restrict__ gchol,
+                                                      const double* __restrict__ gmu, const int* __restrict__ winner,
+                                                      const int* __restrict__ fail, double* __restrict__ grad) {
+  extern __shared__ double sm[];
+  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim;
+  if (fail[c] != 0) return;
+  double* T = sm;  // [U][U] row a', col b
+  // T L^T = T'  ->  row-wise forward substitution
+  for (int ap = tid; ap < U; ap += blockDim.x) {
+    for (int b = 0; b < U; ++b) {
+      double t = Tp[static_cast<size_t>(c) * U * U + ap * U + b];
+      for (int m = 0; m < b; ++m) t -= T[ap * U + m] * chol[static_cast<size_t>(c) * U * U + b + m * U];
+      T[ap * U + b] = t / chol[static_cast<size_t>(c) * U * U + b + b * U];
+    }
+  }
+  __syncthreads();
+  const double* Pc = P + static_cast<size_t>(c) * U * dim;
+  const double* Rc = R + static_cast<size_t>(c) * QP * (N + U);
+  for (int o = tid; o < q * dim; o += blockDim.x) {
+    const int p = o / dim, d = o % dim;
+    const double* xu = Xu + (static_cast<size_t>(c) * U + p) * (DIMP + 2);
+    const double t1 = spec.inv_len[d] * (Gu[(static_cast<size_t>(c) * U + p) * DIMP + d] -
+                                         xu[d] * GkB[static_cast<size_t>(c) * U + p]);
+    const double* pp = Pc + p * dim;
+    const double* kr = Rc + static_cast<size_t>(p) * (N + U);  // (K^-1 R)[:, p]
+    double t2 = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double* xj = X + static_cast<size_t>(j) * dim;
+      const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pp, xj));
+      t2 += grad_cov_entry(spec, kp, pp, xj, -1, -1, d) * kr[j];
+    }
+    const double* G = gchol + (static_cast<size_t>(c) * q + p) * U * U * dim;
+    double t3 = 0.0;
+    for (int a = 0; a < U; ++a)
+      for (int b = 0; b <= a; ++b) t3 += G[(static_cast<size_t>(a) * U + b) * dim + d] * T[a * U + b];
+    double g = -(t1 - t2 - t3) / static_cast<double>(num_mc);
+    if (winner[c] == p) g += gmu[(static_cast<size_t>(c) * q + p) * dim + d];
+    grad[(static_cast<size_t>(c) * q + p) * dim + d] = g;
+  }
+}
+
+__global__ void mean_of_points_kernel(int n, int num, double mean, const double* __restrict__ Kcols,
+                                      const double* __restrict__ beta, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= num) return;
+  const double* k = Kcols + static_cast<size_t>(j) * n;
+  double t = 0.0;
+  for (int r = 0; r < n; ++r) t += k[r] * beta[r];
+  out[j] = mean + t;
+}
+
+}  // namespace
+
+void register_kg_entries(const KgDispatchEntry* entries, int count) {
+  for (int i = 0; i < count; ++i) kg_table().push_back(entries[i]);
+}
+
+const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q) {
+  const KgDispatchEntry* best = nullptr;
+  for (const auto& e : kg_table()) {
+    if (e.kernel != kernel || e.dim < dim || e.qp < Q) continue;
+    if (!best || e.dim < best->dim || (e.dim == best->dim && e.qp < best->qp)) best = &e;
+  }
+  return best;
+}
+
+}  // namespace cmoe
+
+using namespace cmoe;  // NOLINT
+
+// -----------------------------------------------------------------------------------------------------------------
+// the device-resident plan
+// -----------------------------------------------------------------------------------------------------------------
+struct cmoe_kg_plan {
+  const cmoe_gp* gp = nullptr;
+  int nf = 0, num_pts = 0, max_cand = 0, q = 0, p = 0, U = 0, num_mc = 0, ps = 0, M = 0;
+  bool want_grad = false;
+  double best_so_far = 0.0;
+  uint64_t seed = 0;
+  cmoe_gd_params inner{};
+  const KgDispatchEntry* entry = nullptr;
+  int DIMP = 0, QP = 0, batch = 0, nc = 0;
+  bool use_smem = true;
+  int chunk = 0;
+  // static device data
+  DevBuf<double> dXt, dD, dKD, dMuD, dAlpha0, dTable, dXp, dCand;
+  KgMcParams mcp{};
+  // per-batch device scratch
+  PosteriorBatch pb;
+  DevBuf<double> dPk, dXu, dA, dAfull, dKAu, dW, dMuA, dBestPost, dRecC, dOutVal, dOutX, dR, dGu, dGkB, dTp;
+  DevBuf<int> dWinner, dRecStart;
+  DevBuf<unsigned long long> dStats;
+  // results
+  DevBuf<double> dKG, dGrad;
+  DevBuf<int> dFailAll;
+  EventTimer t_total, t_mc;
+  double mc_ms_accum = 0.0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> mc_events;
+  int launches = 0;
+  ~cmoe_kg_plan() {
+    for (auto& e : mc_events) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+  }
+};
+
+namespace {
+
+void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
+  const cmoe_gp& gp = *pl.gp;
+  const KernelSpec& spec = gp.spec;
+  cudaStream_t s = gp.stream;
+  const int N = gp.N, n = gp.n, dim = spec.dim, U = pl.U, q = pl.q, p = pl.p, M = pl.M, QP = pl.QP, DIMP = pl.DIMP;
+  const int mc = pl.num_mc;
+  PosteriorBatch& pb = pl.pb;
+  pb.configure(gp, nb, U, spec.derivs, spec.g, pl.want_grad ? q : 0, s);
+  {
+    const size_t tot = static_cast<size_t>(nb) * U * dim;
+    build_union_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(
+        pl.dCand.p + static_cast<size_t>(c0) * q * dim, pl.dXp.p, nb, q, p, dim, pb.P.p);
+    count_launch();
+  }
+  pb.run(gp, /*diag_mode=*/2, /*want_chol=*/true, pl.want_grad, s);
+  CMOE_CUDA(cudaMemcpyAsync(pl.dFailAll.p + c0, pb.fail.p, nb * sizeof(int), cudaMemcpyDeviceToDevice, s));
+
+  kg_pack_kernel<<<nb, 256, 0, s>>>(spec, N, U, pl.ps, pl.num_pts, DIMP, QP, pl.dXt.p, gp.dKinvY.p, pb.B.p, pb.P.p,
+                                    pl.dD.p, pl.dPk.p, pl.dXu.p, pl.dA.p, pl.dAfull.p);
+  count_launch();
+  // K(X, A_union) for all candidates of the batch (value rows only)
+  build_mix_covariance(spec, gp.dX.p, N, pl.dAfull.p, nb * U, nullptr, 0, pl.dKAu.p, s);
+  const size_t smem_d = static_cast<size_t>(U) * U * sizeof(double);
+  kg_discrete_kernel<<<nb, 256, smem_d, s>>>(spec, n, U, pl.num_pts, QP, gp.mean, pl.best_so_far, gp.dKinvY.p, pb.P.p,
+                                             pl.dAfull.p, pl.dD.p, pl.dKAu.p, pl.dKD.p, pl.dMuD.p, pb.B.p, pb.mu.p,
+                                             pb.chol.p, pb.fail.p, pl.dW.p, pl.dMuA.p, pl.dBestPost.p, pl.dWinner.p);
+  count_launch();
+  const size_t w_bytes = (static_cast<size_t>(M) * QP + M) * sizeof(double);
+  const int w_in_smem = (w_bytes + smem_d) <= 160 * 1024;
+  const size_t smem_p = smem_d + (w_in_smem ? w_bytes : 0);
+  CMOE_CUDA(cudaFuncSetAttribute(kg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+  kg_prep_kernel<<<dim3((mc + 255) / 256, nb), 256, smem_p, s>>>(U, M, QP, mc, pl.seed,
+                                                                 pl.dTable.count ? pl.dTable.p : nullptr, pb.chol.p,
+                                                                 pl.dW.p, pl.dMuA.p, pb.fail.p, w_in_smem, pl.dRecC.p,
+                                                                 pl.dRecStart.p);
+  count_launch();
+
+  KgMcParams prm = pl.mcp;
+  prm.Pk = pl.dPk.p;
+  prm.Xu = pl.dXu.p;
+  prm.A = pl.dA.p;
+  prm.recC = pl.dRecC.p;
+  prm.recStart = pl.dRecStart.p;
+  prm.outVal = pl.dOutVal.p;
+  prm.outX = pl.dOutX.p;
+  prm.stats = pl.dStats.p;
+  const int chunks = (mc + pl.chunk - 1) / pl.chunk;
+  const size_t smem_mc = pl.use_smem ? pl.entry->smem_bytes(N, U) : 0;
+  cudaEventRecord(pl.mc_events[ev_idx].first, s);
+  pl.entry->mc(prm, dim3(chunks, nb), smem_mc, s);
+  cudaEventRecord(pl.mc_events[ev_idx].second, s);
+  count_launch();
+  kg_value_kernel<<<nb, 256, 0, s>>>(mc, pl.dOutVal.p, pl.dBestPost.p, pb.fail.p, pl.dKG.p + c0);
+  count_launch();
+
+  if (pl.want_grad) {
+    KgAccParams ap{};
+    ap.N = N;
+    ap.U = U;
+    ap.dim = dim;
+    ap.num_mc = mc;
+    ap.alpha = spec.alpha;
+    ap.Xt = pl.dXt.p;
+    ap.Xu = pl.dXu.p;
+    ap.recC = pl.dRecC.p;
+    ap.outX = pl.dOutX.p;
+    ap.R = pl.dR.p;
+    ap.Gu = pl.dGu.p;
+    ap.GkB = pl.dGkB.p;
+    CMOE_CUDA(cudaMemsetAsync(pl.dR.p, 0, static_cast<size_t>(nb) * QP * (N + U) * sizeof(double), s));
+    pl.entry->acc(ap, dim3((N + U + 127) / 128, nb), s);
+    kg_tprime_kernel<<<nb, 256, 0, s>>>(N, U, QP, pl.dR.p, pb.B.p, pl.dTp.p);
+    count_launch(2);
+    // K^-1 R: columns of length N with stride N+U, nb*QP of them
+    potrs_lower(gp.dK.p, n, pl.dR.p, N + U, nb * QP, s);
+    kg_grad_kernel<<<nb, 128, static_cast<size_t>(U) * U * sizeof(double), s>>>(
+        spec, N, U, q, QP, DIMP, mc, gp.dX.p, pb.P.p, pl.dXu.p, pl.dR.p, pl.dTp.p, pl.dGu.p, pl.dGkB.p, pb.chol.p,
+        pb.gchol.p, pb.gmu.p, pl.dWinner.p, pb.fail.p, pl.dGrad.p + static_cast<size_t>(c0) * q * dim);
+    count_launch();
+  }
+  CMOE_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
+int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* inner, const double* inner_bounds,
+                        const double* discrete_pts, int num_pts, int max_candidates, int q,
+                        const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                        int want_grad, cmoe_kg_plan** plan_out) {
+  if (plan_out) *plan_out = nullptr;
+  return guarded(nullptr, [&] {
+    CMOE_REQUIRE(plan_out != nullptr, CMOE_ERR_INVALID_VALUE, "plan_out is NULL");
+    CMOE_REQUIRE(max_candidates >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    CMOE_REQUIRE(q >= 1 && p >= 0 && num_mc >= 1 && num_pts >= 0, CMOE_ERR_BOUNDS, "bad sizes");
+    const KernelSpec& spec = gp->spec;
+    const int dim = spec.dim;
+    CMOE_REQUIRE(num_fidelity >= 0 && num_fidelity < dim, CMOE_ERR_BOUNDS, "num_fidelity out of range");
+    CMOE_REQUIRE(spec.g == 0, CMOE_ERR_INVALID_VALUE,
+                 "knowledge gradient with derivative observations (d-KG) is not implemented in this build");
+    CMOE_REQUIRE(inner->max_num_steps <= 4096, CMOE_ERR_BOUNDS, "inner max_num_steps must be <= 4096");
+    require_device(gp->device);
+    std::unique_ptr<cmoe_kg_plan> pl(new cmoe_kg_plan());
+    pl->gp = gp;
+    pl->nf = num_fidelity;
+    pl->num_pts = num_pts;
+    pl->max_cand = max_candidates;
+    pl->q = q;
+    pl->p = p;
+    pl->U = q + p;
+    pl->num_mc = num_mc;
+    pl->ps = dim - num_fidelity;
+    pl->M = pl->U + num_pts;
+    pl->want_grad = want_grad != 0;
+    pl->best_so_far = best_so_far;
+    pl->seed = seed;
+    pl->inner = *inner;
+    const int U = pl->U, N = gp->N, n = gp->n, ps = pl->ps;
+    for (int d = 0; d < ps; ++d)
+      CMOE_REQUIRE(inner_bounds[2 * d] <= inner_bounds[2 * d + 1], CMOE_ERR_BOUNDS, "Tensor product region is EMPTY.");
+    pl->entry = find_kg_entry(spec.kernel, dim, U);
+    CMOE_REQUIRE(pl->entry != nullptr, CMOE_ERR_BOUNDS, "q+p exceeds the largest compiled q-KG kernel (16)");
+    pl->DIMP = pl->entry->dim;
+    pl->QP = pl->entry->qp;
+    const int DIMP = pl->DIMP, QP = pl->QP;
+    cudaStream_t s = gp->stream;
+
+    // static data: scaled training points, discrete set (full dim, fidelity coords = 1), K(X, D), mu_n(D)
+    pl->dXt.alloc(static_cast<size_t>(N) * DIMP);
+    pack_xt_kernel<<<(N * DIMP + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, N, DIMP, pl->dXt.p);
+    std::vector<double> hD(static_cast<size_t>(std::max(1, num_pts)) * dim, 1.0);
+    for (int j = 0; j < num_pts; ++j)
+      for (int d = 0; d < ps; ++d) hD[static_cast<size_t>(j) * dim + d] = discrete_pts[static_cast<size_t>(j) * ps + d];
+    pl->dD.upload(hD.data(), hD.size(), s);
+    pl->dKD.alloc(static_cast<size_t>(n) * std::max(1, num_pts));
+    pl->dMuD.alloc(std::max(1, num_pts));
+    if (num_pts > 0) {
+      build_mix_covariance(spec, gp->dX.p, N, pl->dD.p, num_pts, nullptr, 0, pl->dKD.p, s);
+      mean_of_points_kernel<<<(num_pts + 127) / 128, 128, 0, s>>>(n, num_pts, gp->mean, pl->dKD.p, gp->dKinvY.p,
+                                                                  pl->dMuD.p);
+    }
+    std::vector<double> a0(std::max(1, inner->max_num_steps));
+    for (int i = 0; i < inner->max_num_steps; ++i)
+      a0[i] = inner->pre_mult * std::pow(static_cast<double>(i + 1), -inner->gamma);  // gpp_optimization.hpp:736
+    pl->dAlpha0.upload(a0.data(), a0.size(), s);
+    std::vector<double> hXp(static_cast<size_t>(std::max(1, p)) * dim, 0.0);
+    if (p) std::copy(points_being_sampled, points_being_sampled + static_cast<size_t>(p) * dim, hXp.begin());
+    pl->dXp.upload(hXp.data(), hXp.size(), s);
+    pl->dCand.alloc(static_cast<size_t>(max_candidates) * q * dim);
+    CMOE_CUDA(cudaStreamSynchronize(s));
+
+    // work decomposition
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem_need = pl->entry->smem_bytes(N, U);
+    pl->use_smem = smem_need <= 200 * 1024;
+    // candidates per batch bounded by ~3 GiB of per-sample records
+    const size_t per_cand = static_cast<size_t>(num_mc) * (QP + DIMP + 2) * sizeof(double) +
+                            static_cast<size_t>(n) * U * 4 * sizeof(double);
+    pl->batch = static_cast<int>(std::max<size_t>(1, std::min<size_t>(max_candidates, (size_t(3) << 30) / per_cand)));
+    // samples per CTA: aim for >= ~8 waves of CTAs over the whole batch, at least 512 samples (2 per lane) per CTA
+    {
+      const long long target_ctas = 8LL * sms * 2;
+      long long chunk = (static_cast<long long>(pl->batch) * num_mc + target_ctas - 1) / target_ctas;
+      chunk = std::max<long long>(512, std::min<long long>(chunk, 4096));
+      chunk = (chunk + 255) / 256 * 256;
+      pl->chunk = static_cast<int>(std::min<long long>(chunk, (num_mc + 255) / 256 * 256));
+    }
+    const int B = pl->batch;
+    pl->dPk.alloc(static_cast<size_t>(B) * N * (QP + 2));
+    pl->dXu.alloc(static_cast<size_t>(B) * U * (DIMP + 2));
+    pl->dA.alloc(static_cast<size_t>(B) * pl->M * DIMP);
+    pl->dAfull.alloc(static_cast<size_t>(B) * U * dim);
+    pl->dKAu.alloc(static_cast<size_t>(B) * U * n);
+    pl->dW.alloc(static_cast<size_t>(B) * pl->M * QP);
+    pl->dMuA.alloc(static_cast<size_t>(B) * pl->M);
+    pl->dBestPost.alloc(B);
+    pl->dWinner.alloc(B);
+    pl->dRecC.alloc(static_cast<size_t>(B) * num_mc * QP);
+    pl->dRecStart.alloc(static_cast<size_t>(B) * num_mc);
+    pl->dOutVal.alloc(static_cast<size_t>(B) * num_mc);
+    pl->dOutX.alloc(static_cast<size_t>(B) * num_mc * DIMP);
+    pl->dStats.alloc(2);
+    if (pl->want_grad) {
+      pl->dR.alloc(static_cast<size_t>(B) * QP * (N + U));
+      pl->dGu.alloc(static_cast<size_t>(B) * U * DIMP);
+      pl->dGkB.alloc(static_cast<size_t>(B) * U);
+      pl->dTp.alloc(static_cast<size_t>(B) * U * U);
+    }
+    pl->dKG.alloc(max_candidates);
+    pl->dGrad.alloc(pl->want_grad ? static_cast<size_t>(max_candidates) * q * dim : 1);
+    pl->dFailAll.alloc(max_candidates);
+    const int nbatches = (max_candidates + B - 1) / B;
+    pl->mc_events.resize(nbatches);
+    for (auto& e : pl->mc_events) {
+      cudaEventCreate(&e.first);
+      cudaEventCreate(&e.second);
+    }
+
+    KgMcParams& m = pl->mcp;
+    m.N = N;
+    m.U = U;
+    m.ps = ps;
+    m.dim = dim;
+    m.M = pl->M;
+    m.num_mc = num_mc;
+    m.chunk = pl->chunk;
+    m.use_smem = pl->use_smem ? 1 : 0;
+    m.max_steps = inner->max_num_steps;
+    m.max_restarts = inner->max_num_restarts;
+    m.mean = gp->mean;
+    m.mrc = inner->max_relative_change;
+    m.tol = inner->tolerance;
+    m.step_tol = inner->max_num_steps > 0 ? inner->tolerance / static_cast<double>(inner->max_num_steps) : 0.0;
+    m.alpha = spec.alpha;
+    m.Xt = pl->dXt.p;
+    m.alpha0 = pl->dAlpha0.p;
+    for (int d = 0; d < CMOE_MAX_DIM; ++d) {
+      m.lo[d] = -1.0e300;
+      m.hi[d] = 1.0e300;
+      m.inv_len[d] = (d < dim) ? spec.inv_len[d] : 0.0;
+      m.len[d] = (d < dim) ? 1.0 / spec.inv_len[d] : 0.0;
+    }
+    for (int d = 0; d < ps; ++d) {
+      m.lo[d] = inner_bounds[2 * d];
+      m.hi[d] = inner_bounds[2 * d + 1];
+    }
+    *plan_out = pl.release();
+  });
+}
+
+void cmoe_kg_plan_destroy(cmoe_kg_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->gp->device);
+  delete plan;
+}
+
+int cmoe_kg_plan_set_table(cmoe_kg_plan* plan, const double* table, int table_len) {
+  return guarded(nullptr, [&] {
+    require_device(plan->gp->device);
+    const int need = ((plan->num_mc + 1) / 2) * plan->U;
+    CMOE_REQUIRE(table_len >= need, CMOE_ERR_INVALID_VALUE, "All random numbers stored in the RNG have been used up!");
+    plan->dTable.upload(table, table_len, plan->gp->stream);
+    CMOE_CUDA(cudaStreamSynchronize(plan->gp->stream));
+  });
+}
+
+int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_candidates) {
+  return guarded(nullptr, [&] {
+    CMOE_REQUIRE(num_candidates >= 1 && num_candidates <= plan->max_cand, CMOE_ERR_BOUNDS,
+                 "num_candidates exceeds the plan capacity");
+    require_device(plan->gp->device);
+    plan->nc = num_candidates;
+    plan->dCand.upload(candidates, static_cast<size_t>(num_candidates) * plan->q * plan->gp->spec.dim,
+                       plan->gp->stream);
+  });
+}
+
+int cmoe_kg_plan_run(cmoe_kg_plan* plan) {
+  return guarded(nullptr, [&] {
+    CMOE_REQUIRE(plan->nc >= 1, CMOE_ERR_INVALID_VALUE, "no candidates uploaded");
+    require_device(plan->gp->device);
+    cudaStream_t s = plan->gp->stream;
+    const int l0 = launches_issued();
+    plan->t_total.start(s);
+    CMOE_CUDA(cudaMemsetAsync(plan->dStats.p, 0, 2 * sizeof(unsigned long long), s));
+    size_t ev = 0;
+    for (int c0 = 0; c0 < plan->nc; c0 += plan->batch, ++ev)
+      plan_run_batch(*plan, c0, std::min(plan->batch, plan->nc - c0), ev);
+    plan->t_total.stop(s);
+    plan->launches = launches_issued() - l0;
+  });
+}
+
+int cmoe_kg_plan_sync(cmoe_kg_plan* plan, int* info) {
+  return guarded(info, [&] {
+    require_device(plan->gp->device);
+    cudaStream_t s = plan->gp->stream;
+    std::vector<int> f(plan->nc);
+    plan->dFailAll.download(f.data(), plan->nc, s);
+    CMOE_CUDA(cudaStreamSynchronize(s));
+    for (int c = 0; c < plan->nc; ++c)
+      if (f[c] != 0)
+        throw Error(CMOE_ERR_SINGULAR,
+                    "GP-Variance matrix singular. Check for duplicate points_to_sample/being_sampled or "
+                    "points_to_sample/being_sampled duplicating points_sampled with 0 noise.",
+                    f[c]);
+  });
+}
+
+int cmoe_kg_plan_download(cmoe_kg_plan* plan, double* kg, double* grad_kg, cmoe_kg_stats* stats) {
+  return guarded(nullptr, [&] {
+    require_device(plan->gp->device);
+    cudaStream_t s = plan->gp->stream;
+    if (kg) plan->dKG.download(kg, plan->nc, s);
+    if (grad_kg) {
+      CMOE_REQUIRE(plan->want_grad, CMOE_ERR_INVALID_VALUE, "plan was created without gradients");
+      plan->dGrad.download(grad_kg, static_cast<size_t>(plan->nc) * plan->q * plan->gp->spec.dim, s);
+    }
+    unsigned long long st[2] = {0, 0};
+    if (stats) CMOE_CUDA(cudaMemcpyAsync(st, plan->dStats.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+    CMOE_CUDA(cudaStreamSynchronize(s));
+    if (stats) {
+      stats->mc_samples = static_cast<uint64_t>(plan->nc) * plan->num_mc;
+      stats->posterior_evals = st[0];
+      stats->line_search_steps = st[1];
+    }
+  });
+}
+
+int cmoe_kg_plan_timings(const cmoe_kg_plan* plan, double* total_ms, double* mc_kernel_ms, int* launches) {
+  return guarded(nullptr, [&] {
+    require_device(plan->gp->device);
+    cmoe_kg_plan* pl = const_cast<cmoe_kg_plan*>(plan);
+    if (total_ms) *total_ms = pl->t_total.ms();
+    if (mc_kernel_ms) {
+      double t = 0.0;
+      const int nbatches = (plan->nc + plan->batch - 1) / plan->batch;
+      for (int b = 0; b < nbatches; ++b) {
+        float ms = 0.f;
+        cudaEventSynchronize(pl->mc_events[b].second);
+        cudaEventElapsedTime(&ms, pl->mc_events[b].first, pl->mc_events[b].second);
+        t += ms;
+      }
+      *mc_kernel_ms = t;
+    }
+    if (launches) *launches = plan->launches;
+  });
+}
+
+int cmoe_kg_eval(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* inner, const double* inner_bounds,
+                 const double* discrete_pts, int num_pts, const double* candidates, int num_candidates, int q,
+                 const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                 const double* normals_table, double* kg, double* grad_kg, cmoe_kg_stats* stats, int* info) {
+  cmoe_kg_plan* plan = nullptr;
+  int rc = cmoe_kg_plan_create(gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_candidates, q,
+                               points_being_sampled, p, num_mc, best_so_far, seed, grad_kg != nullptr, &plan);
+  if (rc != CMOE_OK) return rc;
+  if (normals_table) rc = cmoe_kg_plan_set_table(plan, normals_table, ((num_mc + 1) / 2) * (q + p));
+  if (rc == CMOE_OK) rc = cmoe_kg_plan_upload(plan, candidates, num_candidates);
+  if (rc == CMOE_OK) rc = cmoe_kg_plan_run(plan);
+  if (rc == CMOE_OK) rc = cmoe_kg_plan_sync(plan, info);
+  if (rc == CMOE_OK) rc = cmoe_kg_plan_download(plan, kg, grad_kg, stats);
+  cmoe_kg_plan_destroy(plan);
+  return rc;
+}
+
+}  // extern "C"

@@ -137,6 +137,8 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
                         const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
                         int want_grad, cmoe_kg_plan** plan_out);
 void cmoe_kg_plan_destroy(cmoe_kg_plan* plan);
+/* Optional table replay (NormalRNGSimulator semantics): ((num_mc+1)/2)*(q+p) normals; replaces the Philox stream. */
+int cmoe_kg_plan_set_table(cmoe_kg_plan* plan, const double* normals_table, int table_len);
 int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_candidates);
 int cmoe_kg_plan_run(cmoe_kg_plan* plan);
 int cmoe_kg_plan_sync(cmoe_kg_plan* plan, int* info);
@@ -148,9 +150,10 @@ int cmoe_kg_plan_timings(const cmoe_kg_plan* plan, double* total_ms, double* mc_
  * KG at every start -> keep the best 20 (hard-coded `k = 20`, :901) -> restarted gradient descent with LimitUpdate on
  * each (gpp_optimization.hpp:620-705, 1144-1185) -> strict-> argmax (gpp_optimization.hpp:1511, 1540).
  * Python boundary multistart_knowledge_gradient_optimization (gpp_python_knowledge_gradient.cpp:243-304).
- * shard_rank / shard_count select this process's share of the starts (candidate c belongs to rank c % count); the caller
- * (one process per GPU) exchanges the per-start values with one collective — see cornell_moe_b200/multigpu.py.
- * start_values (may be NULL) receives KG at every start owned by this shard (others untouched).
+ * This entry point runs the whole pipeline on one GPU.  With one process per GPU the same pipeline is sharded over
+ * the starts by cornell_moe_b200/multigpu.py: cmoe_kg_eval on this rank's starts -> one all-gather of the values ->
+ * identical top-20 on every rank -> cmoe_kg_gradient_descent on this rank's share -> one all-gather -> arg-max.
+ * start_values (may be NULL) receives KG at every start.
  * best_value / best_point[q*dim] / found_flag follow OptimizationIOContainer (gpp_optimization.hpp:511). */
 int cmoe_multistart_kg(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
                        const double* domain_bounds, const double* inner_bounds, const double* discrete_pts, int num_pts,
