@@ -266,3 +266,148 @@ class GaussianProcess:
             res.append({"mc_samples": st.mc_samples, "posterior_evals": st.posterior_evals,
                         "line_search_steps": st.line_search_steps})
         return res[0] if len(res) == 1 else tuple(res)
+
+
+def fp64_peaks(device=0):
+    """Measured FP64 peaks (TFLOP/s): (DFMA vector pipe, DMMA tensor pipe)."""
+    t = np.zeros(2)
+    _check(lib().cmoe_bench_fp64_peaks(int(device), _d(t)))
+    return float(t[0]), float(t[1])
+
+
+class KGPlan:
+    """Device-resident q-KG evaluation plan (cmoe_kg_plan_*): create -> upload -> run -> sync -> download."""
+
+    def __init__(self, gp, num_mc, best_so_far, inner, inner_bounds, discrete_pts, max_candidates, q, Xp=None,
+                 num_fidelity=0, seed=0, want_grad=True, table=None):
+        self.gp = gp
+        self.q = q
+        self.dim = gp.dim
+        self.want_grad = want_grad
+        Xp = _f64(Xp).reshape(-1, gp.dim) if Xp is not None and len(Xp) else np.zeros((0, gp.dim))
+        inner = GDParams.from_seq(inner)
+        inner_bounds = _f64(inner_bounds).ravel()
+        disc = _f64(discrete_pts).reshape(-1, gp.dim - num_fidelity)
+        h = ctypes.c_void_p()
+        rc = lib().cmoe_kg_plan_create(gp.h, int(num_fidelity), ctypes.byref(inner), _d(inner_bounds), _d(disc),
+                                       disc.shape[0], int(max_candidates), int(q), _d(Xp), Xp.shape[0], int(num_mc),
+                                       ctypes.c_double(best_so_far), ctypes.c_uint64(seed), int(bool(want_grad)),
+                                       ctypes.byref(h))
+        self.h = None
+        _check(rc)
+        self.h = h
+        self.nc = 0
+        if table is not None:
+            table = _f64(table).ravel()
+            _check(lib().cmoe_kg_plan_set_table(self.h, _d(table), table.size))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().cmoe_kg_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def upload(self, candidates):
+        cand = _f64(candidates).reshape(-1, self.q, self.dim)
+        self.nc = cand.shape[0]
+        _check(lib().cmoe_kg_plan_upload(self.h, _d(cand), self.nc))
+
+    def run(self):
+        _check(lib().cmoe_kg_plan_run(self.h))
+
+    def sync(self):
+        info = ctypes.c_int(0)
+        _check(lib().cmoe_kg_plan_sync(self.h, ctypes.byref(info)), info.value)
+
+    def download(self):
+        kg = np.empty(self.nc)
+        g = np.empty((self.nc, self.q, self.dim)) if self.want_grad else None
+        st = KGStats()
+        _check(lib().cmoe_kg_plan_download(self.h, _d(kg), _d(g), ctypes.byref(st)))
+        return kg, g, {"mc_samples": st.mc_samples, "posterior_evals": st.posterior_evals,
+                       "line_search_steps": st.line_search_steps}
+
+    def timings(self):
+        total, mc = ctypes.c_double(), ctypes.c_double()
+        launches = ctypes.c_int()
+        _check(lib().cmoe_kg_plan_timings(self.h, ctypes.byref(total), ctypes.byref(mc), ctypes.byref(launches)))
+        return total.value, mc.value, launches.value
+
+
+def _gd_args(gp, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_fidelity):
+    return (GDParams.from_seq(outer), GDParams.from_seq(inner) if inner is not None else None,
+            _f64(domain_bounds).ravel(), _f64(inner_bounds).ravel() if inner_bounds is not None else None,
+            _f64(discrete_pts).reshape(-1, gp.dim - num_fidelity) if discrete_pts is not None else None)
+
+
+def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
+                  num_fidelity=0, seed=0):
+    """cmoe_multistart_kg: returns (best_point [q, dim], best_value, found_flag, start_values)."""
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    outer, inner, db, ib, disc = _gd_args(gp, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_fidelity)
+    vals = np.empty(ns)
+    best = np.empty((q, dim))
+    bv = ctypes.c_double()
+    found = ctypes.c_int()
+    info = ctypes.c_int()
+    rc = lib().cmoe_multistart_kg(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db), _d(ib),
+                                  _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0], int(num_mc),
+                                  ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals), _d(best),
+                                  ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+    _check(rc, info.value)
+    return best, bv.value, bool(found.value), vals
+
+
+def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0):
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    outer = GDParams.from_seq(outer)
+    db = _f64(domain_bounds).ravel()
+    vals = np.empty(ns)
+    best = np.empty((q, dim))
+    bv = ctypes.c_double()
+    found = ctypes.c_int()
+    info = ctypes.c_int()
+    rc = lib().cmoe_multistart_ei(gp.h, ctypes.byref(outer), _d(db), _d(starts), ns, q, _d(Xp), Xp.shape[0],
+                                  int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals), _d(best),
+                                  ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+    _check(rc, info.value)
+    return best, bv.value, bool(found.value), vals
+
+
+def kg_gradient_descent(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
+                        num_fidelity=0, seed=0):
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    outer, inner, db, ib, disc = _gd_args(gp, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_fidelity)
+    vals = np.empty(ns)
+    pts = np.empty((ns, q, dim))
+    info = ctypes.c_int()
+    rc = lib().cmoe_kg_gradient_descent(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db),
+                                        _d(ib), _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0],
+                                        int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals),
+                                        _d(pts), ctypes.byref(info))
+    _check(rc, info.value)
+    return vals, pts
+
+
+def ei_gradient_descent(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0):
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    outer = GDParams.from_seq(outer)
+    db = _f64(domain_bounds).ravel()
+    vals = np.empty(ns)
+    pts = np.empty((ns, q, dim))
+    info = ctypes.c_int()
+    rc = lib().cmoe_ei_gradient_descent(gp.h, ctypes.byref(outer), _d(db), _d(starts), ns, q, _d(Xp), Xp.shape[0],
+                                        int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals),
+                                        _d(pts), ctypes.byref(info))
+    _check(rc, info.value)
+    return vals, pts

@@ -84,31 +84,69 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// Kernel-specific pieces.  pk0 holds e_j = ln(alpha) - |x~_j|^2/2 for SE and |x~_j|^2 for Matern.
+// exp(t) for t <= ~700 without the library's range checks: Cody-Waite reduction by ln2, degree-11 minimax polynomial
+// (the CUDA math library's coefficients, max relative error 2.2e-16 over [-700, 1]), exponent patched in by integer
+// add.  Arguments below -700 are clamped (the result, <= 1e-304, is a zero contribution to every sum here).
+__device__ __forceinline__ double exp_fast(double t) {
+  t = fmax(t, -700.0);
+  const double kShift = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t*log2e + kShift) is round(t*log2e)
+  double nf = fma(t, 1.4426950408889634, kShift);
+  const int n = __double2loint(nf);
+  nf -= kShift;
+  double r = fma(nf, -6.93147180369123816490e-01, t);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = 2.5022322536502990e-08;
+  p = fma(p, r, 2.7630903488173108e-07);
+  p = fma(p, r, 2.7557514545882439e-06);
+  p = fma(p, r, 2.4801491039099165e-05);
+  p = fma(p, r, 1.9841269589115497e-04);
+  p = fma(p, r, 1.3888888945916380e-03);
+  p = fma(p, r, 8.3333333334550432e-03);
+  p = fma(p, r, 4.1666666666519754e-02);
+  p = fma(p, r, 1.6666666666666477e-01);
+  p = fma(p, r, 5.0000000000000122e-01);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// Kernel-specific pieces.  pk0 holds e_j = ln(alpha) - |x~_j|^2/2 for SE and |x~_j|^2 for Matern; hq = -|x~|^2/2.
 // Returns the value weight kv (k(x, X_j)) and the gradient weight kb (d k / d x_d = kb * (x~_jd - x~_d) / l_d).
 template <int KERNEL>
-__device__ __forceinline__ void kernel_pair(double dot, double pk0, double nq, double alpha, double& kv, double& kb) {
+__device__ __forceinline__ void kernel_pair(double dot, double pk0, double hq, double alpha, double& kv, double& kb) {
   if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
-    kv = exp(dot + pk0 - 0.5 * nq);
+    kv = exp_fast(dot + (pk0 + hq));
     kb = kv;
   } else {
-    const double r2 = fmax(0.0, nq + pk0 - 2.0 * dot);
+    const double r2 = fmax(0.0, pk0 - 2.0 * (hq + dot));
     const double ar = kSqrt5 * sqrt(r2);
-    const double ee = alpha * exp(-ar);
+    const double ee = alpha * exp_fast(-ar);
     kv = ee * (1.0 + ar + (5.0 / 3.0) * r2);
     kb = (5.0 / 3.0) * ee * (1.0 + ar);
   }
 }
 
+// 16-byte loads of the staged operands: LDS.128 when the pointer is known to be shared, LDG.128 (read-only path) else
+template <bool SMEM>
+__device__ __forceinline__ double2 ld2(const double* p) {
+  if (SMEM) {
+    return *reinterpret_cast<const double2*>(p);
+  } else {
+    return __ldg(reinterpret_cast<const double2*>(p));
+  }
+}
+
 // mu+(xq) - m  and  the scaled-gradient accumulators, for one query point (scaled coordinates xq).
-template <int KERNEL, int DIM, int QP>
+template <int KERNEL, int DIM, int QP, bool SMEM>
 __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, const double* __restrict__ Pk,
                                                const double* __restrict__ Xu, int N, int U, double alpha,
                                                const double (&xq)[DIM], const double (&c)[QP], double& S0, double& SB,
                                                double (&s)[DIM]) {
+  static_assert(DIM % 2 == 0 && QP % 2 == 0, "operands are moved as 16-byte pairs");
   double nq = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) nq = fma(xq[d], xq[d], nq);
+  const double hq = -0.5 * nq;
   S0 = 0.0;
   SB = 0.0;
 #pragma unroll
@@ -117,27 +155,47 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
   for (int j = 0; j < N; ++j) {
     const double* xj = Xt + j * DIM;
     const double* pk = Pk + j * (QP + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<SMEM>(xj + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    const double2 h = ld2<SMEM>(pk);  // (e_j, beta_j)
     double dot = 0.0;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xj[d], dot);
-    double a = pk[1];
+    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
+    double a = h.y;
 #pragma unroll
-    for (int u = 0; u < QP; ++u) a = fma(-pk[2 + u], c[u], a);
+    for (int u = 0; u < QP; u += 2) {
+      const double2 b = ld2<SMEM>(pk + 2 + u);
+      a = fma(-b.x, c[u], a);
+      a = fma(-b.y, c[u + 1], a);
+    }
     double kv, kb;
-    kernel_pair<KERNEL>(dot, pk[0], nq, alpha, kv, kb);
+    kernel_pair<KERNEL>(dot, h.x, hq, alpha, kv, kb);
     S0 = fma(a, kv, S0);
     const double wb = a * kb;
     if (KERNEL != CMOE_KERNEL_SQUARE_EXPONENTIAL) SB += wb;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xj[d], s[d]);
+    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
   }
   for (int u = 0; u < U; ++u) {
     const double* xu = Xu + u * (DIM + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<SMEM>(xu + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    const double2 h = ld2<SMEM>(xu + DIM);
     double dot = 0.0;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xu[d], dot);
+    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
     double kv, kb;
-    kernel_pair<KERNEL>(dot, xu[DIM], nq, alpha, kv, kb);
+    kernel_pair<KERNEL>(dot, h.x, hq, alpha, kv, kb);
     double cu = 0.0;
 #pragma unroll
     for (int v = 0; v < QP; ++v)
@@ -146,7 +204,7 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
     const double wb = cu * kb;
     if (KERNEL != CMOE_KERNEL_SQUARE_EXPONENTIAL) SB += wb;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xu[d], s[d]);
+    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
   }
   if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) SB = S0;
 }
@@ -170,89 +228,54 @@ __device__ __forceinline__ double limit_step(double step, double x, double lo, d
 
 enum : int { ST_FETCH = 0, ST_INIT = 1, ST_TRIAL = 2, ST_LIMIT = 3, ST_DONE = 4 };
 
-template <int KERNEL, int DIM, int QP>
-__global__ void __launch_bounds__(256, 2) kg_mc_kernel(const __grid_constant__ KgMcParams prm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint64_t mbar;
-  __shared__ int next_sample;
-  const int cand = blockIdx.y;
-  const int N = prm.N, U = prm.U;
-  const int s_begin = blockIdx.x * prm.chunk;
-  const int s_end = min(prm.num_mc, s_begin + prm.chunk);
-  const double* Xt = prm.Xt;
-  const double* Pk = prm.Pk + static_cast<size_t>(cand) * N * (QP + 2);
-  const double* Xu = prm.Xu + static_cast<size_t>(cand) * U * (DIM + 2);
-  if (prm.use_smem) {
-    // stage the per-candidate operands with TMA bulk copies (UBLKCP) signalled through an mbarrier
-    double* sXt = reinterpret_cast<double*>(smem_raw);
-    double* sPk = sXt + static_cast<size_t>(N) * DIM;
-    double* sXu = sPk + static_cast<size_t>(N) * (QP + 2);
-    const uint32_t bX = static_cast<uint32_t>(N) * DIM * 8u, bP = static_cast<uint32_t>(N) * (QP + 2) * 8u,
-                   bU = static_cast<uint32_t>(U) * (DIM + 2) * 8u;
-    if (threadIdx.x == 0) {
-      mbar_init(&mbar, 1);
-      next_sample = s_begin + blockDim.x;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&mbar, bX + bP + bU);
-      tma_bulk_g2s(sXt, Xt, bX, &mbar);
-      tma_bulk_g2s(sPk, Pk, bP, &mbar);
-      tma_bulk_g2s(sXu, Xu, bU, &mbar);
-    }
-    mbar_wait(&mbar, 0);
-    Xt = sXt;
-    Pk = sPk;
-    Xu = sXu;
-  } else {
-    if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
-    __syncthreads();
-  }
+constexpr int kMcThreads = 256;
 
+// The per-lane line-search state machine.  Live across evaluations: c, the base point xb with f and grad f there,
+// the step size and a few counters; the start point of the current restart run is parked in the sample's output slot.
+template <int KERNEL, int DIM, int QP, bool SMEM>
+__device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* __restrict__ Xt,
+                                           const double* __restrict__ Pk, const double* __restrict__ Xu, int cand,
+                                           int s_begin, int s_end, int* next_sample) {
+  const int N = prm.N, U = prm.U;
   const double* A = prm.A + static_cast<size_t>(cand) * prm.M * DIM;
   const double* recC = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
   const int* recStart = prm.recStart + static_cast<size_t>(cand) * prm.num_mc;
   double* outVal = prm.outVal + static_cast<size_t>(cand) * prm.num_mc;
   double* outX = prm.outX + static_cast<size_t>(cand) * prm.num_mc * DIM;
 
-  // per-lane state
   int state = ST_FETCH;
   int sample = s_begin + threadIdx.x;
-  double c[QP];
-  double xb[DIM], gb[DIM];   // base point (unscaled) and gradient of f = -mu+ there
-  double run0[DIM];          // start of the current restart run
-  double fb = 0.0, alpha_n = 0.0, gnorm = 0.0, f_trial = 0.0;
-  double g_trial[DIM];
+  double c[QP], xb[DIM], gb[DIM];
+  double fb = 0.0, alpha_n = 0.0, gnorm = 0.0;
   int step_i = 0, restart_i = 0, search = 0;
-  unsigned long long n_evals = 0, n_steps = 0;
+  unsigned n_evals = 0, n_steps = 0;
 #pragma unroll
-  for (int d = 0; d < DIM; ++d) xb[d] = gb[d] = run0[d] = g_trial[d] = 0.0;
+  for (int d = 0; d < DIM; ++d) xb[d] = gb[d] = 0.0;
 #pragma unroll
   for (int u = 0; u < QP; ++u) c[u] = 0.0;
 
   while (true) {
     if (state == ST_FETCH) {
       if (sample < s_end) {
+        if (prm.max_restarts > 0) {
 #pragma unroll
-        for (int u = 0; u < QP; ++u) c[u] = recC[static_cast<size_t>(sample) * QP + u];
-        const double* a0 = A + static_cast<size_t>(recStart[sample]) * DIM;
+          for (int u = 0; u < QP; ++u) c[u] = recC[static_cast<size_t>(sample) * QP + u];
+          const double* a0 = A + static_cast<size_t>(recStart[sample]) * DIM;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          xb[d] = a0[d];
-          run0[d] = a0[d];
-        }
-        step_i = 0;
-        restart_i = 0;
-        state = (prm.max_restarts > 0) ? ST_INIT : ST_DONE;
-        if (state == ST_DONE) {
+          for (int d = 0; d < DIM; ++d) {
+            xb[d] = a0[d];
+            outX[static_cast<size_t>(sample) * DIM + d] = a0[d];  // start of restart run 0
+          }
+          step_i = 0;
+          restart_i = 0;
+          state = ST_INIT;
+        } else {
           // ComputeOptimalPosteriorMean returns without touching its outputs (...optimization.cpp:424-426):
-          // best_function_value stays 0 and the best point stays at its fill value 1.0
+          // best_function_value stays 0 and the best point keeps its fill value 1.0
           outVal[sample] = 0.0;
 #pragma unroll
           for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = 1.0 * prm.inv_len[d];
-          sample = atomicAdd(&next_sample, 1);
-          state = ST_FETCH;
-          continue;
+          sample = atomicAdd(next_sample, 1);
         }
       } else {
         state = ST_DONE;
@@ -260,113 +283,93 @@ __global__ void __launch_bounds__(256, 2) kg_mc_kernel(const __grid_constant__ K
     }
     if (__all_sync(0xffffffffu, state == ST_DONE)) break;
 
-    // ---- query point of this lane ----
+    // ---- query point of this lane: base (INIT), base + alpha*grad (TRIAL), base + limited step (LIMIT) ----
     double xq[DIM];
-    double stepv[DIM];
-    if (state == ST_TRIAL) {
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) stepv[d] = alpha_n * gb[d];
-    } else if (state != ST_LIMIT) {
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) stepv[d] = 0.0;
-    } else {
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) stepv[d] = g_trial[d];  // ST_LIMIT: g_trial temporarily holds the limited step
+    for (int d = 0; d < DIM; ++d) {
+      double st = 0.0;
+      if (state == ST_TRIAL || state == ST_LIMIT) st = alpha_n * gb[d];
+      if (state == ST_LIMIT) st = (d < prm.ps) ? limit_step(st, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+      xq[d] = (xb[d] + st) * prm.inv_len[d];
     }
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) xq[d] = (xb[d] + stepv[d]) * prm.inv_len[d];
 
     // ---- the expensive, warp-uniform part ----
     double S0, SB, s[DIM];
-    eval_posterior<KERNEL, DIM, QP>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
-    if (state != ST_DONE) n_evals += 1;
+    eval_posterior<KERNEL, DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
+    if (state != ST_DONE && state != ST_FETCH) n_evals += 1;
     const double fq = -(prm.mean + S0);
-    double gq[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) gq[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
 
     // ---- per-lane transitions (cheap) ----
-    bool finish_run = false;
+    bool finish_run = false, accept = false;
     if (state == ST_INIT) {
       fb = fq;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) gb[d] = gq[d];
-      finish_run = (prm.max_steps <= 0);
-      if (!finish_run) {
-        alpha_n = prm.alpha0[0];
+      for (int d = 0; d < DIM; ++d) gb[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
+      if (prm.max_steps <= 0) {
+        finish_run = true;
+      } else {
+        step_i = -1;  // becomes 0 in the common "start a step" block below
+        accept = true;
+      }
+    } else if (state == ST_TRIAL) {
+      // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
+      const bool ok = (fq - fb) > 0.5 * alpha_n * gnorm;
+      if (!ok) {
+        alpha_n *= 0.5;
+        search += 1;
+        if (search >= 30) finish_run = true;  // exhausted: reject and stop this run (:778-781)
+      } else {
+        // limit the accepted step to the domain; if unchanged, this evaluation IS the final evaluation of the step
+        bool same = true;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          const double raw = alpha_n * gb[d];
+          const double lim = (d < prm.ps) ? limit_step(raw, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+          same = same && (lim == raw);
+        }
+        if (same) {
+          if (fq <= fb) {
+            finish_run = true;
+          } else {
+            accept = true;
+          }
+        } else {
+          state = ST_LIMIT;  // one more evaluation at the limited point
+        }
+      }
+    } else if (state == ST_LIMIT) {
+      if (fq <= fb) {
+        finish_run = true;  // no increase: restore the base point and stop (:778-781)
+      } else {
+        accept = true;
+      }
+    }
+    if (accept) {
+      // the evaluated query point becomes the base point; start the next step (or finish the run)
+      double ns = 0.0;
+      if (state != ST_INIT) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          double st = alpha_n * gb[d];
+          if (state == ST_LIMIT) st = (d < prm.ps) ? limit_step(st, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+          xb[d] += st;
+          ns = fma(st, st, ns);
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gb[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
+        fb = fq;
+        n_steps += 1;
+      }
+      step_i += 1;
+      if (state != ST_INIT && (sqrt(ns) < prm.step_tol || step_i >= prm.max_steps)) {
+        finish_run = true;
+      } else {
+        alpha_n = prm.alpha0[step_i];
         search = 0;
         gnorm = 0.0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
         state = ST_TRIAL;
-      }
-    } else if (state == ST_TRIAL || state == ST_LIMIT) {
-      bool have_limit_eval = false;
-      double f_lim = 0.0;
-      if (state == ST_TRIAL) {
-        // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
-        const bool ok = (fq - fb) > 0.5 * alpha_n * gnorm;
-        if (!ok) {
-          alpha_n *= 0.5;
-          search += 1;
-        }
-        if (ok || search >= 30) {
-          if (search >= 30) {
-            // line search exhausted: the reference rejects the step and stops this run (:778-781)
-            finish_run = true;
-          } else {
-            // limit the accepted step to the domain; if unchanged, the trial evaluation IS the final evaluation
-            bool same = true;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) {
-              const double raw = alpha_n * gb[d];
-              const double lim = (d < prm.ps) ? limit_step(raw, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
-              same = same && (lim == raw);
-              stepv[d] = lim;
-            }
-            if (same) {
-              have_limit_eval = true;
-              f_lim = fq;
-            } else {
-              // need one more evaluation at the limited point: park the step in g_trial
-              f_trial = fq;
-#pragma unroll
-              for (int d = 0; d < DIM; ++d) g_trial[d] = stepv[d];
-              state = ST_LIMIT;
-            }
-          }
-        }
-      } else {
-        have_limit_eval = true;
-        f_lim = fq;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) stepv[d] = g_trial[d];
-      }
-      if (have_limit_eval) {
-        if (f_lim <= fb) {
-          finish_run = true;  // no increase: restore the base point and stop (:778-781)
-        } else {
-          double ns = 0.0;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) {
-            xb[d] += stepv[d];
-            gb[d] = gq[d];
-            ns = fma(stepv[d], stepv[d], ns);
-          }
-          fb = f_lim;
-          n_steps += 1;
-          step_i += 1;
-          if (sqrt(ns) < prm.step_tol || step_i >= prm.max_steps) {
-            finish_run = true;
-          } else {
-            alpha_n = prm.alpha0[step_i];
-            search = 0;
-            gnorm = 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
-            state = ST_TRIAL;
-          }
-        }
       }
     }
     if (finish_run) {
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256, 2) kg_mc_kernel(const __grid_constant__ K
       double nd2 = 0.0;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
-        const double df = run0[d] - xb[d];
+        const double df = outX[static_cast<size_t>(sample) * DIM + d] - xb[d];
         nd2 = fma(df, df, nd2);
       }
       restart_i += 1;
@@ -382,11 +385,11 @@ __global__ void __launch_bounds__(256, 2) kg_mc_kernel(const __grid_constant__ K
         outVal[sample] = fb;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = xb[d] * prm.inv_len[d];
-        sample = atomicAdd(&next_sample, 1);
+        sample = atomicAdd(next_sample, 1);
         state = ST_FETCH;
       } else {
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) run0[d] = xb[d];
+        for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = xb[d];
         step_i = 0;
         alpha_n = prm.alpha0[0];
         search = 0;
@@ -398,11 +401,47 @@ __global__ void __launch_bounds__(256, 2) kg_mc_kernel(const __grid_constant__ K
     }
   }
   // integer counters: atomics keep the totals deterministic
-  n_evals = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(n_evals));
-  n_steps = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(n_steps));
+  n_evals = __reduce_add_sync(0xffffffffu, n_evals);
+  n_steps = __reduce_add_sync(0xffffffffu, n_steps);
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(prm.stats + 0, n_evals);
-    atomicAdd(prm.stats + 1, n_steps);
+    atomicAdd(prm.stats + 0, static_cast<unsigned long long>(n_evals));
+    atomicAdd(prm.stats + 1, static_cast<unsigned long long>(n_steps));
+  }
+}
+
+template <int KERNEL, int DIM, int QP>
+__global__ void __launch_bounds__(kMcThreads, 1) kg_mc_kernel(const __grid_constant__ KgMcParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t mbar;
+  __shared__ int next_sample;
+  const int cand = blockIdx.y;
+  const int N = prm.N, U = prm.U;
+  const int s_begin = blockIdx.x * prm.chunk;
+  const int s_end = min(prm.num_mc, s_begin + prm.chunk);
+  const double* gXt = prm.Xt;
+  const double* gPk = prm.Pk + static_cast<size_t>(cand) * N * (QP + 2);
+  const double* gXu = prm.Xu + static_cast<size_t>(cand) * U * (DIM + 2);
+  if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
+  if (prm.use_smem) {
+    // stage the per-candidate operands with TMA bulk copies (UBLKCP) signalled through an mbarrier
+    double* sXt = reinterpret_cast<double*>(smem_raw);
+    double* sPk = sXt + static_cast<size_t>(N) * DIM;
+    double* sXu = sPk + static_cast<size_t>(N) * (QP + 2);
+    const uint32_t bX = static_cast<uint32_t>(N) * DIM * 8u, bP = static_cast<uint32_t>(N) * (QP + 2) * 8u,
+                   bU = static_cast<uint32_t>(U) * (DIM + 2) * 8u;
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&mbar, bX + bP + bU);
+      tma_bulk_g2s(sXt, gXt, bX, &mbar);
+      tma_bulk_g2s(sPk, gPk, bP, &mbar);
+      tma_bulk_g2s(sXu, gXu, bU, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    kg_mc_body<KERNEL, DIM, QP, true>(prm, sXt, sPk, sXu, cand, s_begin, s_end, &next_sample);
+  } else {
+    __syncthreads();
+    kg_mc_body<KERNEL, DIM, QP, false>(prm, gXt, gPk, gXu, cand, s_begin, s_end, &next_sample);
   }
 }
 
@@ -458,7 +497,7 @@ __global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgA
       nq = fma(v, v, nq);
     }
     double kv, kb;
-    kernel_pair<KERNEL>(dot, pk0, nq, prm.alpha, kv, kb);
+    kernel_pair<KERNEL>(dot, pk0, -0.5 * nq, prm.alpha, kv, kb);
 #pragma unroll
     for (int a = 0; a < QP; ++a) acc[a] = fma(ci[a], kv, acc[a]);
     if (is_u) {
@@ -502,7 +541,7 @@ void launch_kg_mc(const KgMcParams& p, dim3 grid, size_t smem, cudaStream_t s) {
     cudaFuncSetAttribute(kg_mc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  kg_mc_kernel<KERNEL, DIM, QP><<<grid, 256, smem, s>>>(p);
+  kg_mc_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, smem, s>>>(p);
 }
 template <int KERNEL, int DIM, int QP>
 void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {

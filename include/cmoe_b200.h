@@ -184,6 +184,8 @@ int cmoe_ei_gradient_descent(const cmoe_gp* gp, const cmoe_gd_params* outer, con
 int cmoe_bench_cov_build(const cmoe_gp* gp, int repeats, double* usec_per_build);
 /* Blocked Cholesky alone (re-factors a fresh copy of K each repeat). */
 int cmoe_bench_cholesky(const cmoe_gp* gp, int repeats, double* usec_per_factor);
+/* Measured FP64 peaks of this GPU: tflops[0] = DFMA vector pipe, tflops[1] = DMMA tensor pipe (m8n8k4). */
+int cmoe_bench_fp64_peaks(int device, double* tflops);
 /* In-place lower Cholesky of a host matrix through the device path (ComputeCholeskyFactorL, gpp_linear_algebra.cpp:109). */
 int cmoe_cholesky(int n, double* a, int device, int* info);
 /* Solve (L L^T) X = B for nrhs right-hand sides (CholeskyFactorLMatrixMatrixSolve, gpp_linear_algebra.hpp:247). */

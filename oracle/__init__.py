@@ -224,3 +224,36 @@ def philox_normals(seed, first_draw, num_draws, per_draw):
     out = np.empty(num_draws * per_draw)
     lib.oracle_philox_normals(ctypes.c_uint64(seed), ctypes.c_uint64(first_draw), int(num_draws), int(per_draw), _d(out))
     return out.reshape(num_draws, per_draw)
+
+
+def kg_grad_at_point_list(backend, gp, candidates, Xp, num_mc, best_so_far, gd, inner_bounds, discrete_pts,
+                          num_threads, seed=1, num_fidelity=0, want_grad=True):
+    """The CPU baseline call: value (+gradient) of q-KG for a list of candidates, OpenMP over candidates.
+
+    reference back end: the reference's own evaluator/state classes with one NormalRNG per thread;
+    port back end: the C oracle with the Philox table."""
+    cand = _f64(candidates)
+    nc, q, dim = cand.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    gd = _f64(gd)
+    ib = _f64(inner_bounds).ravel()
+    disc = _f64(discrete_pts).reshape(-1, dim - num_fidelity)
+    vals = np.empty(nc)
+    grads = np.empty((nc, q, dim)) if want_grad else None
+    if backend.prefix == "ref_":
+        if want_grad:
+            backend.lib.ref_kg_grad_at_point_list(gp.h, int(num_fidelity), _d(gd), _d(ib), _d(disc), disc.shape[0],
+                                                  _d(cand), _d(Xp), nc, q, Xp.shape[0], int(num_mc),
+                                                  ctypes.c_double(best_so_far), int(num_threads),
+                                                  ctypes.c_uint(seed), _d(vals), _d(grads))
+        else:
+            dom = np.tile([0.0, 1.0], dim)
+            backend.lib.ref_evaluate_kg_at_point_list(gp.h, int(num_fidelity), _d(gd), _d(dom), _d(ib), _d(disc),
+                                                      disc.shape[0], _d(cand), _d(Xp), nc, q, Xp.shape[0],
+                                                      int(num_mc), ctypes.c_double(best_so_far), int(num_threads),
+                                                      ctypes.c_uint(seed), _d(vals), None)
+    else:
+        backend.lib.oracle_kg_at_point_list(gp.h, int(num_fidelity), _d(gd), _d(ib), _d(disc), disc.shape[0], _d(cand),
+                                            _d(Xp), nc, q, Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far),
+                                            int(num_threads), ctypes.c_uint64(seed), _d(vals), _d(grads))
+    return vals, grads
