@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcornell_moe_b200.so")
+LIB_PATH = os.environ.get("CMOE_B200_LIB", os.path.join(_HERE, "libcornell_moe_b200.so"))
 
 OK, ERR_SINGULAR, ERR_BOUNDS, ERR_INVALID_VALUE, ERR_RUNTIME, ERR_NO_DEVICE = range(6)
 SQUARE_EXPONENTIAL, MATERN_NU_2P5 = 0, 1

@@ -1,0 +1,595 @@
+// `GPP`: drop-in for the reference's Boost.Python module `moe.build.GPP` (gpp_python.cpp:453-600) for the GP-posterior
+// + Monte-Carlo acquisition hot path, built with pybind11 (Boost.Python is not available) on top of the C ABI in
+// include/cmoe_b200.h.  Same names, positional signatures, flat-list conventions, status-dict keys and exception
+// classes as the reference, so `moe.optimal_learning.python.cpp_wrappers.*` can `import ... GPP as C_GP` unchanged:
+//
+//   GaussianProcess(hyperparameters, points_sampled, points_sampled_value, noise_variance, derivatives,
+//                   num_derivatives, dim, num_sampled)                     gpp_python_gaussian_process.cpp:42-62, 295
+//     .compute_mean_of_points / compute_mean_of_additional_points / compute_grad_mean_of_points /
+//     .compute_variance_of_points / compute_cholesky_variance_of_points / compute_grad_variance_of_points /
+//     .compute_grad_cholesky_variance_of_points / add_sampled_points / ...   :64-253, 456-463
+//   compute_expected_improvement, compute_grad_expected_improvement, multistart_expected_improvement_optimization,
+//   evaluate_EI_at_point_list                                             gpp_python_expected_improvement.cpp:44-441
+//   compute_posterior_mean, compute_grad_posterior_mean, compute_knowledge_gradient, compute_grad_knowledge_gradient,
+//   multistart_knowledge_gradient_optimization, posterior_mean_optimization, evaluate_KG_at_point_list
+//                                                                         gpp_python_knowledge_gradient.cpp:44-397
+//   GradientDescentParameters, NewtonParameters, RandomnessSourceContainer, OptimizerTypes, DomainTypes,
+//   LogLikelihoodTypes                                                    gpp_python_common.cpp:201-370
+//   OptimalLearningException, BoundsException, InvalidValueException, SingularMatrixException   gpp_python.cpp:189-206
+//
+// Differences that are inherent to the device path and documented in INTEGRATION.md:
+//   * normals come from Philox4x32-10 keyed by the RandomnessSourceContainer's seed (not boost mt19937);
+//   * `max_num_threads` is accepted and validated against the container but the parallel axis is the GPU;
+//   * `use_gpu` / `which_gpu` (dead arguments in the reference) select the device.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "cmoe_b200.h"
+
+namespace py = pybind11;
+
+namespace {
+
+PyObject* g_exc_base = nullptr;
+PyObject* g_exc_bounds = nullptr;
+PyObject* g_exc_invalid = nullptr;
+PyObject* g_exc_singular = nullptr;
+
+[[noreturn]] void raise_status(int rc, int info) {
+  PyObject* type = g_exc_base;
+  if (rc == CMOE_ERR_SINGULAR) type = g_exc_singular;
+  if (rc == CMOE_ERR_BOUNDS) type = g_exc_bounds;
+  if (rc == CMOE_ERR_INVALID_VALUE) type = g_exc_invalid;
+  std::string msg = cmoe_last_error();
+  if (rc == CMOE_ERR_SINGULAR) msg += " (leading minor index " + std::to_string(info) + ")";
+  PyErr_SetString(type, msg.c_str());
+  throw py::error_already_set();
+}
+
+void check(int rc, int info = 0) {
+  if (rc != CMOE_OK) raise_status(rc, info);
+}
+
+std::vector<double> to_vec(const py::list& l, size_t n) {
+  if (static_cast<size_t>(py::len(l)) < n) {
+    PyErr_SetString(g_exc_bounds, "input list shorter than the size implied by the dimension arguments");
+    throw py::error_already_set();
+  }
+  std::vector<double> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = l[i].cast<double>();
+  return v;
+}
+
+std::vector<int> to_ivec(const py::list& l, size_t n) {
+  std::vector<int> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = l[i].cast<int>();
+  return v;
+}
+
+py::list to_list(const std::vector<double>& v) {
+  py::list out;
+  for (double x : v) out.append(x);
+  return out;
+}
+
+// ---- parameter structs (gpp_optimizer_parameters.hpp:46-200) -------------------------------------------------------
+struct GradientDescentParameters {
+  cmoe_gd_params p;
+  GradientDescentParameters(int num_multistarts, int max_num_steps, int max_num_restarts, int num_steps_averaged,
+                            double gamma, double pre_mult, double max_relative_change, double tolerance)
+      : p{num_multistarts, max_num_steps, max_num_restarts, num_steps_averaged, gamma, pre_mult, max_relative_change,
+          tolerance} {}
+};
+
+struct NewtonParameters {
+  int num_multistarts, max_num_steps;
+  double gamma, time_factor, max_relative_change, tolerance;
+  NewtonParameters(int a, int b, double c, double d, double e, double f)
+      : num_multistarts(a), max_num_steps(b), gamma(c), time_factor(d), max_relative_change(e), tolerance(f) {}
+};
+
+enum class OptimizerTypes { kNull = 0, kGradientDescent = 1, kNewton = 2 };
+enum class DomainTypes { kTensorProduct = 0, kSimplex = 1 };
+enum class LogLikelihoodTypes { kLogMarginalLikelihood = 0, kLeaveOneOutLogLikelihood = 1 };
+
+// ---- RandomnessSourceContainer (gpp_python_common.hpp:146-230) ------------------------------------------------------
+struct RandomnessSourceContainer {
+  static constexpr uint32_t kUniformDefaultSeed = 314, kNormalDefaultSeed = 314;
+  std::mt19937 uniform_engine;
+  uint32_t uniform_seed = kUniformDefaultSeed;
+  std::vector<uint64_t> normal_seeds;  // one per "thread", as in the reference
+  explicit RandomnessSourceContainer(int num_threads)
+      : uniform_engine(kUniformDefaultSeed), normal_seeds(std::max(0, num_threads)) {
+    SetExplicitNormalRNGSeed(kNormalDefaultSeed);
+  }
+  void SetExplicitUniformGeneratorSeed(uint32_t seed) { uniform_seed = seed; uniform_engine.seed(seed); }
+  void SetRandomizedUniformGeneratorSeed(uint32_t seed) { SetExplicitUniformGeneratorSeed(mix(seed, 0)); }
+  void ResetUniformGeneratorState() { uniform_engine.seed(uniform_seed); }
+  void SetExplicitNormalRNGSeed(uint32_t seed) {
+    for (size_t i = 0; i < normal_seeds.size(); ++i) normal_seeds[i] = static_cast<uint64_t>(seed) + i;
+  }
+  void SetRandomizedNormalRNGSeed(uint32_t seed) {
+    for (size_t i = 0; i < normal_seeds.size(); ++i) normal_seeds[i] = mix(seed, static_cast<int>(i));
+  }
+  bool SetNormalRNGSeedPythonList(const py::list& seeds, const py::list& flags) {
+    if (py::len(seeds) != py::len(flags) || py::len(seeds) != normal_seeds.size()) return false;
+    for (size_t i = 0; i < normal_seeds.size(); ++i)
+      if (flags[i].cast<int>()) normal_seeds[i] = static_cast<uint64_t>(seeds[i].cast<int64_t>());
+    return true;
+  }
+  void ResetNormalRNGState() {}  // the Philox stream is a pure function of (seed, sample index): nothing to rewind
+  void PrintState() const {
+    std::printf("Uniform seed: %u\n", uniform_seed);
+    for (size_t i = 0; i < normal_seeds.size(); ++i)
+      std::printf("NormalRNG %zu: Philox4x32-10 key %llu\n", i, static_cast<unsigned long long>(normal_seeds[i]));
+  }
+  uint64_t seed0() const { return normal_seeds.empty() ? kNormalDefaultSeed : normal_seeds[0]; }
+  static uint32_t mix(uint32_t seed, int thread_id) {
+    std::random_device rd;
+    return seed ^ (rd() + 0x9e3779b9u + (seed << 6) + (seed >> 2)) ^ static_cast<uint32_t>(thread_id * 2654435761u);
+  }
+};
+
+void require_threads(int max_num_threads, const RandomnessSourceContainer& r) {
+  if (max_num_threads > static_cast<int>(r.normal_seeds.size())) {
+    PyErr_SetString(g_exc_bounds, "Fewer randomness_sources than max_num_threads.");
+    throw py::error_already_set();
+  }
+}
+
+// ---- GaussianProcess ------------------------------------------------------------------------------------------------
+struct GaussianProcess {
+  cmoe_gp* h = nullptr;
+  int dim_ = 0, num_derivatives_ = 0;
+  std::vector<int> derivatives_;
+  GaussianProcess(const py::list& hyperparameters, const py::list& points_sampled, const py::list& points_sampled_value,
+                  const py::list& noise_variance, const py::list& derivatives, int num_derivatives, int dim,
+                  int num_sampled, const std::string& kernel, int which_gpu) {
+    const double alpha = hyperparameters[0].cast<double>();
+    const std::vector<double> lengths = to_vec(hyperparameters[1].cast<py::list>(), dim);
+    const std::vector<double> X = to_vec(points_sampled, static_cast<size_t>(dim) * num_sampled);
+    const std::vector<double> y = to_vec(points_sampled_value, static_cast<size_t>(num_sampled) * (1 + num_derivatives));
+    const std::vector<double> noise = to_vec(noise_variance, 1 + num_derivatives);
+    derivatives_ = to_ivec(derivatives, num_derivatives);
+    dim_ = dim;
+    num_derivatives_ = num_derivatives;
+    // The reference's Python boundary hard-wires MaternNu2p5 (gpp_python_gaussian_process.cpp:53); SE is opt-in.
+    const int kid = (kernel == "square_exponential") ? CMOE_KERNEL_SQUARE_EXPONENTIAL : CMOE_KERNEL_MATERN_NU_2P5;
+    int info = 0;
+    check(cmoe_gp_create(kid, alpha, lengths.data(), X.data(), y.data(), noise.data(), derivatives_.data(),
+                         num_derivatives, dim, num_sampled, which_gpu, &h, &info),
+          info);
+  }
+  ~GaussianProcess() { cmoe_gp_destroy(h); }
+  GaussianProcess(const GaussianProcess&) = delete;
+  GaussianProcess& operator=(const GaussianProcess&) = delete;
+  int dim() const { return dim_; }
+  int num_sampled() const { return cmoe_gp_num_sampled(h); }
+  int Qs(int n) const { return n * (1 + num_derivatives_); }
+
+  py::list mean(const py::list& pts, int n) const {  // GetMeanWrapper :64-79 (no derivative rows)
+    const auto P = to_vec(pts, static_cast<size_t>(n) * dim_);
+    std::vector<double> out(n);
+    int info = 0;
+    check(cmoe_gp_posterior(h, P.data(), 1, n, nullptr, 0, out.data(), nullptr, nullptr, nullptr, nullptr, nullptr, &info), info);
+    return to_list(out);
+  }
+  py::list grad_mean(const py::list& pts, int n) const {  // GetGradMeanWrapper :98-116 (GP's derivative rows)
+    const auto P = to_vec(pts, static_cast<size_t>(n) * dim_);
+    std::vector<double> out(static_cast<size_t>(dim_) * Qs(n));
+    int info = 0;
+    check(cmoe_gp_posterior(h, P.data(), 1, n, derivatives_.data(), num_derivatives_, nullptr, out.data(), nullptr,
+                            nullptr, nullptr, nullptr, &info), info);
+    return to_list(out);
+  }
+  py::list variance(const py::list& pts, int n) const {  // GetVarWrapper :118-154: full symmetric, row by row
+    const auto P = to_vec(pts, static_cast<size_t>(n) * dim_);
+    const int Q = Qs(n);
+    std::vector<double> v(static_cast<size_t>(Q) * Q);
+    int info = 0;
+    check(cmoe_gp_posterior(h, P.data(), 1, n, derivatives_.data(), num_derivatives_, nullptr, nullptr, v.data(),
+                            nullptr, nullptr, nullptr, &info), info);
+    py::list out;
+    for (int i = 0; i < Q; ++i)
+      for (int j = 0; j < Q; ++j) out.append(v[static_cast<size_t>(j) * Q + i]);
+    return out;
+  }
+  py::list chol_variance(const py::list& pts, int n) const {  // GetCholVarWrapper :156-187
+    const auto P = to_vec(pts, static_cast<size_t>(n) * dim_);
+    const int Q = Qs(n);
+    std::vector<double> v(static_cast<size_t>(Q) * Q);
+    int info = 0;
+    check(cmoe_gp_posterior(h, P.data(), 1, n, derivatives_.data(), num_derivatives_, nullptr, nullptr, nullptr,
+                            v.data(), nullptr, nullptr, &info), info);
+    py::list out;
+    for (int i = 0; i < Q; ++i)
+      for (int j = 0; j < Q; ++j) out.append(v[static_cast<size_t>(j) * Q + i]);
+    return out;
+  }
+  py::list grad_variance(const py::list& pts, int n, int num_derivatives, bool chol) const {  // :189-236
+    const auto P = to_vec(pts, static_cast<size_t>(n) * dim_);
+    const int Q = Qs(n);
+    std::vector<double> g(static_cast<size_t>(dim_) * Q * Q * n);
+    int info = 0;
+    check(cmoe_gp_posterior(h, P.data(), 1, n, derivatives_.data(), num_derivatives_, nullptr, nullptr, nullptr, nullptr,
+                            chol ? nullptr : g.data(), chol ? g.data() : nullptr, &info), info);
+    g.resize(static_cast<size_t>(dim_) * Q * Q * std::min(n, std::max(0, num_derivatives)));
+    return to_list(g);
+  }
+  void add_sampled_points(const py::list& pts, const py::list& vals, int n) {  // AddPointsToGPWrapper :238-253
+    const auto P = to_vec(pts, static_cast<size_t>(n) * dim_);
+    const auto V = to_vec(vals, static_cast<size_t>(n) * (1 + num_derivatives_));
+    int info = 0;
+    check(cmoe_gp_add_sampled_points(h, P.data(), V.data(), n, &info), info);
+  }
+};
+
+cmoe_gd_params gd_of(const py::object& optimizer_parameters) {
+  return optimizer_parameters.attr("optimizer_parameters").cast<const GradientDescentParameters&>().p;
+}
+
+std::vector<double> full_bounds(const py::list& domain_bounds, int dim) { return to_vec(domain_bounds, 2 * static_cast<size_t>(dim)); }
+
+// ---- EI ---------------------------------------------------------------------------------------------------------------
+double compute_expected_improvement(const GaussianProcess& gp, const py::list& pts, const py::list& being, int q, int p,
+                                    int max_int_steps, double best_so_far, bool /*force_monte_carlo*/,
+                                    RandomnessSourceContainer& rnd) {
+  const auto X = to_vec(pts, static_cast<size_t>(q) * gp.dim_);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
+  double ei = 0.0;
+  int info = 0;
+  check(cmoe_ei_eval(gp.h, X.data(), 1, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(), nullptr, &ei, nullptr,
+                     &info), info);
+  return ei;
+}
+
+py::list compute_grad_expected_improvement(const GaussianProcess& gp, const py::list& pts, const py::list& being, int q,
+                                           int p, int max_int_steps, double best_so_far, bool /*force_monte_carlo*/,
+                                           RandomnessSourceContainer& rnd) {
+  const auto X = to_vec(pts, static_cast<size_t>(q) * gp.dim_);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
+  double ei = 0.0;
+  std::vector<double> g(static_cast<size_t>(q) * gp.dim_);
+  int info = 0;
+  check(cmoe_ei_eval(gp.h, X.data(), 1, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(), nullptr, &ei, g.data(),
+                     &info), info);
+  return to_list(g);
+}
+
+// Latin hypercube starts in a repeated tensor-product domain (gpp_random.cpp:173-197, gpp_domain.hpp:490-515)
+std::vector<double> lhc_starts(const std::vector<double>& bounds, int dim, int q, int num, std::mt19937& eng) {
+  std::vector<double> out(static_cast<size_t>(num) * q * dim);
+  std::vector<int> idx(num);
+  for (int rep = 0; rep < q; ++rep) {
+    for (int d = 0; d < dim; ++d) {
+      const double edge = (bounds[2 * d + 1] - bounds[2 * d]) / static_cast<double>(num);
+      for (int j = 0; j < num; ++j) idx[j] = j;
+      std::shuffle(idx.begin(), idx.end(), eng);
+      std::uniform_real_distribution<double> u(0.0, edge);
+      for (int j = 0; j < num; ++j)
+        out[(static_cast<size_t>(j) * q + rep) * dim + d] = bounds[2 * d] + edge * idx[j] + u(eng);
+    }
+  }
+  return out;
+}
+
+py::list multistart_expected_improvement_optimization(const py::object& optimizer_parameters, const GaussianProcess& gp,
+                                                      const py::list& domain_bounds, const py::list& being, int q, int p,
+                                                      double best_so_far, int max_int_steps, int max_num_threads,
+                                                      bool /*use_gpu*/, int /*which_gpu*/, RandomnessSourceContainer& rnd,
+                                                      py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const int dim = gp.dim_;
+  const auto bounds = full_bounds(domain_bounds, dim);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const auto domain_type = optimizer_parameters.attr("domain_type").cast<DomainTypes>();
+  const auto opt_type = optimizer_parameters.attr("optimizer_type").cast<OptimizerTypes>();
+  if (domain_type != DomainTypes::kTensorProduct) {
+    PyErr_SetString(g_exc_base, "only the tensor_product domain is implemented on the B200 path");
+    throw py::error_already_set();
+  }
+  std::vector<double> best(static_cast<size_t>(q) * dim, 0.0);
+  double best_value = 0.0;
+  int found = 0, info = 0;
+  if (opt_type == OptimizerTypes::kNull) {
+    const int n = optimizer_parameters.attr("num_random_samples").cast<int>();
+    const auto starts = lhc_starts(bounds, dim, q, n, rnd.uniform_engine);
+    std::vector<double> vals(n);
+    check(cmoe_ei_eval(gp.h, starts.data(), n, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(), nullptr,
+                       vals.data(), nullptr, &info), info);
+    double bv = -1.0;
+    std::copy(starts.begin(), starts.begin() + static_cast<size_t>(q) * dim, best.begin());
+    for (int i = 0; i < n; ++i)
+      if (bv < vals[i]) {
+        bv = vals[i];
+        found = 1;
+        std::copy(starts.begin() + static_cast<size_t>(i) * q * dim, starts.begin() + static_cast<size_t>(i + 1) * q * dim, best.begin());
+      }
+    status["lhc_tensor_product_domain_found_update"] = static_cast<bool>(found);
+  } else if (opt_type == OptimizerTypes::kGradientDescent) {
+    const cmoe_gd_params gd = gd_of(optimizer_parameters);
+    const auto starts = lhc_starts(bounds, dim, q, gd.num_multistarts, rnd.uniform_engine);
+    check(cmoe_multistart_ei(gp.h, &gd, bounds.data(), starts.data(), gd.num_multistarts, q, Xp.data(), p, max_int_steps,
+                             best_so_far, rnd.seed0(), nullptr, best.data(), &best_value, &found, &info), info);
+    status["gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
+  } else {
+    PyErr_SetString(g_exc_base, "ERROR: invalid optimizer choice. Setting all coordinates to 0.0.");
+    throw py::error_already_set();
+  }
+  return to_list(best);
+}
+
+py::list evaluate_EI_at_point_list(const GaussianProcess& gp, const py::list& initial_guesses, const py::list& being,
+                                   int num_multistarts, int q, int p, double best_so_far, int max_int_steps,
+                                   int max_num_threads, RandomnessSourceContainer& rnd, py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const auto starts = to_vec(initial_guesses, static_cast<size_t>(num_multistarts) * q * gp.dim_);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
+  std::vector<double> vals(num_multistarts);
+  int info = 0;
+  check(cmoe_ei_eval(gp.h, starts.data(), num_multistarts, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(),
+                     nullptr, vals.data(), nullptr, &info), info);
+  bool found = false;
+  for (double v : vals) found = found || (v > -1.0);
+  status["evaluate_EI_at_point_list"] = found;
+  return to_list(vals);
+}
+
+// ---- posterior mean / KG ----------------------------------------------------------------------------------------------
+std::vector<double> pad_fidelity(const std::vector<double>& pt, int dim) {
+  std::vector<double> full(dim, 1.0);  // fidelity coordinates pinned to 1.0 (...knowledge_gradient_optimization.cpp:365)
+  std::copy(pt.begin(), pt.end(), full.begin());
+  return full;
+}
+
+double compute_posterior_mean(const GaussianProcess& gp, int num_fidelity, const py::list& pt) {
+  const auto x = pad_fidelity(to_vec(pt, gp.dim_ - num_fidelity), gp.dim_);
+  double m = 0.0;
+  int info = 0;
+  check(cmoe_gp_posterior(gp.h, x.data(), 1, 1, nullptr, 0, &m, nullptr, nullptr, nullptr, nullptr, nullptr, &info), info);
+  return -m;  // the evaluator maximises -mu (...cpp:334-340)
+}
+
+py::list compute_grad_posterior_mean(const GaussianProcess& gp, int num_fidelity, const py::list& pt) {
+  const auto x = pad_fidelity(to_vec(pt, gp.dim_ - num_fidelity), gp.dim_);
+  std::vector<double> g(gp.dim_);
+  int info = 0;
+  check(cmoe_gp_posterior(gp.h, x.data(), 1, 1, nullptr, 0, nullptr, g.data(), nullptr, nullptr, nullptr, nullptr, &info), info);
+  std::vector<double> out(gp.dim_ - num_fidelity);
+  for (size_t i = 0; i < out.size(); ++i) out[i] = -g[i];
+  return to_list(out);
+}
+
+double compute_knowledge_gradient(const GaussianProcess& gp, int num_fidelity, const py::object& optimizer_parameters,
+                                  const py::list& domain_bounds, const py::list& discrete_pts, const py::list& pts,
+                                  const py::list& being, int num_pts, int q, int p, int max_int_steps, double best_so_far,
+                                  RandomnessSourceContainer& rnd) {
+  const int dim = gp.dim_, ps = dim - num_fidelity;
+  const auto inner_bounds = to_vec(domain_bounds, 2 * static_cast<size_t>(ps));
+  const auto D = to_vec(discrete_pts, static_cast<size_t>(num_pts) * ps);
+  const auto X = to_vec(pts, static_cast<size_t>(q) * dim);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters);
+  double kg = 0.0;
+  int info = 0;
+  check(cmoe_kg_eval(gp.h, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, X.data(), 1, q, Xp.data(), p,
+                     max_int_steps, best_so_far, rnd.seed0(), nullptr, &kg, nullptr, nullptr, &info), info);
+  return kg;
+}
+
+py::list compute_grad_knowledge_gradient(const GaussianProcess& gp, int num_fidelity,
+                                         const py::object& optimizer_parameters, const py::list& domain_bounds,
+                                         const py::list& discrete_pts, const py::list& pts, const py::list& being,
+                                         int num_pts, int q, int p, int max_int_steps, double best_so_far,
+                                         RandomnessSourceContainer& rnd) {
+  const int dim = gp.dim_, ps = dim - num_fidelity;
+  const auto inner_bounds = to_vec(domain_bounds, 2 * static_cast<size_t>(ps));
+  const auto D = to_vec(discrete_pts, static_cast<size_t>(num_pts) * ps);
+  const auto X = to_vec(pts, static_cast<size_t>(q) * dim);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters);
+  double kg = 0.0;
+  std::vector<double> g(static_cast<size_t>(q) * dim);
+  int info = 0;
+  check(cmoe_kg_eval(gp.h, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, X.data(), 1, q, Xp.data(), p,
+                     max_int_steps, best_so_far, rnd.seed0(), nullptr, &kg, g.data(), nullptr, &info), info);
+  return to_list(g);
+}
+
+py::list multistart_knowledge_gradient_optimization(const py::object& optimizer_parameters,
+                                                    const py::object& optimizer_parameters_inner,
+                                                    const GaussianProcess& gp, int num_fidelity,
+                                                    const py::list& domain_bounds, const py::list& discrete_pts,
+                                                    const py::list& being, int num_pts, int q, int p, double best_so_far,
+                                                    int max_int_steps, int max_num_threads,
+                                                    RandomnessSourceContainer& rnd, py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const int dim = gp.dim_, ps = dim - num_fidelity;
+  const auto bounds = full_bounds(domain_bounds, dim);
+  const std::vector<double> inner_bounds(bounds.begin(), bounds.begin() + 2 * ps);
+  const auto D = to_vec(discrete_pts, static_cast<size_t>(num_pts) * ps);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const auto domain_type = optimizer_parameters.attr("domain_type").cast<DomainTypes>();
+  const auto opt_type = optimizer_parameters.attr("optimizer_type").cast<OptimizerTypes>();
+  if (domain_type != DomainTypes::kTensorProduct) {
+    PyErr_SetString(g_exc_base, "only the tensor_product domain is implemented on the B200 path");
+    throw py::error_already_set();
+  }
+  const cmoe_gd_params inner = gd_of(optimizer_parameters_inner);
+  std::vector<double> best(static_cast<size_t>(q) * dim, 0.0);
+  double best_value = 0.0;
+  int found = 0, info = 0;
+  if (opt_type == OptimizerTypes::kNull) {
+    const int n = optimizer_parameters.attr("num_random_samples").cast<int>();
+    const auto starts = lhc_starts(bounds, dim, q, n, rnd.uniform_engine);
+    std::vector<double> vals(n);
+    check(cmoe_kg_eval(gp.h, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, starts.data(), n, q, Xp.data(),
+                       p, max_int_steps, best_so_far, rnd.seed0(), nullptr, vals.data(), nullptr, nullptr, &info), info);
+    double bv = -INFINITY;
+    std::copy(starts.begin(), starts.begin() + static_cast<size_t>(q) * dim, best.begin());
+    for (int i = 0; i < n; ++i)
+      if (bv < vals[i]) {
+        bv = vals[i];
+        found = 1;
+        std::copy(starts.begin() + static_cast<size_t>(i) * q * dim, starts.begin() + static_cast<size_t>(i + 1) * q * dim, best.begin());
+      }
+    status["lhc_tensor_product_domain_found_update"] = static_cast<bool>(found);
+  } else if (opt_type == OptimizerTypes::kGradientDescent) {
+    const cmoe_gd_params gd = gd_of(optimizer_parameters);
+    const auto starts = lhc_starts(bounds, dim, q, gd.num_multistarts, rnd.uniform_engine);
+    check(cmoe_multistart_kg(gp.h, num_fidelity, &gd, &inner, bounds.data(), inner_bounds.data(), D.data(), num_pts,
+                             starts.data(), gd.num_multistarts, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(),
+                             nullptr, best.data(), &best_value, &found, &info), info);
+    status["gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
+  } else {
+    PyErr_SetString(g_exc_base, "ERROR: invalid optimizer choice. Setting all coordinates to 0.0.");
+    throw py::error_already_set();
+  }
+  return to_list(best);
+}
+
+py::list evaluate_KG_at_point_list(const GaussianProcess& gp, int num_fidelity, const py::object& optimizer_parameters,
+                                   const py::list& domain_bounds, const py::list& discrete_being_sampled,
+                                   const py::list& initial_guesses, int num_multistarts, int num_pts, int q, int p,
+                                   double best_so_far, int max_int_steps, int max_num_threads,
+                                   RandomnessSourceContainer& rnd, py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const int dim = gp.dim_, ps = dim - num_fidelity;
+  const auto bounds = full_bounds(domain_bounds, dim);
+  const std::vector<double> inner_bounds(bounds.begin(), bounds.begin() + 2 * ps);
+  // [discrete_pts (num_pts x dim) ; points_being_sampled (p x dim)], as the reference wrapper slices it (:376-390)
+  const auto both = to_vec(discrete_being_sampled, static_cast<size_t>(num_pts + p) * dim);
+  std::vector<double> D(static_cast<size_t>(num_pts) * ps);
+  for (int j = 0; j < num_pts; ++j)
+    for (int d = 0; d < ps; ++d) D[static_cast<size_t>(j) * ps + d] = both[static_cast<size_t>(j) * dim + d];
+  const std::vector<double> Xp(both.begin() + static_cast<size_t>(num_pts) * dim, both.end());
+  const auto starts = to_vec(initial_guesses, static_cast<size_t>(num_multistarts) * q * dim);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters);
+  std::vector<double> vals(num_multistarts);
+  int info = 0;
+  check(cmoe_kg_eval(gp.h, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, starts.data(), num_multistarts, q,
+                     Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(), nullptr, vals.data(), nullptr, nullptr, &info),
+        info);
+  bool found = false;
+  for (double v : vals) found = found || std::isfinite(v);
+  status["evaluate_KG_at_point_list"] = found;
+  return to_list(vals);
+}
+
+[[noreturn]] void not_on_path(const char* name) {
+  PyErr_SetString(g_exc_base, (std::string(name) + " is outside the B200 hot path (SURVEY.md 8f) and is not provided by this build").c_str());
+  throw py::error_already_set();
+}
+
+}  // namespace
+
+PYBIND11_MODULE(GPP, m) {
+  m.doc() = "B200-native drop-in for moe.build.GPP (GP posterior + MC acquisition hot path)";
+  g_exc_base = PyErr_NewExceptionWithDoc("GPP.OptimalLearningException",
+                                         "Base exception class for errors raised from the optimal_learning library.",
+                                         PyExc_Exception, nullptr);
+  g_exc_bounds = PyErr_NewExceptionWithDoc("GPP.BoundsException", "value not in range [min, max].", g_exc_base, nullptr);
+  g_exc_invalid = PyErr_NewExceptionWithDoc("GPP.InvalidValueException", "value != truth (+/- tolerance)", g_exc_base, nullptr);
+  g_exc_singular = PyErr_NewExceptionWithDoc("GPP.SingularMatrixException", "num_rows X num_cols matrix is singular", g_exc_base, nullptr);
+  m.attr("OptimalLearningException") = py::handle(g_exc_base);
+  m.attr("BoundsException") = py::handle(g_exc_bounds);
+  m.attr("InvalidValueException") = py::handle(g_exc_invalid);
+  m.attr("SingularMatrixException") = py::handle(g_exc_singular);
+
+  py::enum_<OptimizerTypes>(m, "OptimizerTypes")
+      .value("null", OptimizerTypes::kNull)
+      .value("gradient_descent", OptimizerTypes::kGradientDescent)
+      .value("newton", OptimizerTypes::kNewton);
+  py::enum_<DomainTypes>(m, "DomainTypes")
+      .value("tensor_product", DomainTypes::kTensorProduct)
+      .value("simplex", DomainTypes::kSimplex);
+  py::enum_<LogLikelihoodTypes>(m, "LogLikelihoodTypes")
+      .value("log_marginal_likelihood", LogLikelihoodTypes::kLogMarginalLikelihood)
+      .value("leave_one_out_log_likelihood", LogLikelihoodTypes::kLeaveOneOutLogLikelihood);
+
+  py::class_<GradientDescentParameters>(m, "GradientDescentParameters")
+      .def(py::init<int, int, int, int, double, double, double, double>())
+      .def_property("num_multistarts", [](const GradientDescentParameters& s) { return s.p.num_multistarts; },
+                    [](GradientDescentParameters& s, int v) { s.p.num_multistarts = v; })
+      .def_property("max_num_steps", [](const GradientDescentParameters& s) { return s.p.max_num_steps; },
+                    [](GradientDescentParameters& s, int v) { s.p.max_num_steps = v; })
+      .def_property("max_num_restarts", [](const GradientDescentParameters& s) { return s.p.max_num_restarts; },
+                    [](GradientDescentParameters& s, int v) { s.p.max_num_restarts = v; })
+      .def_property("num_steps_averaged", [](const GradientDescentParameters& s) { return s.p.num_steps_averaged; },
+                    [](GradientDescentParameters& s, int v) { s.p.num_steps_averaged = v; })
+      .def_property("gamma", [](const GradientDescentParameters& s) { return s.p.gamma; },
+                    [](GradientDescentParameters& s, double v) { s.p.gamma = v; })
+      .def_property("pre_mult", [](const GradientDescentParameters& s) { return s.p.pre_mult; },
+                    [](GradientDescentParameters& s, double v) { s.p.pre_mult = v; })
+      .def_property("max_relative_change", [](const GradientDescentParameters& s) { return s.p.max_relative_change; },
+                    [](GradientDescentParameters& s, double v) { s.p.max_relative_change = v; })
+      .def_property("tolerance", [](const GradientDescentParameters& s) { return s.p.tolerance; },
+                    [](GradientDescentParameters& s, double v) { s.p.tolerance = v; });
+  py::class_<NewtonParameters>(m, "NewtonParameters")
+      .def(py::init<int, int, double, double, double, double>())
+      .def_readwrite("num_multistarts", &NewtonParameters::num_multistarts)
+      .def_readwrite("max_num_steps", &NewtonParameters::max_num_steps)
+      .def_readwrite("gamma", &NewtonParameters::gamma)
+      .def_readwrite("time_factor", &NewtonParameters::time_factor)
+      .def_readwrite("max_relative_change", &NewtonParameters::max_relative_change)
+      .def_readwrite("tolerance", &NewtonParameters::tolerance);
+  py::class_<RandomnessSourceContainer>(m, "RandomnessSourceContainer")
+      .def(py::init<int>())
+      .def("SetExplicitUniformGeneratorSeed", &RandomnessSourceContainer::SetExplicitUniformGeneratorSeed)
+      .def("SetRandomizedUniformGeneratorSeed", &RandomnessSourceContainer::SetRandomizedUniformGeneratorSeed)
+      .def("ResetUniformRNGSeed", &RandomnessSourceContainer::ResetUniformGeneratorState)
+      .def("SetExplicitNormalRNGSeed", &RandomnessSourceContainer::SetExplicitNormalRNGSeed)
+      .def("SetRandomizedNormalRNGSeed", &RandomnessSourceContainer::SetRandomizedNormalRNGSeed)
+      .def("SetNormalRNGSeedPythonList", &RandomnessSourceContainer::SetNormalRNGSeedPythonList)
+      .def("ResetNormalRNGSeed", &RandomnessSourceContainer::ResetNormalRNGState)
+      .def("PrintState", &RandomnessSourceContainer::PrintState);
+
+  py::class_<GaussianProcess>(m, "GaussianProcess")
+      .def(py::init<const py::list&, const py::list&, const py::list&, const py::list&, const py::list&, int, int, int,
+                    const std::string&, int>(),
+           py::arg("hyperparameters"), py::arg("points_sampled"), py::arg("points_sampled_value"),
+           py::arg("noise_variance"), py::arg("derivatives"), py::arg("num_derivatives"), py::arg("dim"),
+           py::arg("num_sampled"), py::arg("kernel") = "matern52", py::arg("which_gpu") = 0)
+      .def_property_readonly("dim", &GaussianProcess::dim)
+      .def_property_readonly("num_sampled", &GaussianProcess::num_sampled)
+      .def("compute_mean_of_points", &GaussianProcess::mean)
+      .def("compute_mean_of_additional_points", &GaussianProcess::mean)
+      .def("compute_grad_mean_of_points", &GaussianProcess::grad_mean)
+      .def("compute_variance_of_points", &GaussianProcess::variance)
+      .def("compute_cholesky_variance_of_points", &GaussianProcess::chol_variance)
+      .def("compute_grad_variance_of_points",
+           [](const GaussianProcess& g, const py::list& pts, int n, int nd) { return g.grad_variance(pts, n, nd, false); })
+      .def("compute_grad_cholesky_variance_of_points",
+           [](const GaussianProcess& g, const py::list& pts, int n, int nd) { return g.grad_variance(pts, n, nd, true); })
+      .def("add_sampled_points", &GaussianProcess::add_sampled_points)
+      .def("sample_point_from_gp", [](GaussianProcess&, const py::list&) -> py::list { not_on_path("sample_point_from_gp"); })
+      .def("sample_global_optima", [](GaussianProcess&, int, int, const py::list&) -> py::list { not_on_path("sample_global_optima"); })
+      .def("set_explicit_seed", [](GaussianProcess&, uint32_t) {})
+      .def("set_randomized_seed", [](GaussianProcess&, uint32_t) {})
+      .def("reset_to_most_recent_seed", [](GaussianProcess&) {})
+      .def("print_historical_data", [](GaussianProcess&) {});
+
+  m.def("compute_expected_improvement", &compute_expected_improvement);
+  m.def("compute_grad_expected_improvement", &compute_grad_expected_improvement);
+  m.def("multistart_expected_improvement_optimization", &multistart_expected_improvement_optimization);
+  m.def("evaluate_EI_at_point_list", &evaluate_EI_at_point_list);
+  m.def("compute_posterior_mean", &compute_posterior_mean);
+  m.def("compute_grad_posterior_mean", &compute_grad_posterior_mean);
+  m.def("compute_knowledge_gradient", &compute_knowledge_gradient);
+  m.def("compute_grad_knowledge_gradient", &compute_grad_knowledge_gradient);
+  m.def("multistart_knowledge_gradient_optimization", &multistart_knowledge_gradient_optimization);
+  m.def("evaluate_KG_at_point_list", &evaluate_KG_at_point_list);
+  m.def("posterior_mean_optimization", [](const GaussianProcess&, int, const py::object&, const py::list&, const py::list&,
+                                          py::dict&) -> py::list { not_on_path("posterior_mean_optimization"); });
+  m.def("run_cpp_tests", []() -> int { not_on_path("run_cpp_tests"); });
+  m.def("device_count", []() { return cmoe_device_count(); });
+  m.def("version", []() { return std::string(cmoe_version()); });
+}

@@ -538,13 +538,13 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     const size_t per_cand = static_cast<size_t>(num_mc) * (QP + DIMP + 2) * sizeof(double) +
                             static_cast<size_t>(n) * U * 4 * sizeof(double);
     pl->batch = static_cast<int>(std::max<size_t>(1, std::min<size_t>(max_candidates, (size_t(3) << 30) / per_cand)));
-    // samples per CTA: aim for >= ~8 waves of CTAs over the whole batch, at least 512 samples (2 per lane) per CTA
+    // samples per CTA: aim for >= ~8 waves of CTAs over the whole batch, between 2 and 16 samples per lane
     {
-      const long long target_ctas = 8LL * sms * 2;
+      const long long target_ctas = 8LL * sms * 3;
       long long chunk = (static_cast<long long>(pl->batch) * num_mc + target_ctas - 1) / target_ctas;
-      chunk = std::max<long long>(512, std::min<long long>(chunk, 4096));
-      chunk = (chunk + 255) / 256 * 256;
-      pl->chunk = static_cast<int>(std::min<long long>(chunk, (num_mc + 255) / 256 * 256));
+      chunk = std::max<long long>(2 * kMcThreads, std::min<long long>(chunk, 16 * kMcThreads));
+      chunk = (chunk + kMcThreads - 1) / kMcThreads * kMcThreads;
+      pl->chunk = static_cast<int>(std::min<long long>(chunk, (num_mc + kMcThreads - 1) / kMcThreads * kMcThreads));
     }
     const int B = pl->batch;
     pl->dPk.alloc(static_cast<size_t>(B) * N * (QP + 2));

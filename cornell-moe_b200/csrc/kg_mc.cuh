@@ -86,12 +86,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // exp(t) for t <= ~700 without the library's range checks: Cody-Waite reduction by ln2, degree-11 minimax polynomial
 // (the CUDA math library's coefficients, max relative error 2.2e-16 over [-700, 1]), exponent patched in by integer
-// add.  Arguments below -700 are clamped (the result, <= 1e-304, is a zero contribution to every sum here).
+// add.  Below about -700 the exponent is clamped on the integer side (one ALU op instead of FP64-pipe compares): the
+// polynomial then sees a large |r| but the result is still scaled by 2^-1000, i.e. a zero contribution to every sum here.
 __device__ __forceinline__ double exp_fast(double t) {
-  t = fmax(t, -700.0);
   const double kShift = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t*log2e + kShift) is round(t*log2e)
   double nf = fma(t, 1.4426950408889634, kShift);
-  const int n = __double2loint(nf);
+  const int n = max(__double2loint(nf), -1000);
   nf -= kShift;
   double r = fma(nf, -6.93147180369123816490e-01, t);
   r = fma(nf, -1.90821492927058770002e-10, r);
@@ -228,7 +228,13 @@ __device__ __forceinline__ double limit_step(double step, double x, double lo, d
 
 enum : int { ST_FETCH = 0, ST_INIT = 1, ST_TRIAL = 2, ST_LIMIT = 3, ST_DONE = 4 };
 
-constexpr int kMcThreads = 256;
+#ifndef CMOE_MC_THREADS
+#define CMOE_MC_THREADS 128
+#endif
+#ifndef CMOE_MC_MINBLOCKS
+#define CMOE_MC_MINBLOCKS 3
+#endif
+constexpr int kMcThreads = CMOE_MC_THREADS;
 
 // The per-lane line-search state machine.  Live across evaluations: c, the base point xb with f and grad f there,
 // the step size and a few counters; the start point of the current restart run is parked in the sample's output slot.
@@ -410,7 +416,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
 }
 
 template <int KERNEL, int DIM, int QP>
-__global__ void __launch_bounds__(kMcThreads, 1) kg_mc_kernel(const __grid_constant__ KgMcParams prm) {
+__global__ void __launch_bounds__(kMcThreads, CMOE_MC_MINBLOCKS) kg_mc_kernel(const __grid_constant__ KgMcParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t mbar;
   __shared__ int next_sample;
