@@ -1,0 +1,42 @@
+"""GPU: the CUDA path (through the C ABI) against the committed golden vectors generated from the unmodified reference
+(tests/golden/make_golden.py) — this parity check needs no CPU checker at run time."""
+import os
+
+import numpy as np
+import pytest
+
+from synth import DISCRETE_ONLY_GD, EXAMPLE_INNER_GD, unit_bounds
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+CASES = sorted({k.split("/")[0] for k in GOLD.files})
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_matches_golden(case):
+    from cornell_moe_b200 import capi
+    g = lambda k: GOLD[f"{case}/{k}"]
+    kernel, g_idx = int(g("kernel")), tuple(int(v) for v in g("g_idx"))
+    gp = capi.GaussianProcess(kernel, 1.0, g("lengths"), g("X"), g("y"), g("noise"), g_idx)
+    K, kinvy, mean = gp.state()
+    np.testing.assert_allclose(np.tril(K), g("K_chol_lower"), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(kinvy, g("K_inv_y"), rtol=1e-8, atol=1e-10)
+    assert mean == float(g("mean"))
+    want = ("mean", "grad_mean", "var", "chol_var", "grad_var", "grad_chol")
+    post = gp.posterior(g("pts"), g_idx, want)
+    Q = 3 * (1 + len(g_idx))
+    for k in want:
+        a, b = post[k][0], g(f"post_{k}")
+        if k in ("var", "chol_var"):
+            a, b = np.tril(a.reshape(Q, Q).T), np.tril(b.reshape(Q, Q).T)
+        np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-9, err_msg=k)
+    ei, gei = gp.ei(g("mc_Xq"), g("mc_Xp"), 32, float(g("mc_best_ei")), table=g("ei_table"), grad=True)
+    np.testing.assert_allclose(ei[0], g("ei"), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gei[0], g("ei_grad"), rtol=1e-6, atol=1e-9)
+    if len(g_idx) == 0:  # d-KG (derivative observations) is the next row of SURVEY.md §8
+        dim = g("X").shape[1]
+        for tag, gd in (("discrete", DISCRETE_ONLY_GD), ("linesearch", EXAMPLE_INNER_GD)):
+            kg, gkg = gp.kg(g("mc_Xq"), g("mc_Xp"), 32, float(g("mc_best_kg")), gd, unit_bounds(dim), g("mc_disc"),
+                            table=g("kg_table"), grad=True)
+            np.testing.assert_allclose(kg[0], g(f"kg_{tag}"), rtol=1e-7, atol=1e-10)
+            np.testing.assert_allclose(gkg[0], g(f"kg_{tag}_grad"), rtol=1e-5, atol=1e-8)
