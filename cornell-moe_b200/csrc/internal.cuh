@@ -192,7 +192,9 @@ void ei_eval_batch(const cmoe_gp& gp, const double* candidates, int nc, int q, c
 
 // ---- cov.cu --------------------------------------------------------------------------------------------------
 // Lower triangle of K(X,X) + diag(noise by observation type), n*n column-major.
-void build_covariance(const KernelSpec& spec, const double* X, int N, const double* noise, double* K, cudaStream_t s);
+// Xs = X scaled by 1/l (used by the g == 0 fast path).
+void build_covariance(const KernelSpec& spec, const double* X, const double* Xs, int N, const double* noise, double* K,
+                      cudaStream_t s);
 // K(X, P): rows = sampled rows (N*(1+g)), cols = P rows (num*(1+gs)); column-major, ld = n.
 void build_mix_covariance(const KernelSpec& spec, const double* X, int N, const double* P, int num, const int* dPs,
                           int gs, double* out, cudaStream_t s);

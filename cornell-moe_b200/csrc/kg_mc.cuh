@@ -84,32 +84,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// exp(t) for t <= ~700 without the library's range checks: Cody-Waite reduction by ln2, degree-11 minimax polynomial
-// (the CUDA math library's coefficients, max relative error 2.2e-16 over [-700, 1]), exponent patched in by integer
-// add.  Below about -700 the exponent is clamped on the integer side (one ALU op instead of FP64-pipe compares): the
-// polynomial then sees a large |r| but the result is still scaled by 2^-1000, i.e. a zero contribution to every sum here.
-__device__ __forceinline__ double exp_fast(double t) {
-  const double kShift = 6755399441055744.0;  // 1.5 * 2^52: the low word of (t*log2e + kShift) is round(t*log2e)
-  double nf = fma(t, 1.4426950408889634, kShift);
-  const int n = max(__double2loint(nf), -1000);
-  nf -= kShift;
-  double r = fma(nf, -6.93147180369123816490e-01, t);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double p = 2.5022322536502990e-08;
-  p = fma(p, r, 2.7630903488173108e-07);
-  p = fma(p, r, 2.7557514545882439e-06);
-  p = fma(p, r, 2.4801491039099165e-05);
-  p = fma(p, r, 1.9841269589115497e-04);
-  p = fma(p, r, 1.3888888945916380e-03);
-  p = fma(p, r, 8.3333333334550432e-03);
-  p = fma(p, r, 4.1666666666519754e-02);
-  p = fma(p, r, 1.6666666666666477e-01);
-  p = fma(p, r, 5.0000000000000122e-01);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-
 // Kernel-specific pieces.  pk0 holds e_j = ln(alpha) - |x~_j|^2/2 for SE and |x~_j|^2 for Matern; hq = -|x~|^2/2.
 // Returns the value weight kv (k(x, X_j)) and the gradient weight kb (d k / d x_d = kb * (x~_jd - x~_d) / l_d).
 template <int KERNEL>

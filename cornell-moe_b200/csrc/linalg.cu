@@ -297,6 +297,99 @@ __global__ void __launch_bounds__(256) trsm_kernel(const double* __restrict__ L,
 
 int g_launches = 0;
 
+// --------------------------------------------------------------------------------------------------------------
+// Few right-hand sides, large n (the K^-1 y solve of a big fit): the slab kernel above would run on one SM.
+// Instead march over 128-wide diagonal blocks: a single CTA solves the block (column-oriented substitution out of
+// shared memory), then a grid-wide GEMV removes its contribution from the remaining rows — L is streamed exactly once.
+// --------------------------------------------------------------------------------------------------------------
+constexpr int VB = 128;
+
+template <bool TRANS>
+__global__ void __launch_bounds__(VB) trsv_diag_kernel(const double* __restrict__ L, int n, int b0,
+                                                       double* __restrict__ x) {
+  extern __shared__ double S[];  // [VB][VB+1] lower block of L (row r, col c at S[r*(VB+1)+c])
+  __shared__ double xs[VB];
+  const int t = threadIdx.x;
+  const int nb = min(VB, n - b0);
+  for (int c = 0; c < nb; ++c)
+    if (t < nb && t >= c) S[t * (VB + 1) + c] = L[static_cast<size_t>(b0 + c) * n + b0 + t];
+  double v = (t < nb) ? x[b0 + t] : 0.0;
+  __syncthreads();
+  for (int s = 0; s < nb; ++s) {
+    const int c = TRANS ? (nb - 1 - s) : s;
+    if (t == c) {
+      v = v / S[c * (VB + 1) + c];
+      xs[c] = v;
+    }
+    __syncthreads();
+    const double xc = xs[c];
+    if (!TRANS) {
+      if (t > c && t < nb) v = v - xc * S[t * (VB + 1) + c];
+    } else {
+      if (t < c) v = v - S[c * (VB + 1) + t] * xc;
+    }
+  }
+  if (t < nb) x[b0 + t] = v;
+}
+
+// forward: x[i] -= sum_c L[i, b0+c] x[b0+c] for i >= b0+nb ; one thread per row, coalesced down the columns
+__global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* __restrict__ L, int n, int b0, int nb,
+                                                              double* __restrict__ x) {
+  __shared__ double xs[VB];
+  if (threadIdx.x < nb) xs[threadIdx.x] = x[b0 + threadIdx.x];
+  __syncthreads();
+  const int i = b0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc0 = 0.0, acc1 = 0.0;
+  const double* col = L + static_cast<size_t>(b0) * n + i;
+  int c = 0;
+  for (; c + 1 < nb; c += 2) {
+    acc0 = fma(col[static_cast<size_t>(c) * n], xs[c], acc0);
+    acc1 = fma(col[static_cast<size_t>(c + 1) * n], xs[c + 1], acc1);
+  }
+  if (c < nb) acc0 = fma(col[static_cast<size_t>(c) * n], xs[c], acc0);
+  x[i] = x[i] - (acc0 + acc1);
+}
+
+// backward: x[i] -= sum_r L[b0+r, i] x[b0+r] for i < b0 ; one warp per column i (contiguous read), shuffle reduce
+__global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __restrict__ L, int n, int b0, int nb,
+                                                              double* __restrict__ x) {
+  __shared__ double xs[VB];
+  if (threadIdx.x < nb) xs[threadIdx.x] = x[b0 + threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= b0) return;
+  const double* col = L + static_cast<size_t>(i) * n + b0;
+  double acc = 0.0;
+  for (int r = lane; r < nb; r += 32) acc = fma(col[r], xs[r], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) x[i] = x[i] - acc;
+}
+
+void trsv_blocked(const double* L, int n, double* x, bool trans, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(VB) * (VB + 1) * sizeof(double);
+  CMOE_CUDA(cudaFuncSetAttribute(trsv_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CMOE_CUDA(cudaFuncSetAttribute(trsv_diag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int nblk = (n + VB - 1) / VB;
+  for (int step = 0; step < nblk; ++step) {
+    const int b = trans ? (nblk - 1 - step) : step;
+    const int b0 = b * VB, nb = min(VB, n - b0);
+    if (!trans) {
+      trsv_diag_kernel<false><<<1, VB, smem, s>>>(L, n, b0, x);
+      const int rest = n - b0 - nb;
+      if (rest > 0) trsv_update_fwd_kernel<<<(rest + 255) / 256, 256, 0, s>>>(L, n, b0, nb, x);
+    } else {
+      trsv_diag_kernel<true><<<1, VB, smem, s>>>(L, n, b0, x);
+      if (b0 > 0) trsv_update_bwd_kernel<<<(b0 + 7) / 8, 256, 0, s>>>(L, n, b0, nb, x);
+    }
+    g_launches += 2;
+  }
+  CMOE_CUDA(cudaGetLastError());
+}
+
+
+
 }  // namespace
 
 int launches_issued() { return g_launches; }
@@ -329,6 +422,10 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
 
 void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s) {
   if (n == 0 || nrhs == 0) return;
+  if (nrhs <= 4 && n >= 1024) {
+    for (int r = 0; r < nrhs; ++r) trsv_blocked(L, n, X + static_cast<size_t>(r) * ldx, trans, s);
+    return;
+  }
   const int grid = (nrhs + kTrsmNB - 1) / kTrsmNB;
   if (trans) {
     trsm_kernel<true><<<grid, 256, 0, s>>>(L, n, X, ldx, nrhs);
