@@ -17,7 +17,8 @@ namespace cmoe {
 namespace {
 
 constexpr int TR = 128;  // point rows per tile
-constexpr int TC = 32;   // point cols per tile
+constexpr int TC = 32;   // point cols per sub-tile
+constexpr int TCW = 64;  // point cols per CTA tile (TCW / TC sub-tiles share the staged row slab)
 
 // g == 0 fast path: K[i + j*n] for i >= j (tile granularity), noise[0] on the diagonal.
 // Works on length-scaled coordinates Xs = X / l (so r^2 is a plain sum of squared differences: 2 FP64 ops per
@@ -27,20 +28,28 @@ __global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant
                                                            const double* __restrict__ noise, double* __restrict__ K) {
   extern __shared__ double sm[];
   const int dim = spec.dim;
-  double* Xr = sm;               // [dim][TR]  coordinate-major: a lane's 4 rows are 32 contiguous bytes
-  double* Xc = sm + TR * dim;    // [dim][TC]  (a warp shares its 4 columns: broadcast reads)
-  const int tr = blockIdx.y, tc = blockIdx.x;
-  const int row0 = tr * TR, col0 = tc * TC;
-  if (col0 > row0 + TR - 1) return;  // tile entirely above the diagonal
+  double* Xr = sm;               // [dim][TR]   coordinate-major: a lane's 4 rows are 32 contiguous bytes
+  double* Xc = sm + TR * dim;    // [dim][TCW]  (a warp shares its 4 columns: broadcast reads)
+  // linear block index -> (tile row tr, tile col tc) of the lower-triangular tile grid: tc*TCW <= tr*TR + TR - 1
+  constexpr int kColsPerRow = TR / TCW;  // col tiles that fit under one row tile's diagonal extent
+  int tr = static_cast<int>((sqrt(8.0 * (blockIdx.x / kColsPerRow) + 1.0) - 1.0) * 0.5);
+  while (tr * (tr + 1) / 2 * kColsPerRow > static_cast<int>(blockIdx.x)) --tr;
+  while ((tr + 1) * (tr + 2) / 2 * kColsPerRow <= static_cast<int>(blockIdx.x)) ++tr;
+  const int tc = blockIdx.x - tr * (tr + 1) / 2 * kColsPerRow;
+  const int row0 = tr * TR, colbase = tc * TCW;
+  if (colbase >= N) return;
   for (int e = threadIdx.x; e < TR * dim; e += blockDim.x) {
     const int r = row0 + e % TR, k = e / TR;
     Xr[e] = (r < N) ? Xs[static_cast<size_t>(r) * dim + k] : 0.0;
   }
-  for (int e = threadIdx.x; e < TC * dim; e += blockDim.x) {
-    const int c = col0 + e % TC, k = e / TC;
+  for (int e = threadIdx.x; e < TCW * dim; e += blockDim.x) {
+    const int c = colbase + e % TCW, k = e / TCW;
     Xc[e] = (c < N) ? Xs[static_cast<size_t>(c) * dim + k] : 0.0;
   }
   __syncthreads();
+  for (int sub = 0; sub < TCW / TC; ++sub) {
+  const int col0 = colbase + sub * TC;
+  if (col0 > row0 + TR - 1 || col0 >= N) break;  // sub-tile entirely above the diagonal
   const int rg = threadIdx.x & 31;  // rows rg*4 .. rg*4+3
   const int cg = threadIdx.x >> 5;  // cols cg*4 .. cg*4+3
   const double nz = noise[0];
@@ -55,8 +64,8 @@ __global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant
   for (int k = 0; k < dim; ++k) {
     const double2 ra = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4);
     const double2 rb = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4 + 2);
-    const double2 ca = *reinterpret_cast<const double2*>(Xc + k * TC + cg * 4);
-    const double2 cb = *reinterpret_cast<const double2*>(Xc + k * TC + cg * 4 + 2);
+    const double2 ca = *reinterpret_cast<const double2*>(Xc + k * TCW + sub * TC + cg * 4);
+    const double2 cb = *reinterpret_cast<const double2*>(Xc + k * TCW + sub * TC + cg * 4 + 2);
     const double xr[4] = {ra.x, ra.y, rb.x, rb.y};
     const double xc[4] = {ca.x, ca.y, cb.x, cb.y};
 #pragma unroll
@@ -96,6 +105,7 @@ __global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant
         if (gr + rr < N) dst[rr] = v[rr];
     }
   }
+  }  // sub-tiles
 }
 
 // generic path (derivative observations): one thread per point pair, writes the (1+g)x(1+g) block
@@ -163,8 +173,9 @@ __global__ void philox_table_kernel(uint64_t seed, uint64_t first_draw, int num_
 void build_covariance(const KernelSpec& spec, const double* X, const double* Xs, int N, const double* noise,
                       double* K, cudaStream_t s) {
   if (spec.g == 0) {
-    dim3 grid((N + TC - 1) / TC, (N + TR - 1) / TR);
-    const size_t smem = static_cast<size_t>(TR + TC) * spec.dim * sizeof(double);
+    const int trows = (N + TR - 1) / TR;
+    dim3 grid(trows * (trows + 1) / 2 * (TR / TCW));
+    const size_t smem = static_cast<size_t>(TR + TCW) * spec.dim * sizeof(double);
     cov_build_g0_kernel<<<grid, 256, smem, s>>>(spec, Xs, N, noise, K);
   } else {
     dim3 grid((N + 31) / 32, (N + 7) / 8);

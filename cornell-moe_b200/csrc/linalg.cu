@@ -27,61 +27,66 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int 
   extern __shared__ double dyn_smem[];
   double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
   double (*V)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  __shared__ int failed;
+  __shared__ double rdiag[NB];
   if (*flag != 0) return;
   const int tid = threadIdx.x;
+  const int r = tid & (NB - 1);   // row owned by this thread
+  const int cq = tid >> 6;        // column residue class (columns cq, cq+4, ...)
   double* Ab = A + static_cast<size_t>(k0) * lda + k0;
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e % NB, j = e / NB;
-    S[i][j] = (i < nb && j < nb && i >= j) ? Ab[static_cast<size_t>(j) * lda + i] : 0.0;
-  }
-  if (tid == 0) failed = 0;
+#pragma unroll 4
+  for (int c = cq; c < NB; c += 4) S[r][c] = (r < nb && c < nb && r >= c) ? Ab[static_cast<size_t>(c) * lda + r] : 0.0;
   __syncthreads();
+  // The column recurrence sqrt -> divide -> update is the latency-critical chain of the whole factorisation, so every
+  // thread evaluates the pivot test and the square root itself (uniform outcome, no flag round trip) and there are
+  // only two barriers per column.
+  int failed = 0;
   for (int j = 0; j < nb; ++j) {
-    if (tid == 0) {
-      const double piv = S[j][j];
-      if (piv > kPivotTol) {
-        S[j][j] = sqrt(piv);
-      } else {
-        failed = k0 + j + 1;
-      }
+    const double piv = S[j][j];
+    if (!(piv > kPivotTol)) {  // gpp_linear_algebra.cpp:118
+      failed = k0 + j + 1;
+      break;
+    }
+    const double ljj = sqrt(piv);
+    const double lrj = S[r][j] / ljj;
+    __syncthreads();  // everybody has read column j and the pivot
+    if (cq == 0) {
+      if (r == j) S[j][j] = ljj;
+      if (r > j && r < nb) S[r][j] = lrj;
     }
     __syncthreads();
-    if (failed) break;
-    const double ljj = S[j][j];
-    for (int i = j + 1 + tid; i < nb; i += blockDim.x) S[i][j] /= ljj;
-    __syncthreads();
-    // trailing update of the lower triangle: S[i][c] -= S[i][j] * S[c][j], c in (j, nb), i in [c, nb)
-    const int m = nb - j - 1;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      const int c = j + 1 + e / m, i = j + 1 + e % m;
-      if (i >= c) S[i][c] = S[i][c] - S[i][j] * S[c][j];
-    }
+    // trailing update of the lower triangle: S[r][c] -= l_rj * l_cj for my columns c in (j, nb), r >= c
+    const int c0 = j + 1 + ((cq - (j + 1)) & 3);
+#pragma unroll 4
+    for (int c = c0; c < nb; c += 4)
+      if (r >= c && r < nb) S[r][c] = S[r][c] - lrj * S[c][j];
     __syncthreads();
   }
   if (failed) {
     if (tid == 0) *flag = failed;
     return;
   }
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e % NB, j = e / NB;
-    if (i < nb && j < nb && i >= j) Ab[static_cast<size_t>(j) * lda + i] = S[i][j];
-  }
-  // inv(L_kk): thread c solves L x = e_c by forward substitution; result column-major nb x nb with ld NB.
+#pragma unroll 4
+  for (int c = cq; c < NB; c += 4)
+    if (r < nb && c < nb && r >= c) Ab[static_cast<size_t>(c) * lda + r] = S[r][c];
+  // inv(L_kk) by column-oriented substitution on the identity, all 256 threads: V starts as I, then for each j
+  //   row j *= 1/L_jj ;  rows i > j: V[i][:] -= L_ij V[j][:]      (reciprocals of the diagonal taken once, in parallel)
   if (invL != nullptr) {
-    if (tid < NB) {
-      const int c = tid;
-      for (int i = 0; i < NB; ++i) {
-        double v = 0.0;
-        if (i < nb && c < nb && i >= c) {
-          double acc = (i == c) ? 1.0 : 0.0;
-          for (int m2 = c; m2 < i; ++m2) acc -= S[i][m2] * V[m2][c];
-          v = acc / S[i][i];
-        }
-        V[i][c] = v;
-      }
-    }
+#pragma unroll 4
+    for (int c = cq; c < NB; c += 4) V[r][c] = (r == c && r < nb) ? 1.0 : 0.0;
+    if (cq == 0) rdiag[r] = (r < nb) ? 1.0 / S[r][r] : 0.0;
     __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+      // only columns c <= j of row j are non-zero
+      if (r == j)
+        for (int c = cq; c <= j; c += 4) V[j][c] = V[j][c] * rdiag[j];
+      __syncthreads();
+      if (r > j && r < nb) {
+        const double lij = S[r][j];
+#pragma unroll 4
+        for (int c = cq; c <= j; c += 4) V[r][c] = V[r][c] - lij * V[j][c];
+      }
+      __syncthreads();
+    }
     for (int e = tid; e < NB * NB; e += blockDim.x) invL[e] = V[e % NB][e / NB];
   }
 }
@@ -108,7 +113,7 @@ __device__ __forceinline__ void load_tile(double* __restrict__ T, const double* 
 }
 
 __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                        const double* __restrict__ invL, int mode,
+                                                        const double* __restrict__ invL, int mode, int col_tiles,
                                                         const int* __restrict__ flag) {
   extern __shared__ double smem[];
   if (*flag != 0) return;
@@ -120,12 +125,10 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
     ti = blockIdx.x;
     tj = 0;
   } else {
-    // linear index -> (ti >= tj) of the lower-triangular tile grid
-    const int b = blockIdx.x;
-    ti = static_cast<int>((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
-    while (ti * (ti + 1) / 2 > b) --ti;
-    while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
-    tj = b - ti * (ti + 1) / 2;
+    // rectangular grid (row tiles x the col tiles that remain inside the outer panel); keep the lower triangle
+    ti = blockIdx.x / col_tiles;
+    tj = blockIdx.x % col_tiles;
+    if (tj > ti) return;
   }
   const int row0 = t0 + ti * NB;
   const int rows = min(NB, n - row0);
@@ -189,6 +192,113 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
           }
         }
       }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Outer trailing update of the two-level blocked Cholesky:
+//     C(128x128 tile of the trailing matrix, lower tiles only) -= A_rows(128 x W) * A_cols(128 x W)^T
+// 8 warps (4 x 2), each a 32x64 sub-tile = 4x8 m8n8k4 DMMA fragments (64 FP64 accumulators per thread); operands are
+// streamed in K-chunks of 16 through a 3-stage cp.async pipeline; the accumulator tile is staged through shared memory
+// so that the read-modify-write of C is fully coalesced.
+// --------------------------------------------------------------------------------------------------------------
+constexpr int GT = 128;       // tile edge
+constexpr int GK = 16;        // K chunk
+constexpr int GST = 3;        // pipeline stages
+constexpr int GLD = GT + 4;   // 132 = 4 (mod 16): conflict-free fragment loads
+
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  const int bytes = valid ? 8 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ A, int lda, int n, int p0, int W,
+                                                           const int* __restrict__ flag) {
+  extern __shared__ double gsm[];
+  if (*flag != 0) return;
+  const int t0 = p0 + W;
+  const int b = blockIdx.x;
+  int ti = static_cast<int>((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+  while (ti * (ti + 1) / 2 > b) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
+  const int tj = b - ti * (ti + 1) / 2;
+  const int row0 = t0 + ti * GT, col0 = t0 + tj * GT;
+  const int rows = min(GT, n - row0), cols = min(GT, n - col0);
+  double* As = gsm;                    // [GST][GK][GLD]
+  double* Bs = gsm + GST * GK * GLD;   // [GST][GK][GLD]
+  const double* Ag = A + static_cast<size_t>(p0) * lda + row0;
+  const double* Bg = A + static_cast<size_t>(p0) * lda + col0;
+  const int tid = threadIdx.x;
+  const int nchunks = W / GK;
+
+  auto load_chunk = [&](int kc, int stage) {
+    double* as = As + stage * GK * GLD;
+    double* bs = Bs + stage * GK * GLD;
+#pragma unroll
+    for (int e = tid; e < GT * GK; e += 256) {
+      const int m = e % GT, k = e / GT;
+      cp_async8(as + k * GLD + m, Ag + static_cast<size_t>(kc * GK + k) * lda + m, m < rows);
+      cp_async8(bs + k * GLD + m, Bg + static_cast<size_t>(kc * GK + k) * lda + m, m < cols);
+    }
+  };
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int lr = lane >> 2, lc = lane & 3;
+  double acc[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int st = 0; st < GST - 1; ++st) {
+    if (st < nchunks) load_chunk(st, st);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < nchunks; ++kc) {
+    cp_async_wait<GST - 2>();
+    __syncthreads();
+    const int nxt = kc + GST - 1;
+    if (nxt < nchunks) load_chunk(nxt, nxt % GST);
+    cp_async_commit();
+    const double* as = As + (kc % GST) * GK * GLD;
+    const double* bs = Bs + (kc % GST) * GK * GLD;
+#pragma unroll
+    for (int kk = 0; kk < GK; kk += 4) {
+      double a[4], bb[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = as[(kk + lc) * GLD + wm + i * 8 + lr];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bb[j] = bs[(kk + lc) * GLD + wn + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // stage the accumulator tile: Cs[c][r] (column-major, ld GLD), then coalesced C -= Cs
+  double* Cs = gsm;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) Cs[(wn + j * 8 + lc * 2 + h) * GLD + wm + i * 8 + lr] = acc[i][j][h];
+  __syncthreads();
+  double* Cg = A + static_cast<size_t>(col0) * lda + row0;
+  for (int e = tid; e < GT * GT; e += 256) {
+    const int r = e % GT, c = e / GT;
+    if (r < rows && c < cols) {
+      double* dst = Cg + static_cast<size_t>(c) * lda + r;
+      *dst = *dst - Cs[c * GLD + r];
     }
   }
 }
@@ -311,14 +421,19 @@ __global__ void __launch_bounds__(VB) trsv_diag_kernel(const double* __restrict_
   __shared__ double xs[VB];
   const int t = threadIdx.x;
   const int nb = min(VB, n - b0);
-  for (int c = 0; c < nb; ++c)
-    if (t < nb && t >= c) S[t * (VB + 1) + c] = L[static_cast<size_t>(b0 + c) * n + b0 + t];
+#pragma unroll 8
+  for (int c = 0; c < VB; ++c) {
+    double v = 0.0;
+    if (t < nb && c <= t) v = L[static_cast<size_t>(b0 + c) * n + b0 + t];
+    S[t * (VB + 1) + c] = v;
+  }
   double v = (t < nb) ? x[b0 + t] : 0.0;
+  const double rd = (t < nb) ? 1.0 / L[static_cast<size_t>(b0 + t) * n + b0 + t] : 0.0;  // off the critical chain
   __syncthreads();
   for (int s = 0; s < nb; ++s) {
     const int c = TRANS ? (nb - 1 - s) : s;
     if (t == c) {
-      v = v / S[c * (VB + 1) + c];
+      v = v * rd;
       xs[c] = v;
     }
     __syncthreads();
@@ -332,23 +447,30 @@ __global__ void __launch_bounds__(VB) trsv_diag_kernel(const double* __restrict_
   if (t < nb) x[b0 + t] = v;
 }
 
-// forward: x[i] -= sum_c L[i, b0+c] x[b0+c] for i >= b0+nb ; one thread per row, coalesced down the columns
+// forward: x[i] -= sum_c L[i, b0+c] x[b0+c] for i >= b0+nb.  CTA = 64 rows x 4 column quarters (coalesced down the
+// columns, 4-way unrolled for memory-level parallelism), quarters combined through shared memory in a fixed order.
 __global__ void __launch_bounds__(256) trsv_update_fwd_kernel(const double* __restrict__ L, int n, int b0, int nb,
                                                               double* __restrict__ x) {
   __shared__ double xs[VB];
+  __shared__ double part[4][64];
   if (threadIdx.x < nb) xs[threadIdx.x] = x[b0 + threadIdx.x];
   __syncthreads();
-  const int i = b0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double acc0 = 0.0, acc1 = 0.0;
-  const double* col = L + static_cast<size_t>(b0) * n + i;
-  int c = 0;
-  for (; c + 1 < nb; c += 2) {
-    acc0 = fma(col[static_cast<size_t>(c) * n], xs[c], acc0);
-    acc1 = fma(col[static_cast<size_t>(c + 1) * n], xs[c + 1], acc1);
+  const int rl = threadIdx.x & 63, qd = threadIdx.x >> 6;
+  const int i = b0 + nb + blockIdx.x * 64 + rl;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (i < n) {
+    const int cbeg = qd * (VB / 4), cend = min(nb, cbeg + VB / 4);
+    const double* col = L + static_cast<size_t>(b0) * n + i;
+    int c = cbeg;
+    for (; c + 3 < cend; c += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fma(col[static_cast<size_t>(c + u) * n], xs[c + u], acc[u]);
+    }
+    for (; c < cend; ++c) acc[0] = fma(col[static_cast<size_t>(c) * n], xs[c], acc[0]);
   }
-  if (c < nb) acc0 = fma(col[static_cast<size_t>(c) * n], xs[c], acc0);
-  x[i] = x[i] - (acc0 + acc1);
+  part[qd][rl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (qd == 0 && i < n) x[i] = x[i] - ((part[0][rl] + part[1][rl]) + (part[2][rl] + part[3][rl]));
 }
 
 // backward: x[i] -= sum_r L[b0+r, i] x[b0+r] for i < b0 ; one warp per column i (contiguous read), shuffle reduce
@@ -378,7 +500,7 @@ void trsv_blocked(const double* L, int n, double* x, bool trans, cudaStream_t s)
     if (!trans) {
       trsv_diag_kernel<false><<<1, VB, smem, s>>>(L, n, b0, x);
       const int rest = n - b0 - nb;
-      if (rest > 0) trsv_update_fwd_kernel<<<(rest + 255) / 256, 256, 0, s>>>(L, n, b0, nb, x);
+      if (rest > 0) trsv_update_fwd_kernel<<<(rest + 63) / 64, 256, 0, s>>>(L, n, b0, nb, x);
     } else {
       trsv_diag_kernel<true><<<1, VB, smem, s>>>(L, n, b0, x);
       if (b0 > 0) trsv_update_bwd_kernel<<<(b0 + 7) / 8, 256, 0, s>>>(L, n, b0, nb, x);
@@ -396,24 +518,44 @@ int launches_issued() { return g_launches; }
 void count_launch(int n) { g_launches += n; }
 
 void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
+  constexpr int W = 256;  // outer panel width (4 inner blocks of NB)
   const size_t smem = 2 * NB * LDT * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   const size_t smem_potf2 = 2 * NB * (NB + 1) * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_potf2)));
+  const size_t smem_gemm = static_cast<size_t>(GT) * GLD * sizeof(double);  // >= 2*GST*GK*GLD doubles as well
+  static_assert(GT * GLD >= 2 * GST * GK * GLD, "accumulator staging must cover the pipeline buffers");
+  CMOE_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem_gemm)));
   CMOE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
   DevBuf<double> invL(NB * NB);
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = min(NB, n - k0);
-    const int rem = n - k0 - nb;
-    potf2_kernel<<<1, 256, smem_potf2, s>>>(A, n, k0, nb, rem > 0 ? invL.p : nullptr, flag);
-    count_launch();
-    if (rem > 0) {
-      const int tiles = (rem + NB - 1) / NB;
-      dmma_tile_kernel<<<tiles, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 0, flag);
-      dmma_tile_kernel<<<tiles * (tiles + 1) / 2, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 1, flag);
-      count_launch(2);
+  for (int p0 = 0; p0 < n; p0 += W) {
+    const int pw = min(W, n - p0);         // this panel's width
+    const int pend = p0 + pw;
+    for (int k0 = p0; k0 < pend; k0 += NB) {
+      const int nb = min(NB, n - k0);
+      const int rem = n - k0 - nb;
+      potf2_kernel<<<1, 256, smem_potf2, s>>>(A, n, k0, nb, rem > 0 ? invL.p : nullptr, flag);
+      count_launch();
+      if (rem > 0) {
+        const int row_tiles = (rem + NB - 1) / NB;
+        dmma_tile_kernel<<<row_tiles, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 0, 1, flag);
+        count_launch();
+        // inner trailing update: only the columns that still belong to this outer panel
+        const int col_tiles = (pend - (k0 + nb) + NB - 1) / NB;
+        if (col_tiles > 0) {
+          dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 1, col_tiles, flag);
+          count_launch();
+        }
+      }
+    }
+    const int rem = n - pend;
+    if (rem > 0 && pw == W) {
+      const int tiles = (rem + GT - 1) / GT;
+      dmma_gemm_kernel<<<tiles * (tiles + 1) / 2, 256, smem_gemm, s>>>(A, n, n, p0, W, flag);
+      count_launch();
     }
   }
   CMOE_CUDA(cudaGetLastError());
