@@ -47,25 +47,33 @@ __global__ void pack_xt_kernel(const __grid_constant__ KernelSpec spec, const do
   Xt[e] = (d < spec.dim) ? X[static_cast<size_t>(j) * spec.dim + d] * spec.inv_len[d] : 0.0;
 }
 
-// per-candidate operand packs for the MC kernel (g == 0: rows == training points, Q == U)
+// per-candidate operand packs for the MC kernel.  Training point j owns rows (j, m), m = 0..g; the pack row is
+//   [ e_j | beta_(j,0), B_(j,0),0..QP-1 | beta~_(j,1), B~_(j,1),: | ... ]   (~ = divided by l_t, t = derivs[m-1])
+// so that derivative rows multiply plain scaled coordinate differences in the kernel.  stride = 1 + (1+g)(QP+1) (even).
 __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int ps,
-                                                      int num_pts, int DIMP, int QP, const double* __restrict__ Xt,
-                                                      const double* __restrict__ beta, const double* __restrict__ B,
-                                                      const double* __restrict__ P, const double* __restrict__ D,
-                                                      double* __restrict__ Pk, double* __restrict__ Xu,
-                                                      double* __restrict__ A, double* __restrict__ Afull) {
-  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim;
+                                                      int num_pts, int DIMP, int QP, int stride,
+                                                      const double* __restrict__ Xt, const double* __restrict__ beta,
+                                                      const double* __restrict__ B, const double* __restrict__ P,
+                                                      const double* __restrict__ D, double* __restrict__ Pk,
+                                                      double* __restrict__ Xu, double* __restrict__ A,
+                                                      double* __restrict__ Afull) {
+  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, b1 = 1 + spec.g, n = N * b1, Q = U * b1;
   const bool se = spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL;
   const double lna = log(spec.alpha);
-  double* pk = Pk + static_cast<size_t>(c) * N * (QP + 2);
-  const double* Bc = B + static_cast<size_t>(c) * U * N;
+  double* pk = Pk + static_cast<size_t>(c) * N * stride;
+  const double* Bc = B + static_cast<size_t>(c) * Q * n;
   for (int j = tid; j < N; j += blockDim.x) {
     double nrm = 0.0;
     for (int d = 0; d < DIMP; ++d) nrm = fma(Xt[j * DIMP + d], Xt[j * DIMP + d], nrm);
-    double* o = pk + static_cast<size_t>(j) * (QP + 2);
+    double* o = pk + static_cast<size_t>(j) * stride;
     o[0] = se ? (lna - 0.5 * nrm) : nrm;
-    o[1] = beta[j];
-    for (int u = 0; u < QP; ++u) o[2 + u] = (u < U) ? Bc[static_cast<size_t>(u) * N + j] : 0.0;
+    for (int m = 0; m < b1; ++m) {
+      const double sc = m ? spec.inv_len[spec.derivs[m - 1]] : 1.0;
+      double* row = o + 1 + m * (QP + 1);
+      row[0] = beta[j * b1 + m] * sc;
+      for (int u = 0; u < QP; ++u) row[1 + u] = (u < Q) ? Bc[static_cast<size_t>(u) * n + j * b1 + m] * sc : 0.0;
+    }
+    for (int e = 1 + b1 * (QP + 1); e < stride; ++e) o[e] = 0.0;
   }
   const double* Pc = P + static_cast<size_t>(c) * U * dim;
   double* xu = Xu + static_cast<size_t>(c) * U * (DIMP + 2);
@@ -96,8 +104,8 @@ __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ Ke
   }
 }
 
-// W = L^-1 Cov_n(Xu, A), mu_n(A), best_posterior and its arg-min, one CTA per candidate.
-// KAu = K(X, A_union part) [n][nc*U], KD = K(X, D) [n][num_pts] (shared by all candidates), muD = mu_n(D).
+// W = L^-1 Cov_n(Xu rows, A), mu_n(A), best_posterior and its arg-min, one CTA per candidate.
+// KAu = K(X rows, A_union part) [n][nc*U], KD = K(X rows, D) [n][num_pts] (shared by all candidates), muD = mu_n(D).
 __global__ void __launch_bounds__(256) kg_discrete_kernel(const __grid_constant__ KernelSpec spec, int n, int U,
                                                           int num_pts, int QP, double mean, double best_so_far,
                                                           const double* __restrict__ beta,
@@ -114,13 +122,13 @@ __global__ void __launch_bounds__(256) kg_discrete_kernel(const __grid_constant_
                                                           double* __restrict__ muA, double* __restrict__ best_post,
                                                           int* __restrict__ winner) {
   extern __shared__ double sm[];
-  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, M = U + num_pts;
+  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, M = U + num_pts, bs = 1 + spec.g, Q = U * bs;
   if (fail[c] != 0) return;
-  double* Ls = sm;  // [U][U] column-major
-  for (int e = tid; e < U * U; e += blockDim.x) Ls[e] = chol[static_cast<size_t>(c) * U * U + e];
+  double* Ls = sm;  // [Q][Q] column-major
+  for (int e = tid; e < Q * Q; e += blockDim.x) Ls[e] = chol[static_cast<size_t>(c) * Q * Q + e];
   __syncthreads();
   const double* Pc = P + static_cast<size_t>(c) * U * dim;
-  const double* Bc = B + static_cast<size_t>(c) * U * n;
+  const double* Bc = B + static_cast<size_t>(c) * Q * n;
   double* Wc = W + static_cast<size_t>(c) * M * QP;
   for (int j = tid; j < M; j += blockDim.x) {
     const double* kcol = (j < U) ? (KAu + (static_cast<size_t>(c) * U + j) * n) : (KD + static_cast<size_t>(j - U) * n);
@@ -135,28 +143,28 @@ __global__ void __launch_bounds__(256) kg_discrete_kernel(const __grid_constant_
     }
     muA[static_cast<size_t>(c) * M + j] = m;
     double v[kMaxQ];
-    for (int a = 0; a < U; ++a) {
+    for (int a = 0; a < Q; ++a) {
       const double* ba = Bc + static_cast<size_t>(a) * n;
       double t = 0.0;
       for (int r = 0; r < n; ++r) t += ba[r] * kcol[r];
-      const double* pa = Pc + a * dim;
+      const double* pa = Pc + (a / bs) * dim;
       const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pa, aj));
-      v[a] = kp.A - t;
+      v[a] = cov_entry(spec, kp, pa, aj, row_type(a % bs, spec.derivs), -1) - t;
     }
     // forward substitution  L w = v
-    for (int a = 0; a < U; ++a) {
+    for (int a = 0; a < Q; ++a) {
       double t = v[a];
-      for (int b = 0; b < a; ++b) t -= Ls[a + b * U] * v[b];
-      v[a] = t / Ls[a + a * U];
+      for (int b = 0; b < a; ++b) t -= Ls[a + b * Q] * v[b];
+      v[a] = t / Ls[a + a * Q];
     }
-    for (int a = 0; a < QP; ++a) Wc[static_cast<size_t>(j) * QP + a] = (a < U) ? v[a] : 0.0;
+    for (int a = 0; a < QP; ++a) Wc[static_cast<size_t>(j) * QP + a] = (a < Q) ? v[a] : 0.0;
   }
   if (tid == 0) {
-    // best_posterior = min(best_so_far, min_j mu_j) with the first strict minimiser (...cpp:146-153)
+    // best_posterior = min(best_so_far, min_j mu_j) over the function-value rows, first strict minimiser (...cpp:146-153)
     double bp = best_so_far;
     int w = -1;
     for (int j = 0; j < U; ++j) {
-      const double m = mu[static_cast<size_t>(c) * U + j];
+      const double m = mu[static_cast<size_t>(c) * Q + j * bs];
       if (m < bp) {
         bp = m;
         w = j;
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(256) kg_discrete_kernel(const __grid_constant_
 }
 
 // per sample: normals (antithetic pairs), c = L^-T z, arg-min of mu_n(A_j) + W_j . z over the discretisation set
-__global__ void __launch_bounds__(256) kg_prep_kernel(int U, int M, int QP, int num_mc, uint64_t seed,
+__global__ void __launch_bounds__(256) kg_prep_kernel(int Q, int M, int QP, int num_mc, uint64_t seed,
                                                       const double* __restrict__ table,
                                                       const double* __restrict__ chol, const double* __restrict__ W,
                                                       const double* __restrict__ muA, const int* __restrict__ fail,
@@ -178,9 +186,9 @@ __global__ void __launch_bounds__(256) kg_prep_kernel(int U, int M, int QP, int 
   const int c = blockIdx.y;
   if (fail[c] != 0) return;
   double* Ls = sm;
-  double* Ws = sm + U * U;
+  double* Ws = sm + Q * Q;
   double* ms = Ws + (w_in_smem ? static_cast<size_t>(M) * QP : 0);
-  for (int e = threadIdx.x; e < U * U; e += blockDim.x) Ls[e] = chol[static_cast<size_t>(c) * U * U + e];
+  for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) Ls[e] = chol[static_cast<size_t>(c) * Q * Q + e];
   const double* Wc = W + static_cast<size_t>(c) * M * QP;
   const double* mc_ = muA + static_cast<size_t>(c) * M;
   if (w_in_smem) {
@@ -196,13 +204,13 @@ __global__ void __launch_bounds__(256) kg_prep_kernel(int U, int M, int QP, int 
   const double sign = (s & 1) ? -1.0 : 1.0;  // odd iterations reuse -z of the previous one (...cpp:88-97)
   double z[kMaxQ];
   if (table != nullptr) {
-    for (int i = 0; i < U; ++i) z[i] = sign * table[static_cast<size_t>(pair) * U + i];
+    for (int i = 0; i < Q; ++i) z[i] = sign * table[static_cast<size_t>(pair) * Q + i];
   } else {
-    for (int k = 0; 2 * k < U; ++k) {
+    for (int k = 0; 2 * k < Q; ++k) {
       double a, b;
       philox_normal_pair(seed, static_cast<uint64_t>(pair), k, a, b);
       z[2 * k] = sign * a;
-      if (2 * k + 1 < U) z[2 * k + 1] = sign * b;
+      if (2 * k + 1 < Q) z[2 * k + 1] = sign * b;
     }
   }
   // arg-min over the discretisation set (first strict minimiser, ...cpp:436-449)
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(256) kg_prep_kernel(int U, int M, int QP, int 
   double best = 0.0;
   for (int j = 0; j < M; ++j) {
     double v = mp[j];
-    for (int a = 0; a < U; ++a) v = fma(Wp[static_cast<size_t>(j) * QP + a], z[a], v);
+    for (int a = 0; a < Q; ++a) v = fma(Wp[static_cast<size_t>(j) * QP + a], z[a], v);
     if (j == 0 || best > v) {
       best = v;
       arg = j;
@@ -218,13 +226,13 @@ __global__ void __launch_bounds__(256) kg_prep_kernel(int U, int M, int QP, int 
   }
   recStart[static_cast<size_t>(c) * num_mc + s] = arg;
   // c = L^-T z (back substitution)
-  for (int a = U - 1; a >= 0; --a) {
+  for (int a = Q - 1; a >= 0; --a) {
     double t = z[a];
-    for (int b = a + 1; b < U; ++b) t -= Ls[b + a * U] * z[b];
-    z[a] = t / Ls[a + a * U];
+    for (int b = a + 1; b < Q; ++b) t -= Ls[b + a * Q] * z[b];
+    z[a] = t / Ls[a + a * Q];
   }
   double* out = recC + (static_cast<size_t>(c) * num_mc + s) * QP;
-  for (int a = 0; a < QP; ++a) out[a] = (a < U) ? z[a] : 0.0;
+  for (int a = 0; a < QP; ++a) out[a] = (a < Q) ? z[a] : 0.0;
 }
 
 // KG[c] = best_posterior + mean_i best_function_value_i ; fixed-order reduction
@@ -244,66 +252,129 @@ __global__ void __launch_bounds__(256) kg_value_kernel(int num_mc, const double*
   if (threadIdx.x == 0) kg[c] = best_post[c] + total / static_cast<double>(num_mc);
 }
 
-// T' [a', a] = R[a'][N + a] - sum_j R[a'][j] B[j, a]   (must run BEFORE R is overwritten by K^-1 R)
-__global__ void __launch_bounds__(256) kg_tprime_kernel(int N, int U, int QP, const double* __restrict__ R,
+// T' [a', a] = R[a'][n + a] - sum_rows R[a'][row] B[row, a]   (must run BEFORE R is overwritten by K^-1 R)
+__global__ void __launch_bounds__(256) kg_tprime_kernel(int n, int Q, int QP, const double* __restrict__ R,
                                                         const double* __restrict__ B, double* __restrict__ Tp) {
   const int c = blockIdx.x;
-  const double* Rc = R + static_cast<size_t>(c) * QP * (N + U);
-  const double* Bc = B + static_cast<size_t>(c) * U * N;
-  for (int o = threadIdx.x; o < U * U; o += blockDim.x) {
-    const int ap = o / U, a = o % U;
-    const double* r = Rc + static_cast<size_t>(ap) * (N + U);
-    const double* b = Bc + static_cast<size_t>(a) * N;
+  const double* Rc = R + static_cast<size_t>(c) * QP * (n + Q);
+  const double* Bc = B + static_cast<size_t>(c) * Q * n;
+  for (int o = threadIdx.x; o < Q * Q; o += blockDim.x) {
+    const int ap = o / Q, a = o % Q;
+    const double* r = Rc + static_cast<size_t>(ap) * (n + Q);
+    const double* b = Bc + static_cast<size_t>(a) * n;
     double t = 0.0;
-    for (int j = 0; j < N; ++j) t += r[j] * b[j];
-    Tp[static_cast<size_t>(c) * U * U + o] = r[N + a] - t;
+    for (int j = 0; j < n; ++j) t += r[j] * b[j];
+    Tp[static_cast<size_t>(c) * Q * Q + o] = r[n + a] - t;
   }
 }
 
-// grad KG[c][p][d] = [p == winner] dmu_p[d] - (1/mc) ( G1 - sum_j dK*[d,j,p] (K^-1 R)[j,p] - <dL_pd, T> )
+// General (derivative-observation) version of the phase-2 accumulation: one thread per row of [X rows ; Xu rows],
+//   R[a][row] = sum_i c_ia K(row, x*_i)      in fixed sample order.
+__global__ void __launch_bounds__(128) kg_acc_gen_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int QP,
+                                                         int DIMP, int num_mc, const double* __restrict__ X,
+                                                         const double* __restrict__ P,
+                                                         const double* __restrict__ recC,
+                                                         const double* __restrict__ outX, double* __restrict__ R) {
+  const int cand = blockIdx.y, dim = spec.dim, b1 = 1 + spec.g, n = N * b1, Q = U * b1;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n + Q) return;
+  const bool is_u = row >= n;
+  const int pt = is_u ? (row - n) / b1 : row / b1;
+  const int ty = row_type(is_u ? (row - n) % b1 : row % b1, spec.derivs);
+  const double* xr = is_u ? (P + (static_cast<size_t>(cand) * U + pt) * dim) : (X + static_cast<size_t>(pt) * dim);
+  double acc[kMaxQ];
+  for (int a = 0; a < Q; ++a) acc[a] = 0.0;
+  const double* xs = outX + static_cast<size_t>(cand) * num_mc * DIMP;
+  const double* cs = recC + static_cast<size_t>(cand) * num_mc * QP;
+  for (int i = 0; i < num_mc; ++i) {
+    double xi[CMOE_MAX_DIM];
+    for (int d = 0; d < dim; ++d) xi[d] = xs[static_cast<size_t>(i) * DIMP + d] / spec.inv_len[d];
+    const KParts kp = kernel_parts(spec, weighted_sqdist(spec, xr, xi));
+    const double kval = cov_entry(spec, kp, xr, xi, ty, -1);
+    const double* ci = cs + static_cast<size_t>(i) * QP;
+    for (int a = 0; a < Q; ++a) acc[a] = fma(ci[a], kval, acc[a]);
+  }
+  double* Rc = R + static_cast<size_t>(cand) * QP * (n + Q);
+  for (int a = 0; a < Q; ++a) Rc[static_cast<size_t>(a) * (n + Q) + row] = acc[a];
+}
+
+// G1[p][d] = sum_i sum_m c_i,(p,m) d K(Xu_p row m, x*_i) / d Xu_p,d     (fixed sample order); grid nc, thread per (p, d)
+__global__ void __launch_bounds__(128) kg_g1_kernel(const __grid_constant__ KernelSpec spec, int U, int q, int QP,
+                                                    int DIMP, int num_mc, const double* __restrict__ P,
+                                                    const double* __restrict__ recC, const double* __restrict__ outX,
+                                                    double* __restrict__ G1) {
+  const int cand = blockIdx.x, dim = spec.dim, bs = 1 + spec.g;
+  const double* xs = outX + static_cast<size_t>(cand) * num_mc * DIMP;
+  const double* cs = recC + static_cast<size_t>(cand) * num_mc * QP;
+  for (int o = threadIdx.x; o < q * dim; o += blockDim.x) {
+    const int p = o / dim, d = o % dim;
+    const double* pp = P + (static_cast<size_t>(cand) * U + p) * dim;
+    double acc = 0.0;
+    for (int i = 0; i < num_mc; ++i) {
+      double xi[CMOE_MAX_DIM];
+      for (int e = 0; e < dim; ++e) xi[e] = xs[static_cast<size_t>(i) * DIMP + e] / spec.inv_len[e];
+      const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pp, xi));
+      const double* ci = cs + static_cast<size_t>(i) * QP;
+      for (int m = 0; m < bs; ++m)
+        acc = fma(ci[p * bs + m], grad_cov_entry(spec, kp, pp, xi, row_type(m, spec.derivs), -1, d), acc);
+    }
+    G1[(static_cast<size_t>(cand) * q + p) * dim + d] = acc;
+  }
+}
+
+// grad KG[c][p][d] = [p == winner] dmu_p[d] - (1/mc) ( G1 - sum_rows dK*[d,row,(p,m)] (K^-1 R)[row,(p,m)] - <dL_pd, T> )
+// G1 comes either from kg_g1_kernel (general) or from the fast-path accumulators Gu/GkB (g == 0).
 __global__ void __launch_bounds__(128) kg_grad_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int q,
                                                       int QP, int DIMP, int num_mc, const double* __restrict__ X,
                                                       const double* __restrict__ P, const double* __restrict__ Xu,
                                                       const double* __restrict__ R, const double* __restrict__ Tp,
                                                       const double* __restrict__ Gu, const double* __restrict__ GkB,
-                                                      const double* __restrict__ chol,
+                                                      const double* __restrict__ G1, const double* __restrict__ chol,
                                                       const double* __restrict__ gchol,
                                                       const double* __restrict__ gmu, const int* __restrict__ winner,
                                                       const int* __restrict__ fail, double* __restrict__ grad) {
   extern __shared__ double sm[];
-  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim;
+  const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, b1 = 1 + spec.g, n = N * b1, Q = U * b1;
   if (fail[c] != 0) return;
-  double* T = sm;  // [U][U] row a', col b
+  double* T = sm;  // [Q][Q] row a', col b
+  const double* Lc = chol + static_cast<size_t>(c) * Q * Q;
   // T L^T = T'  ->  row-wise forward substitution
-  for (int ap = tid; ap < U; ap += blockDim.x) {
-    for (int b = 0; b < U; ++b) {
-      double t = Tp[static_cast<size_t>(c) * U * U + ap * U + b];
-      for (int m = 0; m < b; ++m) t -= T[ap * U + m] * chol[static_cast<size_t>(c) * U * U + b + m * U];
-      T[ap * U + b] = t / chol[static_cast<size_t>(c) * U * U + b + b * U];
+  for (int ap = tid; ap < Q; ap += blockDim.x) {
+    for (int b = 0; b < Q; ++b) {
+      double t = Tp[static_cast<size_t>(c) * Q * Q + ap * Q + b];
+      for (int m = 0; m < b; ++m) t -= T[ap * Q + m] * Lc[b + m * Q];
+      T[ap * Q + b] = t / Lc[b + b * Q];
     }
   }
   __syncthreads();
   const double* Pc = P + static_cast<size_t>(c) * U * dim;
-  const double* Rc = R + static_cast<size_t>(c) * QP * (N + U);
+  const double* Rc = R + static_cast<size_t>(c) * QP * (n + Q);
   for (int o = tid; o < q * dim; o += blockDim.x) {
     const int p = o / dim, d = o % dim;
-    const double* xu = Xu + (static_cast<size_t>(c) * U + p) * (DIMP + 2);
-    const double t1 = spec.inv_len[d] * (Gu[(static_cast<size_t>(c) * U + p) * DIMP + d] -
-                                         xu[d] * GkB[static_cast<size_t>(c) * U + p]);
+    double t1;
+    if (G1 != nullptr) {
+      t1 = G1[(static_cast<size_t>(c) * q + p) * dim + d];
+    } else {
+      const double* xu = Xu + (static_cast<size_t>(c) * U + p) * (DIMP + 2);
+      t1 = spec.inv_len[d] * (Gu[(static_cast<size_t>(c) * U + p) * DIMP + d] - xu[d] * GkB[static_cast<size_t>(c) * U + p]);
+    }
     const double* pp = Pc + p * dim;
-    const double* kr = Rc + static_cast<size_t>(p) * (N + U);  // (K^-1 R)[:, p]
     double t2 = 0.0;
     for (int j = 0; j < N; ++j) {
       const double* xj = X + static_cast<size_t>(j) * dim;
       const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pp, xj));
-      t2 += grad_cov_entry(spec, kp, pp, xj, -1, -1, d) * kr[j];
+      for (int m = 0; m < b1; ++m) {
+        const double* kr = Rc + static_cast<size_t>(p * b1 + m) * (n + Q);  // (K^-1 R)[:, (p, m)]
+        for (int cc = 0; cc < b1; ++cc)
+          t2 += grad_cov_entry(spec, kp, pp, xj, row_type(m, spec.derivs), row_type(cc, spec.derivs), d) * kr[j * b1 + cc];
+      }
     }
-    const double* G = gchol + (static_cast<size_t>(c) * q + p) * U * U * dim;
+    const double* G = gchol + (static_cast<size_t>(c) * q + p) * Q * Q * dim;
     double t3 = 0.0;
-    for (int a = 0; a < U; ++a)
-      for (int b = 0; b <= a; ++b) t3 += G[(static_cast<size_t>(a) * U + b) * dim + d] * T[a * U + b];
+    for (int a = 0; a < Q; ++a)
+      for (int b = 0; b <= a; ++b) t3 += G[(static_cast<size_t>(a) * Q + b) * dim + d] * T[a * Q + b];
     double g = -(t1 - t2 - t3) / static_cast<double>(num_mc);
-    if (winner[c] == p) g += gmu[(static_cast<size_t>(c) * q + p) * dim + d];
+    if (winner[c] == p) g += gmu[(static_cast<size_t>(c) * q * b1 + p * b1) * dim + d];
     grad[(static_cast<size_t>(c) * q + p) * dim + d] = g;
   }
 }
@@ -324,10 +395,11 @@ void register_kg_entries(const KgDispatchEntry* entries, int count) {
   for (int i = 0; i < count; ++i) kg_table().push_back(entries[i]);
 }
 
-const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q) {
+const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q, bool need_gen) {
   const KgDispatchEntry* best = nullptr;
   for (const auto& e : kg_table()) {
     if (e.kernel != kernel || e.dim < dim || e.qp < Q) continue;
+    if (need_gen && e.mc_gen == nullptr) continue;
     if (!best || e.dim < best->dim || (e.dim == best->dim && e.qp < best->qp)) best = &e;
   }
   return best;
@@ -349,6 +421,7 @@ struct cmoe_kg_plan {
   cmoe_gd_params inner{};
   const KgDispatchEntry* entry = nullptr;
   int DIMP = 0, QP = 0, batch = 0, nc = 0;
+  int Q = 0, stride = 0;  // rows of the union block U*(1+g); doubles per training point in the operand pack
   bool use_smem = true;
   int chunk = 0;
   // static device data
@@ -356,7 +429,7 @@ struct cmoe_kg_plan {
   KgMcParams mcp{};
   // per-batch device scratch
   PosteriorBatch pb;
-  DevBuf<double> dPk, dXu, dA, dAfull, dKAu, dW, dMuA, dBestPost, dRecC, dOutVal, dOutX, dR, dGu, dGkB, dTp;
+  DevBuf<double> dPk, dXu, dA, dAfull, dKAu, dW, dMuA, dBestPost, dRecC, dOutVal, dOutX, dR, dGu, dGkB, dTp, dG1;
   DevBuf<int> dWinner, dRecStart;
   DevBuf<unsigned long long> dStats;
   // results
@@ -381,7 +454,8 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   const KernelSpec& spec = gp.spec;
   cudaStream_t s = gp.stream;
   const int N = gp.N, n = gp.n, dim = spec.dim, U = pl.U, q = pl.q, p = pl.p, M = pl.M, QP = pl.QP, DIMP = pl.DIMP;
-  const int mc = pl.num_mc;
+  const int mc = pl.num_mc, Q = pl.Q;
+  const bool gen = spec.g > 0;
   PosteriorBatch& pb = pl.pb;
   pb.configure(gp, nb, U, spec.derivs, spec.g, pl.want_grad ? q : 0, s);
   {
@@ -393,12 +467,12 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   pb.run(gp, /*diag_mode=*/2, /*want_chol=*/true, pl.want_grad, s);
   CMOE_CUDA(cudaMemcpyAsync(pl.dFailAll.p + c0, pb.fail.p, nb * sizeof(int), cudaMemcpyDeviceToDevice, s));
 
-  kg_pack_kernel<<<nb, 256, 0, s>>>(spec, N, U, pl.ps, pl.num_pts, DIMP, QP, pl.dXt.p, gp.dKinvY.p, pb.B.p, pb.P.p,
+  kg_pack_kernel<<<nb, 256, 0, s>>>(spec, N, U, pl.ps, pl.num_pts, DIMP, QP, pl.stride, pl.dXt.p, gp.dKinvY.p, pb.B.p, pb.P.p,
                                     pl.dD.p, pl.dPk.p, pl.dXu.p, pl.dA.p, pl.dAfull.p);
   count_launch();
   // K(X, A_union) for all candidates of the batch (value rows only)
   build_mix_covariance(spec, gp.dX.p, N, pl.dAfull.p, nb * U, nullptr, 0, pl.dKAu.p, s);
-  const size_t smem_d = static_cast<size_t>(U) * U * sizeof(double);
+  const size_t smem_d = static_cast<size_t>(Q) * Q * sizeof(double);
   kg_discrete_kernel<<<nb, 256, smem_d, s>>>(spec, n, U, pl.num_pts, QP, gp.mean, pl.best_so_far, gp.dKinvY.p, pb.P.p,
                                              pl.dAfull.p, pl.dD.p, pl.dKAu.p, pl.dKD.p, pl.dMuD.p, pb.B.p, pb.mu.p,
                                              pb.chol.p, pb.fail.p, pl.dW.p, pl.dMuA.p, pl.dBestPost.p, pl.dWinner.p);
@@ -407,7 +481,7 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   const int w_in_smem = (w_bytes + smem_d) <= 160 * 1024;
   const size_t smem_p = smem_d + (w_in_smem ? w_bytes : 0);
   CMOE_CUDA(cudaFuncSetAttribute(kg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-  kg_prep_kernel<<<dim3((mc + 255) / 256, nb), 256, smem_p, s>>>(U, M, QP, mc, pl.seed,
+  kg_prep_kernel<<<dim3((mc + 255) / 256, nb), 256, smem_p, s>>>(Q, M, QP, mc, pl.seed,
                                                                  pl.dTable.count ? pl.dTable.p : nullptr, pb.chol.p,
                                                                  pl.dW.p, pl.dMuA.p, pb.fail.p, w_in_smem, pl.dRecC.p,
                                                                  pl.dRecStart.p);
@@ -423,9 +497,13 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   prm.outX = pl.dOutX.p;
   prm.stats = pl.dStats.p;
   const int chunks = (mc + pl.chunk - 1) / pl.chunk;
-  const size_t smem_mc = pl.use_smem ? pl.entry->smem_bytes(N, U) : 0;
+  const size_t smem_mc = (!gen && pl.use_smem) ? pl.entry->smem_bytes(N, U) : 0;
   cudaEventRecord(pl.mc_events[ev_idx].first, s);
-  pl.entry->mc(prm, dim3(chunks, nb), smem_mc, s);
+  if (gen) {
+    pl.entry->mc_gen(prm, dim3(chunks, nb), 0, s);
+  } else {
+    pl.entry->mc(prm, dim3(chunks, nb), smem_mc, s);
+  }
   cudaEventRecord(pl.mc_events[ev_idx].second, s);
   count_launch();
   kg_value_kernel<<<nb, 256, 0, s>>>(mc, pl.dOutVal.p, pl.dBestPost.p, pb.fail.p, pl.dKG.p + c0);
@@ -445,15 +523,23 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
     ap.R = pl.dR.p;
     ap.Gu = pl.dGu.p;
     ap.GkB = pl.dGkB.p;
-    CMOE_CUDA(cudaMemsetAsync(pl.dR.p, 0, static_cast<size_t>(nb) * QP * (N + U) * sizeof(double), s));
-    pl.entry->acc(ap, dim3((N + U + 127) / 128, nb), s);
-    kg_tprime_kernel<<<nb, 256, 0, s>>>(N, U, QP, pl.dR.p, pb.B.p, pl.dTp.p);
+    CMOE_CUDA(cudaMemsetAsync(pl.dR.p, 0, static_cast<size_t>(nb) * QP * (n + Q) * sizeof(double), s));
+    if (gen) {
+      kg_acc_gen_kernel<<<dim3((n + Q + 127) / 128, nb), 128, 0, s>>>(spec, N, U, QP, DIMP, mc, gp.dX.p, pb.P.p,
+                                                                     pl.dRecC.p, pl.dOutX.p, pl.dR.p);
+      kg_g1_kernel<<<nb, 128, 0, s>>>(spec, U, q, QP, DIMP, mc, pb.P.p, pl.dRecC.p, pl.dOutX.p, pl.dG1.p);
+      count_launch();
+    } else {
+      pl.entry->acc(ap, dim3((N + U + 127) / 128, nb), s);
+    }
+    kg_tprime_kernel<<<nb, 256, 0, s>>>(n, Q, QP, pl.dR.p, pb.B.p, pl.dTp.p);
     count_launch(2);
-    // K^-1 R: columns of length N with stride N+U, nb*QP of them
-    potrs_lower(gp.dK.p, n, pl.dR.p, N + U, nb * QP, s);
-    kg_grad_kernel<<<nb, 128, static_cast<size_t>(U) * U * sizeof(double), s>>>(
-        spec, N, U, q, QP, DIMP, mc, gp.dX.p, pb.P.p, pl.dXu.p, pl.dR.p, pl.dTp.p, pl.dGu.p, pl.dGkB.p, pb.chol.p,
-        pb.gchol.p, pb.gmu.p, pl.dWinner.p, pb.fail.p, pl.dGrad.p + static_cast<size_t>(c0) * q * dim);
+    // K^-1 R: columns of length n with stride n+Q, nb*QP of them
+    potrs_lower(gp.dK.p, n, pl.dR.p, n + Q, nb * QP, s);
+    kg_grad_kernel<<<nb, 128, static_cast<size_t>(Q) * Q * sizeof(double), s>>>(
+        spec, N, U, q, QP, DIMP, mc, gp.dX.p, pb.P.p, pl.dXu.p, pl.dR.p, pl.dTp.p, pl.dGu.p, pl.dGkB.p,
+        gen ? pl.dG1.p : nullptr, pb.chol.p, pb.gchol.p, pb.gmu.p, pl.dWinner.p, pb.fail.p,
+        pl.dGrad.p + static_cast<size_t>(c0) * q * dim);
     count_launch();
   }
   CMOE_CUDA(cudaGetLastError());
@@ -475,8 +561,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     const KernelSpec& spec = gp->spec;
     const int dim = spec.dim;
     CMOE_REQUIRE(num_fidelity >= 0 && num_fidelity < dim, CMOE_ERR_BOUNDS, "num_fidelity out of range");
-    CMOE_REQUIRE(spec.g == 0, CMOE_ERR_INVALID_VALUE,
-                 "knowledge gradient with derivative observations (d-KG) is not implemented in this build");
+    CMOE_REQUIRE(spec.g <= kMaxG, CMOE_ERR_BOUNDS, "at most 8 derivative observations per point in the q-KG kernel");
     CMOE_REQUIRE(inner->max_num_steps <= 4096, CMOE_ERR_BOUNDS, "inner max_num_steps must be <= 4096");
     require_device(gp->device);
     std::unique_ptr<cmoe_kg_plan> pl(new cmoe_kg_plan());
@@ -497,11 +582,14 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     const int U = pl->U, N = gp->N, n = gp->n, ps = pl->ps;
     for (int d = 0; d < ps; ++d)
       CMOE_REQUIRE(inner_bounds[2 * d] <= inner_bounds[2 * d + 1], CMOE_ERR_BOUNDS, "Tensor product region is EMPTY.");
-    pl->entry = find_kg_entry(spec.kernel, dim, U);
-    CMOE_REQUIRE(pl->entry != nullptr, CMOE_ERR_BOUNDS, "q+p exceeds the largest compiled q-KG kernel (16)");
+    pl->Q = pl->U * (1 + spec.g);
+    pl->entry = find_kg_entry(spec.kernel, dim, pl->Q, spec.g > 0);
+    CMOE_REQUIRE(pl->entry != nullptr, CMOE_ERR_BOUNDS,
+                 "(q+p)*(1+num_derivatives) or dim exceeds the largest compiled q-KG kernel (32 rows, 8 dims)");
     pl->DIMP = pl->entry->dim;
     pl->QP = pl->entry->qp;
-    const int DIMP = pl->DIMP, QP = pl->QP;
+    const int DIMP = pl->DIMP, QP = pl->QP, Q = pl->Q;
+    pl->stride = (1 + (1 + spec.g) * (QP + 1) + 1) / 2 * 2;
     cudaStream_t s = gp->stream;
 
     // static data: scaled training points, discrete set (full dim, fidelity coords = 1), K(X, D), mu_n(D)
@@ -533,10 +621,10 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem_need = pl->entry->smem_bytes(N, U);
-    pl->use_smem = smem_need <= 200 * 1024;
+    pl->use_smem = spec.g == 0 && smem_need <= 200 * 1024;
     // candidates per batch bounded by ~3 GiB of per-sample records
     const size_t per_cand = static_cast<size_t>(num_mc) * (QP + DIMP + 2) * sizeof(double) +
-                            static_cast<size_t>(n) * U * 4 * sizeof(double);
+                            static_cast<size_t>(n) * Q * 4 * sizeof(double);
     pl->batch = static_cast<int>(std::max<size_t>(1, std::min<size_t>(max_candidates, (size_t(3) << 30) / per_cand)));
     // samples per CTA: aim for >= ~8 waves of CTAs over the whole batch, between 2 and 16 samples per lane
     {
@@ -547,7 +635,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
       pl->chunk = static_cast<int>(std::min<long long>(chunk, (num_mc + kMcThreads - 1) / kMcThreads * kMcThreads));
     }
     const int B = pl->batch;
-    pl->dPk.alloc(static_cast<size_t>(B) * N * (QP + 2));
+    pl->dPk.alloc(static_cast<size_t>(B) * N * pl->stride);
     pl->dXu.alloc(static_cast<size_t>(B) * U * (DIMP + 2));
     pl->dA.alloc(static_cast<size_t>(B) * pl->M * DIMP);
     pl->dAfull.alloc(static_cast<size_t>(B) * U * dim);
@@ -562,10 +650,11 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->dOutX.alloc(static_cast<size_t>(B) * num_mc * DIMP);
     pl->dStats.alloc(2);
     if (pl->want_grad) {
-      pl->dR.alloc(static_cast<size_t>(B) * QP * (N + U));
+      pl->dR.alloc(static_cast<size_t>(B) * QP * (n + Q));
       pl->dGu.alloc(static_cast<size_t>(B) * U * DIMP);
       pl->dGkB.alloc(static_cast<size_t>(B) * U);
-      pl->dTp.alloc(static_cast<size_t>(B) * U * U);
+      pl->dTp.alloc(static_cast<size_t>(B) * Q * Q);
+      pl->dG1.alloc(static_cast<size_t>(B) * q * dim);
     }
     pl->dKG.alloc(max_candidates);
     pl->dGrad.alloc(pl->want_grad ? static_cast<size_t>(max_candidates) * q * dim : 1);
@@ -586,6 +675,10 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     m.num_mc = num_mc;
     m.chunk = pl->chunk;
     m.use_smem = pl->use_smem ? 1 : 0;
+    m.g = spec.g;
+    m.Q = Q;
+    m.pk_stride = pl->stride;
+    for (int k = 0; k < 8; ++k) m.derivs[k] = (k < spec.g) ? spec.derivs[k] : 0;
     m.max_steps = inner->max_num_steps;
     m.max_restarts = inner->max_num_restarts;
     m.mean = gp->mean;
@@ -618,7 +711,7 @@ void cmoe_kg_plan_destroy(cmoe_kg_plan* plan) {
 int cmoe_kg_plan_set_table(cmoe_kg_plan* plan, const double* table, int table_len) {
   return guarded(nullptr, [&] {
     require_device(plan->gp->device);
-    const int need = ((plan->num_mc + 1) / 2) * plan->U;
+    const int need = ((plan->num_mc + 1) / 2) * plan->Q;
     CMOE_REQUIRE(table_len >= need, CMOE_ERR_INVALID_VALUE, "All random numbers stored in the RNG have been used up!");
     plan->dTable.upload(table, table_len, plan->gp->stream);
     CMOE_CUDA(cudaStreamSynchronize(plan->gp->stream));
@@ -716,7 +809,7 @@ int cmoe_kg_eval(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* inne
   int rc = cmoe_kg_plan_create(gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_candidates, q,
                                points_being_sampled, p, num_mc, best_so_far, seed, grad_kg != nullptr, &plan);
   if (rc != CMOE_OK) return rc;
-  if (normals_table) rc = cmoe_kg_plan_set_table(plan, normals_table, ((num_mc + 1) / 2) * (q + p));
+  if (normals_table) rc = cmoe_kg_plan_set_table(plan, normals_table, ((num_mc + 1) / 2) * (q + p) * (1 + gp->spec.g));
   if (rc == CMOE_OK) rc = cmoe_kg_plan_upload(plan, candidates, num_candidates);
   if (rc == CMOE_OK) rc = cmoe_kg_plan_run(plan);
   if (rc == CMOE_OK) rc = cmoe_kg_plan_sync(plan, info);

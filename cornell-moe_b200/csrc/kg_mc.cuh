@@ -28,6 +28,10 @@ struct KgMcParams {
   int num_mc;
   int chunk;    // samples per CTA
   int use_smem;
+  int g;          // derivative observations per point (0 on the fast path)
+  int Q;          // rows of the union block = U * (1 + g)
+  int pk_stride;  // doubles per training point in Pk: 1 + (1+g)*(QP+1), rounded up to even
+  int derivs[8];  // observed partial-derivative indices (g <= 8 on the general path)
   int max_steps, max_restarts;
   double mean, mrc, tol, step_tol, alpha;
   const double* Xt;      // [N][DIM] scaled training points (zero padded)
@@ -183,6 +187,131 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
   if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) SB = S0;
 }
 
+// Kernel pieces for the general path: kv = k(x, X_j) (value row), kb = factor of the first-derivative rows,
+// kc = factor of d kb / d x  (SE: all three equal k; Matern-5/2: cov0, first_derivative_part, alpha_exp_part of
+// gpp_covariance.cpp:353-355).
+template <int KERNEL>
+__device__ __forceinline__ void kernel_triple(double dot, double pk0, double hq, double alpha, double& kv, double& kb,
+                                              double& kc) {
+  if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
+    kv = exp_fast(dot + (pk0 + hq));
+    kb = kv;
+    kc = kv;
+  } else {
+    const double r2 = fmax(0.0, pk0 - 2.0 * (hq + dot));
+    const double ar = kSqrt5 * sqrt(r2);
+    const double ee = alpha * exp_fast(-ar);
+    kv = ee * (1.0 + ar + (5.0 / 3.0) * r2);
+    kb = (5.0 / 3.0) * ee * (1.0 + ar);
+    kc = (25.0 / 3.0) * ee;
+  }
+}
+
+constexpr int kMaxG = 8;
+
+// General evaluation with derivative observations (d-KG): every training point owns 1+g rows
+//   K((j,0), x) = kv ,  K((j,m), x) = kb (x~_t - X~_jt) / l_t   (t = derivs[m-1]; the 1/l_t is folded into the pack)
+//   mu+(x) - m = sum_j [ a_j0 kv + kb sum_m a~_jm (x~_t - X~_jt) ]  with  a_(j,m) = beta_(j,m) - B_(j,m),: . c
+//   d/dx~_d   = (X~_jd - x~_d) (a_j0 kb + kc wsum) + kb a~_jm [d == t]
+// Operands come straight from global memory (read-only path): with g > 0 the pack does not fit in shared memory.
+template <int KERNEL, int DIM, int QP>
+__device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const double* __restrict__ Xt,
+                                                   const double* __restrict__ Pk, const double* __restrict__ Xu,
+                                                   const double (&xq)[DIM], const double (&c)[QP],
+                                                   const double* __restrict__ cl, double& S0, double& SB,
+                                                   double (&s)[DIM], double (&em)[kMaxG]) {
+  const int N = prm.N, U = prm.U, g = prm.g, stride = prm.pk_stride;
+  double nq = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) nq = fma(xq[d], xq[d], nq);
+  const double hq = -0.5 * nq;
+  // query coordinates at the derivative indices (compile-time register indexing only)
+  double xm[kMaxG];
+#pragma unroll
+  for (int m = 0; m < kMaxG; ++m) {
+    xm[m] = 0.0;
+    em[m] = 0.0;
+    if (m < g) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        if (d == prm.derivs[m]) xm[m] = xq[d];
+    }
+  }
+  S0 = 0.0;
+  SB = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) s[d] = 0.0;
+  for (int j = 0; j < N; ++j) {
+    const double* xj = Xt + static_cast<size_t>(j) * DIM;
+    const double* pk = Pk + static_cast<size_t>(j) * stride;
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<false>(xj + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    double dot = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
+    double kv, kb, kc;
+    kernel_triple<KERNEL>(dot, __ldg(pk), hq, prm.alpha, kv, kb, kc);
+    double a0 = __ldg(pk + 1);
+#pragma unroll
+    for (int u = 0; u < QP; ++u) a0 = fma(-__ldg(pk + 2 + u), c[u], a0);
+    double wsum = 0.0;
+#pragma unroll
+    for (int m = 0; m < kMaxG; ++m) {
+      if (m < g) {
+        const double* row = pk + 1 + (m + 1) * (QP + 1);
+        double am = __ldg(row);
+#pragma unroll
+        for (int u = 0; u < QP; ++u) am = fma(-__ldg(row + 1 + u), c[u], am);
+        wsum = fma(am, xm[m] - __ldg(xj + prm.derivs[m]), wsum);
+        em[m] = fma(kb, am, em[m]);
+      }
+    }
+    S0 = fma(a0, kv, S0);
+    S0 = fma(kb, wsum, S0);
+    const double wb = fma(kc, wsum, a0 * kb);
+    SB += wb;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
+  }
+  const int bs = 1 + g;
+  for (int u = 0; u < U; ++u) {
+    const double* xu = Xu + static_cast<size_t>(u) * (DIM + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<false>(xu + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    double dot = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
+    double kv, kb, kc;
+    kernel_triple<KERNEL>(dot, __ldg(xu + DIM), hq, prm.alpha, kv, kb, kc);
+    const double a0 = cl[u * bs];
+    double wsum = 0.0;
+#pragma unroll
+    for (int m = 0; m < kMaxG; ++m) {
+      if (m < g) {
+        const double am = cl[u * bs + 1 + m] * prm.inv_len[prm.derivs[m]];
+        wsum = fma(am, xm[m] - __ldg(xu + prm.derivs[m]), wsum);
+        em[m] = fma(kb, am, em[m]);
+      }
+    }
+    S0 = fma(a0, kv, S0);
+    S0 = fma(kb, wsum, S0);
+    const double wb = fma(kc, wsum, a0 * kb);
+    SB += wb;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
+  }
+}
+
 // TensorProductDomain::LimitUpdate, gpp_domain.cpp:64-104, for one coordinate
 __device__ __forceinline__ double limit_step(double step, double x, double lo, double hi, double mrc) {
   double dist = fmin(x - lo, hi - x);
@@ -212,7 +341,7 @@ constexpr int kMcThreads = CMOE_MC_THREADS;
 
 // The per-lane line-search state machine.  Live across evaluations: c, the base point xb with f and grad f there,
 // the step size and a few counters; the start point of the current restart run is parked in the sample's output slot.
-template <int KERNEL, int DIM, int QP, bool SMEM>
+template <int KERNEL, int DIM, int QP, bool SMEM, bool GEN>
 __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* __restrict__ Xt,
                                            const double* __restrict__ Pk, const double* __restrict__ Xu, int cand,
                                            int s_begin, int s_end, int* next_sample) {
@@ -226,6 +355,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
   int state = ST_FETCH;
   int sample = s_begin + threadIdx.x;
   double c[QP], xb[DIM], gb[DIM];
+  double cl[GEN ? QP : 1];  // general path: run-time indexable copy of c for the union rows (lives in local memory)
   double fb = 0.0, alpha_n = 0.0, gnorm = 0.0;
   int step_i = 0, restart_i = 0, search = 0;
   unsigned n_evals = 0, n_steps = 0;
@@ -240,6 +370,10 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         if (prm.max_restarts > 0) {
 #pragma unroll
           for (int u = 0; u < QP; ++u) c[u] = recC[static_cast<size_t>(sample) * QP + u];
+          if (GEN) {
+#pragma unroll
+            for (int u = 0; u < QP; ++u) cl[GEN ? u : 0] = c[u];
+          }
           const double* a0 = A + static_cast<size_t>(recStart[sample]) * DIM;
 #pragma unroll
           for (int d = 0; d < DIM; ++d) {
@@ -275,7 +409,21 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
 
     // ---- the expensive, warp-uniform part ----
     double S0, SB, s[DIM];
-    eval_posterior<KERNEL, DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
+    double em[kMaxG];
+    if (GEN) {
+      eval_posterior_gen<KERNEL, DIM, QP>(prm, Xt, Pk, Xu, xq, c, cl, S0, SB, s, em);
+      // kb a~_jm lands on coordinate derivs[m]: fold it into s so that the common gradient formula below holds
+      // (grad_d = inv_len_d (s_d - x~_d SB)), using compile-time register indices only
+#pragma unroll
+      for (int m = 0; m < kMaxG; ++m)
+        if (m < prm.g) {
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            if (d == prm.derivs[m]) s[d] += em[m];
+        }
+    } else {
+      eval_posterior<KERNEL, DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
+    }
     if (state != ST_DONE && state != ST_FETCH) n_evals += 1;
     const double fq = -(prm.mean + S0);
 
@@ -418,11 +566,25 @@ __global__ void __launch_bounds__(kMcThreads, CMOE_MC_MINBLOCKS) kg_mc_kernel(co
       tma_bulk_g2s(sXu, gXu, bU, &mbar);
     }
     mbar_wait(&mbar, 0);
-    kg_mc_body<KERNEL, DIM, QP, true>(prm, sXt, sPk, sXu, cand, s_begin, s_end, &next_sample);
+    kg_mc_body<KERNEL, DIM, QP, true, false>(prm, sXt, sPk, sXu, cand, s_begin, s_end, &next_sample);
   } else {
     __syncthreads();
-    kg_mc_body<KERNEL, DIM, QP, false>(prm, gXt, gPk, gXu, cand, s_begin, s_end, &next_sample);
+    kg_mc_body<KERNEL, DIM, QP, false, false>(prm, gXt, gPk, gXu, cand, s_begin, s_end, &next_sample);
   }
+}
+
+// General-path kernel (derivative observations): same state machine, operands read through the read-only path.
+template <int KERNEL, int DIM, int QP>
+__global__ void __launch_bounds__(kMcThreads, 2) kg_mc_gen_kernel(const __grid_constant__ KgMcParams prm) {
+  __shared__ int next_sample;
+  const int cand = blockIdx.y;
+  const int s_begin = blockIdx.x * prm.chunk;
+  const int s_end = min(prm.num_mc, s_begin + prm.chunk);
+  if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
+  __syncthreads();
+  const double* gPk = prm.Pk + static_cast<size_t>(cand) * prm.N * prm.pk_stride;
+  const double* gXu = prm.Xu + static_cast<size_t>(cand) * prm.U * (DIM + 2);
+  kg_mc_body<KERNEL, DIM, QP, false, true>(prm, prm.Xt, gPk, gXu, cand, s_begin, s_end, &next_sample);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -507,12 +669,13 @@ using KgMcLaunch = void (*)(const KgMcParams&, dim3 grid, size_t smem, cudaStrea
 using KgAccLaunch = void (*)(const KgAccParams&, dim3 grid, cudaStream_t s);
 struct KgDispatchEntry {
   int kernel, dim, qp;
-  KgMcLaunch mc;
+  KgMcLaunch mc;      // g == 0 fast path (TMA-staged operands)
+  KgMcLaunch mc_gen;  // general path (derivative observations); may be null
   KgAccLaunch acc;
   size_t (*smem_bytes)(int N, int U);
 };
 void register_kg_entries(const KgDispatchEntry* entries, int count);
-const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q);
+const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q, bool need_gen);
 
 template <int KERNEL, int DIM, int QP>
 void launch_kg_mc(const KgMcParams& p, dim3 grid, size_t smem, cudaStream_t s) {
@@ -524,6 +687,10 @@ void launch_kg_mc(const KgMcParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   kg_mc_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, smem, s>>>(p);
 }
 template <int KERNEL, int DIM, int QP>
+void launch_kg_mc_gen(const KgMcParams& p, dim3 grid, size_t, cudaStream_t s) {
+  kg_mc_gen_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, 0, s>>>(p);
+}
+template <int KERNEL, int DIM, int QP>
 void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {
   kg_acc_kernel<KERNEL, DIM, QP><<<grid, 128, 0, s>>>(p);
 }
@@ -533,9 +700,12 @@ size_t kg_smem_bytes(int N, int U) {
 }
 
 #define CMOE_KG_ENTRY(K, D, Q) \
-  { K, D, Q, &launch_kg_mc<K, D, Q>, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
+  { K, D, Q, &launch_kg_mc<K, D, Q>, nullptr, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
+#define CMOE_KG_ENTRY_GEN(K, D, Q) \
+  { K, D, Q, &launch_kg_mc<K, D, Q>, &launch_kg_mc_gen<K, D, Q>, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
 #define CMOE_KG_ENTRIES_FOR_DIM(D)                                                                              \
-  CMOE_KG_ENTRY(0, D, 2), CMOE_KG_ENTRY(0, D, 4), CMOE_KG_ENTRY(0, D, 8), CMOE_KG_ENTRY(0, D, 16),               \
-      CMOE_KG_ENTRY(1, D, 2), CMOE_KG_ENTRY(1, D, 4), CMOE_KG_ENTRY(1, D, 8), CMOE_KG_ENTRY(1, D, 16)
+  CMOE_KG_ENTRY(0, D, 2), CMOE_KG_ENTRY(0, D, 4), CMOE_KG_ENTRY_GEN(0, D, 8), CMOE_KG_ENTRY_GEN(0, D, 16),       \
+      CMOE_KG_ENTRY_GEN(0, D, 32), CMOE_KG_ENTRY(1, D, 2), CMOE_KG_ENTRY(1, D, 4), CMOE_KG_ENTRY_GEN(1, D, 8),  \
+      CMOE_KG_ENTRY_GEN(1, D, 16), CMOE_KG_ENTRY_GEN(1, D, 32)
 
 }  // namespace cmoe

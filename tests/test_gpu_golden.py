@@ -33,10 +33,9 @@ def test_cuda_matches_golden(case):
     ei, gei = gp.ei(g("mc_Xq"), g("mc_Xp"), 32, float(g("mc_best_ei")), table=g("ei_table"), grad=True)
     np.testing.assert_allclose(ei[0], g("ei"), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(gei[0], g("ei_grad"), rtol=1e-6, atol=1e-9)
-    if len(g_idx) == 0:  # d-KG (derivative observations) is the next row of SURVEY.md §8
-        dim = g("X").shape[1]
-        for tag, gd in (("discrete", DISCRETE_ONLY_GD), ("linesearch", EXAMPLE_INNER_GD)):
-            kg, gkg = gp.kg(g("mc_Xq"), g("mc_Xp"), 32, float(g("mc_best_kg")), gd, unit_bounds(dim), g("mc_disc"),
-                            table=g("kg_table"), grad=True)
-            np.testing.assert_allclose(kg[0], g(f"kg_{tag}"), rtol=1e-7, atol=1e-10)
-            np.testing.assert_allclose(gkg[0], g(f"kg_{tag}_grad"), rtol=1e-5, atol=1e-8)
+    dim = g("X").shape[1]  # q-KG and d-KG (derivative observations) alike
+    for tag, gd in (("discrete", DISCRETE_ONLY_GD), ("linesearch", EXAMPLE_INNER_GD)):
+        kg, gkg = gp.kg(g("mc_Xq"), g("mc_Xp"), 32, float(g("mc_best_kg")), gd, unit_bounds(dim), g("mc_disc"),
+                        table=g("kg_table"), grad=True)
+        np.testing.assert_allclose(kg[0], g(f"kg_{tag}"), rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(gkg[0], g(f"kg_{tag}_grad"), rtol=1e-5, atol=1e-8)

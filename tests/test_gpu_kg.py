@@ -129,3 +129,44 @@ def test_kg_north_star_shape_properties(capi):
         v, g = ref.kg(cands[c], None, 64, best, table, EXAMPLE_INNER_GD, unit_bounds(8), disc, grad=True)
         np.testing.assert_allclose(kg64[c], v, rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(g64[c], g, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("gd", [DISCRETE_ONLY_GD, EXAMPLE_INNER_GD])
+@pytest.mark.parametrize("q,p,g_idx", [(1, 0, (0,)), (2, 1, (0, 1)), (2, 0, (0, 1, 2))])
+def test_dkg_derivative_observations_table_fed(capi, kernel, gd, q, p, g_idx):
+    """d-KG: the GP holds derivative observations, candidates carry derivative rows (config 4's structure)."""
+    prob = make_problem(12, 3, g_idx=g_idx, seed=9, noise=0.1)
+    gp, ref = _pair(capi, kernel, prob)
+    rng = np.random.default_rng(27)
+    cands = rng.uniform(size=(3, q, 3))
+    Xp = rng.uniform(size=(p, 3))
+    disc = rng.uniform(size=(5, 3))
+    mc = 32
+    Q = (q + p) * (1 + len(g_idx))
+    table = rng.standard_normal((mc // 2) * Q)
+    best = float(ref.mean_additional(disc).min())
+    kg, grad = gp.kg(cands, Xp, mc, best, gd, unit_bounds(3), disc, table=table, grad=True)
+    for c in range(3):
+        v, g = ref.kg(cands[c], Xp, mc, best, table, gd, unit_bounds(3), disc, grad=True)
+        np.testing.assert_allclose(kg[c], v, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
+
+
+def test_dkg_config4_shape_spot_check(capi):
+    """BASELINE.json configs[3] structure: d = 4, all 4 partial derivatives observed, q = 4 (system n = N*5); reduced N
+    and num_mc so that the CPU checker finishes in seconds, Philox stream on the device."""
+    prob = make_problem(40, 4, g_idx=(0, 1, 2, 3), seed=4, noise=1e-2)
+    gp, ref = _pair(capi, 0, prob)
+    rng = np.random.default_rng(3)
+    q, mc = 4, 64
+    cands = rng.uniform(size=(4, q, 4))
+    disc = rng.uniform(size=(10, 4))
+    best = float(ref.mean_additional(disc).min())
+    kg, grad, st = gp.kg(cands, None, mc, best, EXAMPLE_INNER_GD, unit_bounds(4), disc, seed=0xC0FFEE, grad=True, stats=True)
+    assert st["posterior_evals"] >= 4 * mc
+    table = orc.philox_normals(0xC0FFEE, 0, mc // 2, q * 5)
+    for c in range(2):
+        v, g = ref.kg(cands[c], None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(4), disc, grad=True)
+        np.testing.assert_allclose(kg[c], v, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(grad[c], g, rtol=1e-4, atol=1e-7)
