@@ -42,6 +42,7 @@ void require_device(int device) {
 }
 
 void fit_gp(cmoe_gp* gp, bool mean_change) {
+  drop_cached_plan(gp);  // the cached workspace refers to the previous training set
   const KernelSpec& spec = gp->spec;
   const int N = gp->N, b = 1 + spec.g, n = N * b;
   gp->n = n;
@@ -94,6 +95,7 @@ void fit_gp(cmoe_gp* gp, bool mean_change) {
 }  // namespace cmoe
 
 cmoe_gp::~cmoe_gp() {
+  cmoe::drop_cached_plan(this);
   if (stream) {
     cudaSetDevice(device);
     cudaStreamDestroy(stream);

@@ -142,6 +142,9 @@ struct cmoe_gp {
   cmoe::DevBuf<double> dKinvY;    // [n]
   cmoe::DevBuf<int> dFlag;        // [1] Cholesky failure index
   double fit_usec[3] = {0, 0, 0};
+  // one cached q-KG plan (device workspace) so that repeated cmoe_kg_eval calls with the same configuration — every
+  // step of an outer optimiser — do not re-allocate gigabytes of scratch; owned by kg.cu
+  mutable struct cmoe_kg_plan* cached_plan = nullptr;
   ~cmoe_gp();
 };
 
@@ -151,6 +154,8 @@ constexpr int kTrsmNB = 32;
 
 // ---- gp.cu ----
 void fit_gp(cmoe_gp* gp, bool mean_change);
+// ---- kg.cu ----
+void drop_cached_plan(const cmoe_gp* gp);
 
 // ---- linalg.cu -----------------------------------------------------------------------------------------------
 // In-place blocked lower Cholesky of the n*n column-major matrix A (lda = n).  *flag (device) receives 0 or the

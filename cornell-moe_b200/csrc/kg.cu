@@ -14,6 +14,7 @@
 //   -> [gradient] accumulate R = sum_i k(X, x*_i) c_i^T, K^-1 R, contraction with dK*, dL  -> KG, grad KG.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "kg_mc.cuh"
 
@@ -391,6 +392,13 @@ __global__ void mean_of_points_kernel(int n, int num, double mean, const double*
 
 }  // namespace
 
+void drop_cached_plan(const cmoe_gp* gp) {
+  if (gp->cached_plan) {
+    cmoe_kg_plan_destroy(gp->cached_plan);
+    gp->cached_plan = nullptr;
+  }
+}
+
 void register_kg_entries(const KgDispatchEntry* entries, int count) {
   for (int i = 0; i < count; ++i) kg_table().push_back(entries[i]);
 }
@@ -419,6 +427,7 @@ struct cmoe_kg_plan {
   double best_so_far = 0.0;
   uint64_t seed = 0;
   cmoe_gd_params inner{};
+  std::vector<double> h_inner_bounds, h_discrete, h_Xp;  // host copies (cache key of cmoe_kg_eval)
   const KgDispatchEntry* entry = nullptr;
   int DIMP = 0, QP = 0, batch = 0, nc = 0;
   int Q = 0, stride = 0;  // rows of the union block U*(1+g); doubles per training point in the operand pack
@@ -579,6 +588,9 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->best_so_far = best_so_far;
     pl->seed = seed;
     pl->inner = *inner;
+    pl->h_inner_bounds.assign(inner_bounds, inner_bounds + 2 * static_cast<size_t>(pl->ps));
+    pl->h_discrete.assign(discrete_pts, discrete_pts + static_cast<size_t>(num_pts) * pl->ps);
+    if (p) pl->h_Xp.assign(points_being_sampled, points_being_sampled + static_cast<size_t>(p) * dim);
     const int U = pl->U, N = gp->N, n = gp->n, ps = pl->ps;
     for (int d = 0; d < ps; ++d)
       CMOE_REQUIRE(inner_bounds[2 * d] <= inner_bounds[2 * d + 1], CMOE_ERR_BOUNDS, "Tensor product region is EMPTY.");
@@ -805,16 +817,40 @@ int cmoe_kg_eval(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* inne
                  const double* discrete_pts, int num_pts, const double* candidates, int num_candidates, int q,
                  const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
                  const double* normals_table, double* kg, double* grad_kg, cmoe_kg_stats* stats, int* info) {
-  cmoe_kg_plan* plan = nullptr;
-  int rc = cmoe_kg_plan_create(gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_candidates, q,
-                               points_being_sampled, p, num_mc, best_so_far, seed, grad_kg != nullptr, &plan);
-  if (rc != CMOE_OK) return rc;
-  if (normals_table) rc = cmoe_kg_plan_set_table(plan, normals_table, ((num_mc + 1) / 2) * (q + p) * (1 + gp->spec.g));
+  // Reuse the GP's cached plan when the configuration matches (same discrete set, bounds, inner optimiser, sizes);
+  // best_so_far and the seed are plain parameters and are refreshed in place.
+  const int ps = gp->spec.dim - num_fidelity, dim = gp->spec.dim;
+  cmoe_kg_plan* plan = gp->cached_plan;
+  const bool want_grad = grad_kg != nullptr;
+  bool reuse = plan != nullptr && num_fidelity >= 0 && ps >= 1 && plan->nf == num_fidelity &&
+               plan->num_pts == num_pts && plan->q == q && plan->p == p && plan->num_mc == num_mc &&
+               plan->want_grad == want_grad && plan->max_cand >= num_candidates &&
+               std::memcmp(&plan->inner, inner, sizeof(cmoe_gd_params)) == 0 &&
+               std::equal(plan->h_inner_bounds.begin(), plan->h_inner_bounds.end(), inner_bounds) &&
+               std::equal(plan->h_discrete.begin(), plan->h_discrete.end(), discrete_pts) &&
+               (p == 0 || std::equal(plan->h_Xp.begin(), plan->h_Xp.end(), points_being_sampled));
+  int rc = CMOE_OK;
+  if (!reuse) {
+    drop_cached_plan(gp);
+    plan = nullptr;
+    rc = cmoe_kg_plan_create(gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_candidates, q,
+                             points_being_sampled, p, num_mc, best_so_far, seed, want_grad ? 1 : 0, &plan);
+    if (rc != CMOE_OK) return rc;
+    gp->cached_plan = plan;
+  } else {
+    plan->best_so_far = best_so_far;
+    plan->seed = seed;
+  }
+  if (normals_table) {
+    rc = cmoe_kg_plan_set_table(plan, normals_table, ((num_mc + 1) / 2) * (q + p) * (1 + gp->spec.g));
+  } else if (plan->dTable.count) {
+    plan->dTable.release();
+  }
+  (void)dim;
   if (rc == CMOE_OK) rc = cmoe_kg_plan_upload(plan, candidates, num_candidates);
   if (rc == CMOE_OK) rc = cmoe_kg_plan_run(plan);
   if (rc == CMOE_OK) rc = cmoe_kg_plan_sync(plan, info);
   if (rc == CMOE_OK) rc = cmoe_kg_plan_download(plan, kg, grad_kg, stats);
-  cmoe_kg_plan_destroy(plan);
   return rc;
 }
 

@@ -17,6 +17,10 @@
  * classes (gpp_exception.hpp:170-509, gpp_python.cpp:189-206).  `info` receives the payload
  * (leading-minor index k+1 for CMOE_ERR_SINGULAR, exactly as gpp_linear_algebra.cpp:141-142 returns it).
  * There is NO CPU fallback: without a CUDA device every compute call returns CMOE_ERR_NO_DEVICE.
+ *
+ * Threading: like the reference's Python boundary (GIL held for the whole call) a handle is used by one host thread at a
+ * time; calls on the same cmoe_gp are issued on that handle's CUDA stream and must be serialised by the caller.
+ * Repeated cmoe_kg_eval calls with an unchanged configuration reuse a device workspace cached in the handle.
  */
 #ifndef CMOE_B200_H_
 #define CMOE_B200_H_
