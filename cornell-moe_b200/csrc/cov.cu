@@ -23,7 +23,7 @@ constexpr int TCW = 64;  // point cols per CTA tile (TCW / TC sub-tiles share th
 // g == 0 fast path: K[i + j*n] for i >= j (tile granularity), noise[0] on the diagonal.
 // Works on length-scaled coordinates Xs = X / l (so r^2 is a plain sum of squared differences: 2 FP64 ops per
 // dimension, no division) and the branch-free exp; both keep the entry within ~1 ulp of the reference's formula.
-__global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant__ KernelSpec spec,
+__global__ void __launch_bounds__(256, 3) cov_build_g0_kernel(const __grid_constant__ KernelSpec spec,
                                                            const double* __restrict__ Xs, int N,
                                                            const double* __restrict__ noise, double* __restrict__ K) {
   extern __shared__ double sm[];
@@ -38,25 +38,44 @@ __global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant
   const int tc = blockIdx.x - tr * (tr + 1) / 2 * kColsPerRow;
   const int row0 = tr * TR, colbase = tc * TCW;
   if (colbase >= N) return;
+  // coalesced, asynchronous (LDGSTS) slab loads, transposed on the fly into the coordinate-major shared layout
   for (int e = threadIdx.x; e < TR * dim; e += blockDim.x) {
-    const int r = row0 + e % TR, k = e / TR;
-    Xr[e] = (r < N) ? Xs[static_cast<size_t>(r) * dim + k] : 0.0;
+    const int r = e / dim, k = e - r * dim;
+    const bool ok = row0 + r < N;
+    cp_async8(Xr + k * TR + r, ok ? Xs + static_cast<size_t>(row0) * dim + e : Xs, ok);
   }
   for (int e = threadIdx.x; e < TCW * dim; e += blockDim.x) {
-    const int c = colbase + e % TCW, k = e / TCW;
-    Xc[e] = (c < N) ? Xs[static_cast<size_t>(c) * dim + k] : 0.0;
+    const int c = e / dim, k = e - c * dim;
+    const bool ok = colbase + c < N;
+    cp_async8(Xc + k * TCW + c, ok ? Xs + static_cast<size_t>(colbase) * dim + e : Xs, ok);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   for (int sub = 0; sub < TCW / TC; ++sub) {
   const int col0 = colbase + sub * TC;
   if (col0 > row0 + TR - 1 || col0 >= N) break;  // sub-tile entirely above the diagonal
-  const int rg = threadIdx.x & 31;  // rows rg*4 .. rg*4+3
-  const int cg = threadIdx.x >> 5;  // cols cg*4 .. cg*4+3
+  // 2-D register blocking inside a warp: lane = (lr, lc) owns rows roff..roff+3 and cols coff..coff+3 of a 32x16 warp
+  // tile, so an LDS.128 of the row slab touches 8 distinct 16-byte chunks (1 wavefront) instead of 32 (4 wavefronts)
+  // and the kernel is FP64- rather than shared-memory-bound.  8 warps = 4 (rows) x 2 (cols) cover 128 x 32.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int roff4 = ((warp & 3) * 32 + (lane & 7) * 4) / 4;   // in units of 4 rows
+  const int coff4 = ((warp >> 2) * 16 + (lane >> 3) * 4) / 4; // in units of 4 cols
+  const int rg = roff4, cg = coff4;
   const double nz = noise[0];
   const bool se = spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL;
   // -r^2/2 = x_i.x_j - |x_i|^2/2 - |x_j|^2/2 : one FMA per dimension and entry (the absolute error of the expanded
   // form is ~1e-16 * (|x_i|^2 + |x_j|^2), i.e. a relative perturbation of k of that size — far below the noise term)
-  double t[4][4], hr[4] = {0.0, 0.0, 0.0, 0.0}, hc[4] = {0.0, 0.0, 0.0, 0.0};
+  double t[4][4], hc[4] = {0.0, 0.0, 0.0, 0.0};
+  double hr[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k = 0; k < dim; ++k) {
+    const double2 ra = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4);
+    const double2 rb = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4 + 2);
+    hr[0] = fma(-0.5 * ra.x, ra.x, hr[0]);
+    hr[1] = fma(-0.5 * ra.y, ra.y, hr[1]);
+    hr[2] = fma(-0.5 * rb.x, rb.x, hr[2]);
+    hr[3] = fma(-0.5 * rb.y, rb.y, hr[3]);
+  }
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
@@ -70,7 +89,6 @@ __global__ void __launch_bounds__(256) cov_build_g0_kernel(const __grid_constant
     const double xc[4] = {ca.x, ca.y, cb.x, cb.y};
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
-      hr[rr] = fma(-0.5 * xr[rr], xr[rr], hr[rr]);
       hc[rr] = fma(-0.5 * xc[rr], xc[rr], hc[rr]);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) t[rr][cc] = fma(xr[rr], xc[cc], t[rr][cc]);

@@ -208,15 +208,6 @@ constexpr int GK = 16;        // K chunk
 constexpr int GST = 3;        // pipeline stages
 constexpr int GLD = GT + 4;   // 132 = 4 (mod 16): conflict-free fragment loads
 
-__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
-  const int bytes = valid ? 8 : 0;  // src-size 0 -> zero fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 __global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ A, int lda, int n, int p0, int W,
                                                            const int* __restrict__ flag) {
   extern __shared__ double gsm[];
@@ -242,8 +233,8 @@ __global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ 
 #pragma unroll
     for (int e = tid; e < GT * GK; e += 256) {
       const int m = e % GT, k = e / GT;
-      cp_async8(as + k * GLD + m, Ag + static_cast<size_t>(kc * GK + k) * lda + m, m < rows);
-      cp_async8(bs + k * GLD + m, Bg + static_cast<size_t>(kc * GK + k) * lda + m, m < cols);
+      cp_async8(as + k * GLD + m, m < rows ? Ag + static_cast<size_t>(kc * GK + k) * lda + m : Ag, m < rows);
+      cp_async8(bs + k * GLD + m, m < cols ? Bg + static_cast<size_t>(kc * GK + k) * lda + m : Bg, m < cols);
     }
   };
 
