@@ -411,3 +411,129 @@ def ei_gradient_descent(gp, starts, Xp, num_mc, best_so_far, outer, domain_bound
                                         _d(pts), ctypes.byref(info))
     _check(rc, info.value)
     return vals, pts
+
+
+def posterior_mean_optimization(gp, initial_guess, params, domain_bounds, num_fidelity=0):
+    """cmoe_posterior_mean_optimization: returns (best_point [dim - num_fidelity], -min mu, found)."""
+    ps = gp.dim - num_fidelity
+    x0 = _f64(initial_guess).ravel()
+    assert x0.size == ps
+    params = GDParams.from_seq(params)
+    db = _f64(domain_bounds).ravel()
+    best = np.zeros(ps)
+    val = ctypes.c_double()
+    found = ctypes.c_int()
+    _check(lib().cmoe_posterior_mean_optimization(gp.h, int(num_fidelity), ctypes.byref(params), _d(db), _d(x0),
+                                                  _d(best), ctypes.byref(val), ctypes.byref(found)))
+    return best, val.value, bool(found.value)
+
+
+def ei_analytic(gp, points, best_so_far, grad=False):
+    """cmoe_ei_analytic: closed-form 1-EI (and gradient) at points [n, dim]."""
+    pts = _f64(points).reshape(-1, gp.dim)
+    vals = np.empty(pts.shape[0])
+    g = np.empty_like(pts) if grad else None
+    info = ctypes.c_int()
+    _check(lib().cmoe_ei_analytic(gp.h, _d(pts), pts.shape[0], ctypes.c_double(best_so_far), _d(vals), _d(g),
+                                  ctypes.byref(info)), info.value)
+    return (vals, g) if grad else vals
+
+
+class GaussianProcessEnsemble:
+    """An array of GP handles over the same data, one per hyper-parameter sample — the reference's GaussianProcessMCMC
+    (gpp_knowledge_gradient_mcmc_optimization.cpp:24-48).  hypers[M][1+dim] = (alpha, lengths); noises[M][1+g]."""
+
+    def __init__(self, hypers, noises, X, y, derivs=None, kernel=MATERN_NU_2P5, device=0):
+        hypers, noises = _f64(hypers), _f64(noises)
+        self.members = [GaussianProcess(kernel, hypers[m, 0], hypers[m, 1:], X, y, noises[m], derivs, device)
+                        for m in range(hypers.shape[0])]
+        self.dim = self.members[0].dim
+
+    def __len__(self):
+        return len(self.members)
+
+    def _handles(self):
+        return (ctypes.c_void_p * len(self.members))(*[gp.h for gp in self.members])
+
+    def _cands(self, candidates, Xp):
+        cand = _f64(candidates)
+        if cand.ndim == 2:
+            cand = cand[None]
+        Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
+        return cand, Xp
+
+    def kg(self, candidates, Xp, num_mc, best_so_far, inner, inner_bounds, discrete_pts, num_fidelity=0, seed=0,
+           table=None, grad=False):
+        """cmoe_kg_eval_mcmc.  discrete_pts [M, num_pts, dim - nf]; best_so_far [M]."""
+        cand, Xp = self._cands(candidates, Xp)
+        nc, q, _ = cand.shape
+        M = len(self.members)
+        disc = _f64(discrete_pts).reshape(M, -1, self.dim - num_fidelity)
+        best = _f64(best_so_far).ravel()
+        assert best.size == M
+        table = _f64(table).ravel() if table is not None else None
+        inner = GDParams.from_seq(inner)
+        ib = _f64(inner_bounds).ravel()
+        vals = np.empty(nc)
+        g = np.empty((nc, q, self.dim)) if grad else None
+        info = ctypes.c_int()
+        rc = lib().cmoe_kg_eval_mcmc(self._handles(), M, int(num_fidelity), ctypes.byref(inner), _d(ib), _d(disc),
+                                     disc.shape[1], _d(cand), nc, q, _d(Xp), Xp.shape[0], int(num_mc), _d(best),
+                                     ctypes.c_uint64(seed), _d(table), _d(vals), _d(g), ctypes.byref(info))
+        _check(rc, info.value)
+        return (vals, g) if grad else vals
+
+    def ei(self, candidates, Xp, num_mc, best_so_far, seed=0, table=None, grad=False, analytic_single=False):
+        """cmoe_ei_eval_mcmc."""
+        cand, Xp = self._cands(candidates, Xp)
+        nc, q, _ = cand.shape
+        M = len(self.members)
+        best = _f64(best_so_far).ravel()
+        assert best.size == M
+        table = _f64(table).ravel() if table is not None else None
+        vals = np.empty(nc)
+        g = np.empty((nc, q, self.dim)) if grad else None
+        info = ctypes.c_int()
+        rc = lib().cmoe_ei_eval_mcmc(self._handles(), M, _d(cand), nc, q, _d(Xp), Xp.shape[0], int(num_mc), _d(best),
+                                     ctypes.c_uint64(seed), _d(table), int(bool(analytic_single)), _d(vals), _d(g),
+                                     ctypes.byref(info))
+        _check(rc, info.value)
+        return (vals, g) if grad else vals
+
+    def multistart_kg(self, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
+                      num_fidelity=0, seed=0):
+        """cmoe_multistart_kg_mcmc: returns (best_point [q, dim], best_value, found_flag, start_values)."""
+        starts = _f64(starts)
+        ns, q, dim = starts.shape
+        _, Xp = self._cands(starts, Xp)
+        M = len(self.members)
+        disc = _f64(discrete_pts).reshape(M, -1, self.dim - num_fidelity)
+        best_in = _f64(best_so_far).ravel()
+        outer, inner = GDParams.from_seq(outer), GDParams.from_seq(inner)
+        db, ib = _f64(domain_bounds).ravel(), _f64(inner_bounds).ravel()
+        vals, best = np.empty(ns), np.empty((q, dim))
+        bv, found, info = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().cmoe_multistart_kg_mcmc(self._handles(), M, int(num_fidelity), ctypes.byref(outer),
+                                           ctypes.byref(inner), _d(db), _d(ib), _d(disc), disc.shape[1], _d(starts), ns,
+                                           q, _d(Xp), Xp.shape[0], int(num_mc), _d(best_in), ctypes.c_uint64(seed),
+                                           _d(vals), _d(best), ctypes.byref(bv), ctypes.byref(found),
+                                           ctypes.byref(info))
+        _check(rc, info.value)
+        return best, bv.value, bool(found.value), vals
+
+    def multistart_ei(self, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0):
+        """cmoe_multistart_ei_mcmc: returns (best_point [q, dim], best_value, found_flag, start_values)."""
+        starts = _f64(starts)
+        ns, q, dim = starts.shape
+        _, Xp = self._cands(starts, Xp)
+        M = len(self.members)
+        best_in = _f64(best_so_far).ravel()
+        outer = GDParams.from_seq(outer)
+        db = _f64(domain_bounds).ravel()
+        vals, best = np.empty(ns), np.empty((q, dim))
+        bv, found, info = ctypes.c_double(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().cmoe_multistart_ei_mcmc(self._handles(), M, ctypes.byref(outer), _d(db), _d(starts), ns, q, _d(Xp),
+                                           Xp.shape[0], int(num_mc), _d(best_in), ctypes.c_uint64(seed), _d(vals),
+                                           _d(best), ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+        _check(rc, info.value)
+        return best, bv.value, bool(found.value), vals

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256, 3) cov_build_g0_kernel(const __grid_const
   for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) t[rr][cc] = 0.0;
+#pragma unroll 2
   for (int k = 0; k < dim; ++k) {
     const double2 ra = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4);
     const double2 rb = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4 + 2);

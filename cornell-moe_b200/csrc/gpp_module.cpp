@@ -13,6 +13,10 @@
 //   compute_posterior_mean, compute_grad_posterior_mean, compute_knowledge_gradient, compute_grad_knowledge_gradient,
 //   multistart_knowledge_gradient_optimization, posterior_mean_optimization, evaluate_KG_at_point_list
 //                                                                         gpp_python_knowledge_gradient.cpp:44-397
+//   GaussianProcessMCMC, compute_{,grad_}knowledge_gradient_mcmc, multistart_knowledge_gradient_mcmc_optimization,
+//   evaluate_KG_mcmc_at_point_list                                        gpp_python_knowledge_gradient_mcmc.cpp:49-384
+//   compute_{,grad_}expected_improvement_mcmc, multistart_expected_improvement_mcmc_optimization,
+//   evaluate_EI_mcmc_at_point_list                                        gpp_python_expected_improvement_mcmc.cpp:46-300
 //   GradientDescentParameters, NewtonParameters, RandomnessSourceContainer, OptimizerTypes, DomainTypes,
 //   LogLikelihoodTypes                                                    gpp_python_common.cpp:201-370
 //   OptimalLearningException, BoundsException, InvalidValueException, SingularMatrixException   gpp_python.cpp:189-206
@@ -335,8 +339,11 @@ py::list evaluate_EI_at_point_list(const GaussianProcess& gp, const py::list& in
   const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
   std::vector<double> vals(num_multistarts);
   int info = 0;
-  check(cmoe_ei_eval(gp.h, starts.data(), num_multistarts, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(),
-                     nullptr, vals.data(), nullptr, &info), info);
+  if (q == 1 && p == 0)  // closed-form 1-EI, as EvaluateEIAtPointList does (gpp_math.cpp:2317)
+    check(cmoe_ei_analytic(gp.h, starts.data(), num_multistarts, best_so_far, vals.data(), nullptr, &info), info);
+  else
+    check(cmoe_ei_eval(gp.h, starts.data(), num_multistarts, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(),
+                       nullptr, vals.data(), nullptr, &info), info);
   bool found = false;
   for (double v : vals) found = found || (v > -1.0);
   status["evaluate_EI_at_point_list"] = found;
@@ -484,6 +491,260 @@ py::list evaluate_KG_at_point_list(const GaussianProcess& gp, int num_fidelity, 
   return to_list(vals);
 }
 
+// ---- GaussianProcessMCMC + MCMC-averaged acquisition ---------------------------------------------------------------------
+// (gpp_python_knowledge_gradient_mcmc.cpp:49-384, gpp_python_expected_improvement_mcmc.cpp:46-300)
+struct GaussianProcessMCMC {
+  std::vector<cmoe_gp*> members;
+  int dim_ = 0, num_derivatives_ = 0, num_sampled_ = 0;
+  std::vector<int> derivatives_;
+  GaussianProcessMCMC(const py::list& hyperparameters_list, const py::list& noise_variance_list,
+                      const py::list& points_sampled, const py::list& points_sampled_value, const py::list& derivatives,
+                      int num_mcmc, int num_derivatives, int dim, int num_sampled, const std::string& kernel,
+                      int which_gpu) {
+    // hyperparameters_list: num_mcmc x (alpha, length_1..length_dim) flat; noise_variance_list: num_mcmc x (1+g) flat
+    const auto hyp = to_vec(hyperparameters_list, static_cast<size_t>(num_mcmc) * (dim + 1));
+    const auto noise = to_vec(noise_variance_list, static_cast<size_t>(num_mcmc) * (1 + num_derivatives));
+    const auto X = to_vec(points_sampled, static_cast<size_t>(dim) * num_sampled);
+    const auto y = to_vec(points_sampled_value, static_cast<size_t>(num_sampled) * (1 + num_derivatives));
+    derivatives_ = to_ivec(derivatives, num_derivatives);
+    dim_ = dim;
+    num_derivatives_ = num_derivatives;
+    num_sampled_ = num_sampled;
+    const int kid = (kernel == "square_exponential") ? CMOE_KERNEL_SQUARE_EXPONENTIAL : CMOE_KERNEL_MATERN_NU_2P5;
+    for (int m = 0; m < num_mcmc; ++m) {
+      cmoe_gp* h = nullptr;
+      int info = 0;
+      const int rc = cmoe_gp_create(kid, hyp[static_cast<size_t>(m) * (dim + 1)], hyp.data() + static_cast<size_t>(m) * (dim + 1) + 1,
+                                    X.data(), y.data(), noise.data() + static_cast<size_t>(m) * (1 + num_derivatives),
+                                    derivatives_.data(), num_derivatives, dim, num_sampled, which_gpu, &h, &info);
+      if (rc != CMOE_OK) {
+        for (cmoe_gp* g : members) cmoe_gp_destroy(g);
+        members.clear();
+        check(rc, info);
+      }
+      members.push_back(h);
+    }
+  }
+  ~GaussianProcessMCMC() {
+    for (cmoe_gp* g : members) cmoe_gp_destroy(g);
+  }
+  GaussianProcessMCMC(const GaussianProcessMCMC&) = delete;
+  GaussianProcessMCMC& operator=(const GaussianProcessMCMC&) = delete;
+  int num_mcmc() const { return static_cast<int>(members.size()); }
+  const cmoe_gp* const* handles() const { return members.data(); }
+};
+
+double compute_knowledge_gradient_mcmc(const GaussianProcessMCMC& gp, int num_fidelity, const py::object& optimizer_parameters,
+                                       const py::list& domain_bounds, const py::list& discrete_pts, const py::list& pts,
+                                       const py::list& being, int num_pts, int q, int p, int max_int_steps,
+                                       const py::list& best_so_far, RandomnessSourceContainer& rnd) {
+  const int dim = gp.dim_, ps = dim - num_fidelity, M = gp.num_mcmc();
+  const auto inner_bounds = to_vec(domain_bounds, 2 * static_cast<size_t>(ps));
+  const auto D = to_vec(discrete_pts, static_cast<size_t>(M) * num_pts * ps);
+  const auto X = to_vec(pts, static_cast<size_t>(q) * dim);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const auto best = to_vec(best_so_far, M);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters);
+  double kg = 0.0;
+  int info = 0;
+  check(cmoe_kg_eval_mcmc(gp.handles(), M, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, X.data(), 1, q,
+                          Xp.data(), p, max_int_steps, best.data(), rnd.seed0(), nullptr, &kg, nullptr, &info), info);
+  return kg;
+}
+
+py::list compute_grad_knowledge_gradient_mcmc(const GaussianProcessMCMC& gp, int num_fidelity,
+                                              const py::object& optimizer_parameters, const py::list& domain_bounds,
+                                              const py::list& discrete_pts, const py::list& pts, const py::list& being,
+                                              int num_pts, int q, int p, int max_int_steps, const py::list& best_so_far,
+                                              RandomnessSourceContainer& rnd) {
+  const int dim = gp.dim_, ps = dim - num_fidelity, M = gp.num_mcmc();
+  const auto inner_bounds = to_vec(domain_bounds, 2 * static_cast<size_t>(ps));
+  const auto D = to_vec(discrete_pts, static_cast<size_t>(M) * num_pts * ps);
+  const auto X = to_vec(pts, static_cast<size_t>(q) * dim);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const auto best = to_vec(best_so_far, M);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters);
+  double kg = 0.0;
+  std::vector<double> g(static_cast<size_t>(q) * dim);
+  int info = 0;
+  check(cmoe_kg_eval_mcmc(gp.handles(), M, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, X.data(), 1, q,
+                          Xp.data(), p, max_int_steps, best.data(), rnd.seed0(), nullptr, &kg, g.data(), &info), info);
+  return to_list(g);
+}
+
+template <typename EvalAll, typename Multistart>
+py::list mcmc_optimization_common(const py::object& optimizer_parameters, const std::vector<double>& bounds, int dim,
+                                  int q, double init_best, RandomnessSourceContainer& rnd, py::dict& status,
+                                  EvalAll&& eval_all, Multistart&& multistart) {
+  const auto domain_type = optimizer_parameters.attr("domain_type").cast<DomainTypes>();
+  const auto opt_type = optimizer_parameters.attr("optimizer_type").cast<OptimizerTypes>();
+  if (domain_type != DomainTypes::kTensorProduct) {
+    PyErr_SetString(g_exc_base, "only the tensor_product domain is implemented on the B200 path");
+    throw py::error_already_set();
+  }
+  std::vector<double> best(static_cast<size_t>(q) * dim, 0.0);
+  int found = 0;
+  if (opt_type == OptimizerTypes::kNull) {
+    const int n = optimizer_parameters.attr("num_random_samples").cast<int>();
+    const auto starts = lhc_starts(bounds, dim, q, n, rnd.uniform_engine);
+    std::vector<double> vals(n);
+    eval_all(starts, n, vals);
+    double bv = init_best;
+    std::copy(starts.begin(), starts.begin() + static_cast<size_t>(q) * dim, best.begin());
+    for (int i = 0; i < n; ++i)
+      if (bv < vals[i]) {
+        bv = vals[i];
+        found = 1;
+        std::copy(starts.begin() + static_cast<size_t>(i) * q * dim, starts.begin() + static_cast<size_t>(i + 1) * q * dim, best.begin());
+      }
+    status["lhc_tensor_product_domain_found_update"] = static_cast<bool>(found);
+  } else if (opt_type == OptimizerTypes::kGradientDescent) {
+    const cmoe_gd_params gd = gd_of(optimizer_parameters);
+    const auto starts = lhc_starts(bounds, dim, q, gd.num_multistarts, rnd.uniform_engine);
+    multistart(gd, starts, best, found);
+    status["gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
+  } else {
+    PyErr_SetString(g_exc_base, "ERROR: invalid optimizer choice. Setting all coordinates to 0.0.");
+    throw py::error_already_set();
+  }
+  return to_list(best);
+}
+
+py::list multistart_knowledge_gradient_mcmc_optimization(const py::object& optimizer_parameters,
+                                                         const py::object& optimizer_parameters_inner,
+                                                         const GaussianProcessMCMC& gp, int num_fidelity,
+                                                         const py::list& domain_bounds, const py::list& discrete_pts,
+                                                         const py::list& being, int num_pts, int q, int p,
+                                                         const py::list& best_so_far, int max_int_steps,
+                                                         int max_num_threads, RandomnessSourceContainer& rnd,
+                                                         py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const int dim = gp.dim_, ps = dim - num_fidelity, M = gp.num_mcmc();
+  const auto bounds = full_bounds(domain_bounds, dim);
+  const std::vector<double> inner_bounds(bounds.begin(), bounds.begin() + 2 * ps);
+  const auto D = to_vec(discrete_pts, static_cast<size_t>(M) * num_pts * ps);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const auto best = to_vec(best_so_far, M);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters_inner);
+  return mcmc_optimization_common(
+      optimizer_parameters, bounds, dim, q, -INFINITY, rnd, status,
+      [&](const std::vector<double>& starts, int n, std::vector<double>& vals) {
+        int info = 0;
+        check(cmoe_kg_eval_mcmc(gp.handles(), M, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts,
+                                starts.data(), n, q, Xp.data(), p, max_int_steps, best.data(), rnd.seed0(), nullptr,
+                                vals.data(), nullptr, &info), info);
+      },
+      [&](const cmoe_gd_params& gd, const std::vector<double>& starts, std::vector<double>& out, int& found) {
+        int info = 0;
+        double bv = 0.0;
+        check(cmoe_multistart_kg_mcmc(gp.handles(), M, num_fidelity, &gd, &inner, bounds.data(), inner_bounds.data(),
+                                      D.data(), num_pts, starts.data(), gd.num_multistarts, q, Xp.data(), p,
+                                      max_int_steps, best.data(), rnd.seed0(), nullptr, out.data(), &bv, &found, &info),
+              info);
+      });
+}
+
+py::list evaluate_KG_mcmc_at_point_list(const GaussianProcessMCMC& gp, int num_fidelity,
+                                        const py::object& optimizer_parameters, const py::list& domain_bounds,
+                                        const py::list& initial_guesses, const py::list& discrete_being_sampled,
+                                        int num_multistarts, int num_pts, int q, int p, const py::list& best_so_far,
+                                        int max_int_steps, int max_num_threads, RandomnessSourceContainer& rnd,
+                                        py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const int dim = gp.dim_, ps = dim - num_fidelity, M = gp.num_mcmc();
+  const auto bounds = full_bounds(domain_bounds, dim);
+  const std::vector<double> inner_bounds(bounds.begin(), bounds.begin() + 2 * ps);
+  // flat [num_mcmc x num_pts x (dim - nf) discrete points ; p x dim points being sampled], as the reference slices it (:349-374)
+  const size_t nd = static_cast<size_t>(M) * num_pts * ps;
+  const auto both = to_vec(discrete_being_sampled, nd + static_cast<size_t>(p) * dim);
+  const std::vector<double> D(both.begin(), both.begin() + nd);
+  const std::vector<double> Xp(both.begin() + nd, both.end());
+  const auto starts = to_vec(initial_guesses, static_cast<size_t>(num_multistarts) * q * dim);
+  const auto best = to_vec(best_so_far, M);
+  const cmoe_gd_params inner = gd_of(optimizer_parameters);
+  std::vector<double> vals(num_multistarts);
+  int info = 0;
+  check(cmoe_kg_eval_mcmc(gp.handles(), M, num_fidelity, &inner, inner_bounds.data(), D.data(), num_pts, starts.data(),
+                          num_multistarts, q, Xp.data(), p, max_int_steps, best.data(), rnd.seed0(), nullptr, vals.data(),
+                          nullptr, &info), info);
+  bool found = false;
+  for (double v : vals) found = found || (v > -INFINITY);
+  status["evaluate_KG_at_point_list"] = found;
+  return to_list(vals);
+}
+
+double compute_expected_improvement_mcmc(const GaussianProcessMCMC& gp, const py::list& pts, const py::list& being, int q,
+                                         int p, int max_int_steps, const py::list& best_so_far,
+                                         RandomnessSourceContainer& rnd) {
+  const auto X = to_vec(pts, static_cast<size_t>(q) * gp.dim_);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
+  const auto best = to_vec(best_so_far, gp.num_mcmc());
+  double ei = 0.0;
+  int info = 0;
+  check(cmoe_ei_eval_mcmc(gp.handles(), gp.num_mcmc(), X.data(), 1, q, Xp.data(), p, max_int_steps, best.data(),
+                          rnd.seed0(), nullptr, 0, &ei, nullptr, &info), info);
+  return ei;
+}
+
+py::list compute_grad_expected_improvement_mcmc(const GaussianProcessMCMC& gp, const py::list& pts, const py::list& being,
+                                                int q, int p, int max_int_steps, const py::list& best_so_far,
+                                                RandomnessSourceContainer& rnd) {
+  const auto X = to_vec(pts, static_cast<size_t>(q) * gp.dim_);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
+  const auto best = to_vec(best_so_far, gp.num_mcmc());
+  double ei = 0.0;
+  std::vector<double> g(static_cast<size_t>(q) * gp.dim_);
+  int info = 0;
+  check(cmoe_ei_eval_mcmc(gp.handles(), gp.num_mcmc(), X.data(), 1, q, Xp.data(), p, max_int_steps, best.data(),
+                          rnd.seed0(), nullptr, 0, &ei, g.data(), &info), info);
+  return to_list(g);
+}
+
+py::list multistart_expected_improvement_mcmc_optimization(const py::object& optimizer_parameters,
+                                                           const GaussianProcessMCMC& gp, const py::list& domain_bounds,
+                                                           const py::list& being, int q, int p,
+                                                           const py::list& best_so_far, int max_int_steps,
+                                                           int max_num_threads, RandomnessSourceContainer& rnd,
+                                                           py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const int dim = gp.dim_, M = gp.num_mcmc();
+  const auto bounds = full_bounds(domain_bounds, dim);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
+  const auto best = to_vec(best_so_far, M);
+  return mcmc_optimization_common(
+      optimizer_parameters, bounds, dim, q, 0.0, rnd, status,
+      [&](const std::vector<double>& starts, int n, std::vector<double>& vals) {
+        int info = 0;
+        check(cmoe_ei_eval_mcmc(gp.handles(), M, starts.data(), n, q, Xp.data(), p, max_int_steps, best.data(),
+                                rnd.seed0(), nullptr, 1, vals.data(), nullptr, &info), info);
+      },
+      [&](const cmoe_gd_params& gd, const std::vector<double>& starts, std::vector<double>& out, int& found) {
+        int info = 0;
+        double bv = 0.0;
+        check(cmoe_multistart_ei_mcmc(gp.handles(), M, &gd, bounds.data(), starts.data(), gd.num_multistarts, q,
+                                      Xp.data(), p, max_int_steps, best.data(), rnd.seed0(), nullptr, out.data(), &bv,
+                                      &found, &info), info);
+      });
+}
+
+py::list evaluate_EI_mcmc_at_point_list(const GaussianProcessMCMC& gp, const py::list& initial_guesses,
+                                        const py::list& being, int num_multistarts, int q, int p,
+                                        const py::list& best_so_far, int max_int_steps, int max_num_threads,
+                                        RandomnessSourceContainer& rnd, py::dict& status) {
+  require_threads(max_num_threads, rnd);
+  const auto starts = to_vec(initial_guesses, static_cast<size_t>(num_multistarts) * q * gp.dim_);
+  const auto Xp = to_vec(being, static_cast<size_t>(p) * gp.dim_);
+  const auto best = to_vec(best_so_far, gp.num_mcmc());
+  std::vector<double> vals(num_multistarts);
+  int info = 0;
+  check(cmoe_ei_eval_mcmc(gp.handles(), gp.num_mcmc(), starts.data(), num_multistarts, q, Xp.data(), p, max_int_steps,
+                          best.data(), rnd.seed0(), nullptr, 1, vals.data(), nullptr, &info), info);
+  bool found = false;
+  for (double v : vals) found = found || (v > 0.0);
+  status["evaluate_EI_at_point_list"] = found;
+  return to_list(vals);
+}
+
 [[noreturn]] void not_on_path(const char* name) {
   PyErr_SetString(g_exc_base, (std::string(name) + " is outside the B200 hot path (SURVEY.md 8f) and is not provided by this build").c_str());
   throw py::error_already_set();
@@ -587,8 +848,38 @@ PYBIND11_MODULE(GPP, m) {
   m.def("compute_grad_knowledge_gradient", &compute_grad_knowledge_gradient);
   m.def("multistart_knowledge_gradient_optimization", &multistart_knowledge_gradient_optimization);
   m.def("evaluate_KG_at_point_list", &evaluate_KG_at_point_list);
-  m.def("posterior_mean_optimization", [](const GaussianProcess&, int, const py::object&, const py::list&, const py::list&,
-                                          py::dict&) -> py::list { not_on_path("posterior_mean_optimization"); });
+  m.def("posterior_mean_optimization",
+        [](const GaussianProcess& gp, int num_fidelity, const py::object& optimizer_parameters,
+           const py::list& domain_bounds, const py::list& initial_guess, py::dict& status) -> py::list {
+          const int ps = gp.dim_ - num_fidelity;
+          const auto bounds = to_vec(domain_bounds, 2 * static_cast<size_t>(ps));
+          const auto x0 = to_vec(initial_guess, ps);
+          const cmoe_gd_params gd = gd_of(optimizer_parameters);
+          std::vector<double> best(ps, 0.0);
+          double value = 0.0;
+          int found = 0;
+          check(cmoe_posterior_mean_optimization(gp.h, num_fidelity, &gd, bounds.data(), x0.data(), best.data(), &value,
+                                                 &found));
+          (void)status;  // the reference leaves `status` untouched for this entry point (:306-350)
+          return to_list(best);
+        });
+  py::class_<GaussianProcessMCMC>(m, "GaussianProcessMCMC")
+      .def(py::init<const py::list&, const py::list&, const py::list&, const py::list&, const py::list&, int, int, int,
+                    int, const std::string&, int>(),
+           py::arg("hyperparameters_list"), py::arg("noise_variance_list"), py::arg("points_sampled"),
+           py::arg("points_sampled_value"), py::arg("derivatives"), py::arg("num_mcmc"), py::arg("num_derivatives"),
+           py::arg("dim"), py::arg("num_sampled"), py::arg("kernel") = "matern52", py::arg("which_gpu") = 0)
+      .def_property_readonly("dim", [](const GaussianProcessMCMC& g) { return g.dim_; })
+      .def_property_readonly("num_mcmc", &GaussianProcessMCMC::num_mcmc)
+      .def_property_readonly("num_sampled", [](const GaussianProcessMCMC& g) { return g.num_sampled_; });
+  m.def("compute_knowledge_gradient_mcmc", &compute_knowledge_gradient_mcmc);
+  m.def("compute_grad_knowledge_gradient_mcmc", &compute_grad_knowledge_gradient_mcmc);
+  m.def("multistart_knowledge_gradient_mcmc_optimization", &multistart_knowledge_gradient_mcmc_optimization);
+  m.def("evaluate_KG_mcmc_at_point_list", &evaluate_KG_mcmc_at_point_list);
+  m.def("compute_expected_improvement_mcmc", &compute_expected_improvement_mcmc);
+  m.def("compute_grad_expected_improvement_mcmc", &compute_grad_expected_improvement_mcmc);
+  m.def("multistart_expected_improvement_mcmc_optimization", &multistart_expected_improvement_mcmc_optimization);
+  m.def("evaluate_EI_mcmc_at_point_list", &evaluate_EI_mcmc_at_point_list);
   m.def("run_cpp_tests", []() -> int { not_on_path("run_cpp_tests"); });
   m.def("device_count", []() { return cmoe_device_count(); });
   m.def("version", []() { return std::string(cmoe_version()); });

@@ -22,32 +22,32 @@ constexpr double kPivotTol = 1.0e-16;  // gpp_linear_algebra.cpp:118
 // --------------------------------------------------------------------------------------------------------------
 // potf2: factor one nb x nb diagonal block in shared memory (single CTA), and emit inv(L_kk) for the panel update.
 // --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int lda, int k0, int nb,
-                                                    double* __restrict__ invL, int* __restrict__ flag) {
-  extern __shared__ double dyn_smem[];
-  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
-  double (*V)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  __shared__ double rdiag[NB];
-  if (*flag != 0) return;
-  const int tid = threadIdx.x;
-  const int r = tid & (NB - 1);   // row owned by this thread
-  const int cq = tid >> 6;        // column residue class (columns cq, cq+4, ...)
-  double* Ab = A + static_cast<size_t>(k0) * lda + k0;
-#pragma unroll 4
-  for (int c = cq; c < NB; c += 4) S[r][c] = (r < nb && c < nb && r >= c) ? Ab[static_cast<size_t>(c) * lda + r] : 0.0;
-  __syncthreads();
+// Factor the nb x nb block held in shared memory S (row r, col c at S[r][c], lower part) in place; returns 0 or the
+// global leading-minor index of the failing pivot.  256 threads: thread = (row r, column residue class cq).
+__device__ __forceinline__ int factor_block(double (*S)[NB + 1], int nb, int k0, int r, int cq, int fast_chain) {
   // The column recurrence sqrt -> divide -> update is the latency-critical chain of the whole factorisation, so every
   // thread evaluates the pivot test and the square root itself (uniform outcome, no flag round trip) and there are
-  // only two barriers per column.
-  int failed = 0;
+  // only three barriers per column.
   for (int j = 0; j < nb; ++j) {
     const double piv = S[j][j];
-    if (!(piv > kPivotTol)) {  // gpp_linear_algebra.cpp:118
-      failed = k0 + j + 1;
-      break;
+    if (!(piv > kPivotTol)) return k0 + j + 1;  // gpp_linear_algebra.cpp:118, 141-142
+    double ljj, lrj;
+    if (fast_chain) {
+      // sqrt and divide through one reciprocal square root + Newton corrections: same results as sqrt()/"/" to the
+      // last bit in all but rare halfway cases (and exactly when the true results are representable), at a third
+      // of the dependent latency.  Used for multi-block factorisations, where this chain is the critical path.
+      const double y = rsqrt(piv);
+      double l = piv * y;
+      l = fma(0.5 * y, fma(-l, l, piv), l);
+      ljj = l;
+      const double a = S[r][j];
+      double qv = a * y;
+      qv = fma(fma(-qv, l, a), y, qv);
+      lrj = qv;
+    } else {
+      ljj = sqrt(piv);
+      lrj = S[r][j] / ljj;
     }
-    const double ljj = sqrt(piv);
-    const double lrj = S[r][j] / ljj;
     __syncthreads();  // everybody has read column j and the pivot
     if (cq == 0) {
       if (r == j) S[j][j] = ljj;
@@ -61,34 +61,67 @@ __global__ void __launch_bounds__(256) potf2_kernel(double* __restrict__ A, int 
       if (r >= c && r < nb) S[r][c] = S[r][c] - lrj * S[c][j];
     __syncthreads();
   }
+  return 0;
+}
+
+// One launch per 64-column block step: CTA 0 factors the diagonal block and writes it back; every other CTA owns 64
+// rows of the panel below it, factors the (L2-resident) diagonal block redundantly in its own shared memory — cheaper
+// than a second dependent launch — and then solves  X L_kk^T = A_ik  by column-oriented substitution (one barrier
+// per column).  Failure (pivot <= 1e-16) is detected identically by every CTA; CTA 0 records k+1 in *flag.
+__global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                          int* __restrict__ flag, int* __restrict__ loaded,
+                                                          int fast_chain) {
+  extern __shared__ double dyn_smem[];
+  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
+  double (*R)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  __shared__ double rdiag[NB];
+  if (*flag != 0) return;
+  const int tid = threadIdx.x;
+  const int r = tid & (NB - 1);   // row owned by this thread
+  const int cq = tid >> 6;        // column residue class (columns cq, cq+4, ...)
+  double* Ab = A + static_cast<size_t>(k0) * lda + k0;
+#pragma unroll 4
+  for (int c = cq; c < NB; c += 4) S[r][c] = (r < nb && c < nb && r >= c) ? Ab[static_cast<size_t>(c) * lda + r] : 0.0;
+  const int row0 = k0 + nb + (static_cast<int>(blockIdx.x) - 1) * NB;
+  const int rows = (blockIdx.x == 0) ? 0 : min(NB, n - row0);
+  if (blockIdx.x > 0) {
+    const double* Ar = A + static_cast<size_t>(k0) * lda + row0;
+#pragma unroll 4
+    for (int c = cq; c < NB; c += 4) R[r][c] = (r < rows && c < nb) ? Ar[static_cast<size_t>(c) * lda + r] : 0.0;
+  }
+  __syncthreads();
+  // CTA 0 overwrites the diagonal block in place; it must not do so before every panel CTA has read the original
+  if (blockIdx.x > 0 && tid == 0) atomicAdd(loaded, 1);
+  const int failed = factor_block(S, nb, k0, r, cq, fast_chain);
   if (failed) {
-    if (tid == 0) *flag = failed;
+    if (blockIdx.x == 0 && tid == 0) *flag = failed;
     return;
   }
+  if (blockIdx.x == 0) {
+    if (tid == 0) {
+      const int expect = static_cast<int>(gridDim.x) - 1;
+      while (atomicAdd(loaded, 0) < expect) __nanosleep(100);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = cq; c < NB; c += 4)
+      if (r < nb && c < nb && r >= c) Ab[static_cast<size_t>(c) * lda + r] = S[r][c];
+    return;
+  }
+  if (cq == 0) rdiag[r] = (r < nb) ? 1.0 / S[r][r] : 0.0;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    const double xj = R[r][j] * rdiag[j];
+    if (cq == (j & 3)) R[r][j] = xj;  // the owner of column j keeps the solved value
+    const int c0 = j + 1 + ((cq - (j + 1)) & 3);
+#pragma unroll 4
+    for (int c = c0; c < nb; c += 4) R[r][c] = R[r][c] - xj * S[c][j];
+    __syncthreads();
+  }
+  double* Aw = A + static_cast<size_t>(k0) * lda + row0;
 #pragma unroll 4
   for (int c = cq; c < NB; c += 4)
-    if (r < nb && c < nb && r >= c) Ab[static_cast<size_t>(c) * lda + r] = S[r][c];
-  // inv(L_kk) by column-oriented substitution on the identity, all 256 threads: V starts as I, then for each j
-  //   row j *= 1/L_jj ;  rows i > j: V[i][:] -= L_ij V[j][:]      (reciprocals of the diagonal taken once, in parallel)
-  if (invL != nullptr) {
-#pragma unroll 4
-    for (int c = cq; c < NB; c += 4) V[r][c] = (r == c && r < nb) ? 1.0 : 0.0;
-    if (cq == 0) rdiag[r] = (r < nb) ? 1.0 / S[r][r] : 0.0;
-    __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-      // only columns c <= j of row j are non-zero
-      if (r == j)
-        for (int c = cq; c <= j; c += 4) V[j][c] = V[j][c] * rdiag[j];
-      __syncthreads();
-      if (r > j && r < nb) {
-        const double lij = S[r][j];
-#pragma unroll 4
-        for (int c = cq; c <= j; c += 4) V[r][c] = V[r][c] - lij * V[j][c];
-      }
-      __syncthreads();
-    }
-    for (int e = tid; e < NB * NB; e += blockDim.x) invL[e] = V[e % NB][e / NB];
-  }
+    if (r < rows && c < nb) Aw[static_cast<size_t>(c) * lda + r] = R[r][c];
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -208,8 +241,10 @@ constexpr int GK = 16;        // K chunk
 constexpr int GST = 3;        // pipeline stages
 constexpr int GLD = GT + 4;   // 132 = 4 (mod 16): conflict-free fragment loads
 
-__global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ A, int lda, int n, int p0, int W,
-                                                           const int* __restrict__ flag) {
+constexpr int GTHREADS = 512;  // 16 warps = 4 x 4 warp tiles of 32 x 32 (4 warps per scheduler keep the DMMA pipe fed)
+
+__global__ void __launch_bounds__(GTHREADS, 1) dmma_gemm_kernel(double* __restrict__ A, int lda, int n, int p0, int W,
+                                                                const int* __restrict__ flag) {
   extern __shared__ double gsm[];
   if (*flag != 0) return;
   const int t0 = p0 + W;
@@ -231,7 +266,7 @@ __global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ 
     double* as = As + stage * GK * GLD;
     double* bs = Bs + stage * GK * GLD;
 #pragma unroll
-    for (int e = tid; e < GT * GK; e += 256) {
+    for (int e = tid; e < GT * GK; e += GTHREADS) {
       const int m = e % GT, k = e / GT;
       cp_async8(as + k * GLD + m, m < rows ? Ag + static_cast<size_t>(kc * GK + k) * lda + m : Ag, m < rows);
       cp_async8(bs + k * GLD + m, m < cols ? Bg + static_cast<size_t>(kc * GK + k) * lda + m : Bg, m < cols);
@@ -239,13 +274,13 @@ __global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ 
   };
 
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
   const int lr = lane >> 2, lc = lane & 3;
-  double acc[4][8][2];
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int st = 0; st < GST - 1; ++st) {
@@ -262,15 +297,15 @@ __global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ 
     const double* bs = Bs + (kc % GST) * GK * GLD;
 #pragma unroll
     for (int kk = 0; kk < GK; kk += 4) {
-      double a[4], bb[8];
+      double a[4], bb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = as[(kk + lc) * GLD + wm + i * 8 + lr];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bb[j] = bs[(kk + lc) * GLD + wn + j * 8 + lr];
+      for (int j = 0; j < 4; ++j) bb[j] = bs[(kk + lc) * GLD + wn + j * 8 + lr];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
     }
   }
   cp_async_wait<0>();
@@ -280,12 +315,12 @@ __global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(double* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) Cs[(wn + j * 8 + lc * 2 + h) * GLD + wm + i * 8 + lr] = acc[i][j][h];
   __syncthreads();
   double* Cg = A + static_cast<size_t>(col0) * lda + row0;
-  for (int e = tid; e < GT * GT; e += 256) {
+  for (int e = tid; e < GT * GT; e += GTHREADS) {
     const int r = e % GT, c = e / GT;
     if (r < rows && c < cols) {
       double* dst = Cg + static_cast<size_t>(c) * lda + r;
@@ -513,44 +548,44 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
   const size_t smem = 2 * NB * LDT * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  const size_t smem_potf2 = 2 * NB * (NB + 1) * sizeof(double);
-  CMOE_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem_potf2)));
+  const size_t smem_panel = 2 * NB * (NB + 1) * sizeof(double);
+  CMOE_CUDA(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem_panel)));
   const size_t smem_gemm = static_cast<size_t>(GT) * GLD * sizeof(double);  // >= 2*GST*GK*GLD doubles as well
   static_assert(GT * GLD >= 2 * GST * GK * GLD, "accumulator staging must cover the pipeline buffers");
   CMOE_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_gemm)));
   CMOE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
-  DevBuf<double> invL(NB * NB);
+  const int nsteps = (n + NB - 1) / NB;
+  DevBuf<int> loaded_buf(nsteps);  // one arrival counter per block step
+  int* loaded = loaded_buf.p;
+  CMOE_CUDA(cudaMemsetAsync(loaded, 0, nsteps * sizeof(int), s));
+  const int fast_chain = n > 4 * NB ? 1 : 0;  // small systems keep IEEE sqrt / divide (exact known-answer cases)
   for (int p0 = 0; p0 < n; p0 += W) {
     const int pw = min(W, n - p0);         // this panel's width
     const int pend = p0 + pw;
     for (int k0 = p0; k0 < pend; k0 += NB) {
       const int nb = min(NB, n - k0);
       const int rem = n - k0 - nb;
-      potf2_kernel<<<1, 256, smem_potf2, s>>>(A, n, k0, nb, rem > 0 ? invL.p : nullptr, flag);
+      const int row_tiles = (rem + NB - 1) / NB;
+      potrf_panel_kernel<<<1 + row_tiles, 256, smem_panel, s>>>(A, n, n, k0, nb, flag, loaded + k0 / NB, fast_chain);
       count_launch();
-      if (rem > 0) {
-        const int row_tiles = (rem + NB - 1) / NB;
-        dmma_tile_kernel<<<row_tiles, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 0, 1, flag);
+      // inner trailing update: only the columns that still belong to this outer panel
+      const int col_tiles = (pend - (k0 + nb) + NB - 1) / NB;
+      if (rem > 0 && col_tiles > 0) {
+        dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, nullptr, 1, col_tiles, flag);
         count_launch();
-        // inner trailing update: only the columns that still belong to this outer panel
-        const int col_tiles = (pend - (k0 + nb) + NB - 1) / NB;
-        if (col_tiles > 0) {
-          dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, invL.p, 1, col_tiles, flag);
-          count_launch();
-        }
       }
     }
     const int rem = n - pend;
     if (rem > 0 && pw == W) {
       const int tiles = (rem + GT - 1) / GT;
-      dmma_gemm_kernel<<<tiles * (tiles + 1) / 2, 256, smem_gemm, s>>>(A, n, n, p0, W, flag);
+      dmma_gemm_kernel<<<tiles * (tiles + 1) / 2, GTHREADS, smem_gemm, s>>>(A, n, n, p0, W, flag);
       count_launch();
     }
   }
   CMOE_CUDA(cudaGetLastError());
-  CMOE_CUDA(cudaStreamSynchronize(s));  // invL scratch is freed on return
+  CMOE_CUDA(cudaStreamSynchronize(s));  // the counter scratch is freed on return
 }
 
 void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s) {

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <functional>
 #include <limits>
+#include <memory>
 #include <queue>
 
 #include "internal.cuh"
@@ -237,6 +238,121 @@ BatchEval make_ei_eval(const cmoe_gp* gp, int q, const double* Xp, int p, int nu
   };
 }
 
+// ---- ensembles of GPs ("MCMC-averaged" acquisition: one GP per hyper-parameter sample) -----------------------------
+// KnowledgeGradientMCMCEvaluator (gpp_knowledge_gradient_mcmc_optimization.cpp:87-180): mean of the per-GP q-KG, divided
+// by the fidelity cost max_i prod_{j >= dim-nf} x_ij, gradient by the quotient rule.
+// ExpectedImprovementMCMCEvaluator (gpp_expected_improvement_mcmc_optimization.cpp:47-85): plain mean.
+// Every GP sees the same normal draws (the reference hands one NormalRNG to every per-GP state and rewinds it per call).
+// Divergence, documented in DESIGN.md: the reference's MCMC state refreshes only the FIRST candidate point in the copy
+// it computes the cost from (..mcmc_optimization.cpp:187-188); the cost here always uses the current q points.
+void apply_fidelity_cost(const double* pts, int nc, int q, int dim, int nf, int num_gp, double* values, double* grads) {
+  const size_t ps = static_cast<size_t>(q) * dim;
+  for (int c = 0; c < nc; ++c) {
+    const double* x = pts + c * ps;
+    double cost = 1.0;
+    int index = -1;
+    if (nf > 0) {
+      cost = 0.0;
+      for (int i = 0; i < q; ++i) {
+        double point_cost = 1.0;
+        for (int j = dim - nf; j < dim; ++j) point_cost *= x[static_cast<size_t>(i) * dim + j];
+        if (cost < point_cost) {
+          cost = point_cost;
+          index = i;
+        }
+      }
+    }
+    const double kg_avg = values[c] / static_cast<double>(num_gp);
+    values[c] = values[c] / (static_cast<double>(num_gp) * cost);
+    if (grads) {
+      double* g = grads + c * ps;
+      for (size_t k = 0; k < ps; ++k) {
+        double gradcost = 0.0;
+        if (index >= 0 && k / dim == static_cast<size_t>(index) && static_cast<int>(k % dim) >= dim - nf)
+          gradcost = cost / x[k];
+        const double ga = g[k] / static_cast<double>(num_gp);
+        g[k] = (ga * cost - kg_avg * gradcost) / (cost * cost);
+      }
+    }
+  }
+}
+
+struct KgEnsembleEvaluator {
+  std::vector<std::unique_ptr<KgEvaluator>> evs;
+  int q = 0, dim = 0, nf = 0;
+  std::vector<double> tv, tg;
+  void operator()(const double* pts, int nc, double* values, double* grads) {
+    const size_t ps = static_cast<size_t>(q) * dim;
+    // phase 1: enqueue every member on its own stream; phase 2: drain in member order (fixed summation order)
+    for (auto& ev : evs) {
+      cmoe_kg_plan* pl = grads ? ev->gplan : ev->vplan;
+      KgEvaluator::check(cmoe_kg_plan_upload(pl, pts, nc));
+      KgEvaluator::check(cmoe_kg_plan_run(pl));
+    }
+    std::fill(values, values + nc, 0.0);
+    if (grads) std::fill(grads, grads + nc * ps, 0.0);
+    tv.resize(nc);
+    if (grads) tg.resize(nc * ps);
+    for (auto& ev : evs) {
+      cmoe_kg_plan* pl = grads ? ev->gplan : ev->vplan;
+      int info = 0;
+      KgEvaluator::check(cmoe_kg_plan_sync(pl, &info), info);
+      KgEvaluator::check(cmoe_kg_plan_download(pl, tv.data(), grads ? tg.data() : nullptr, nullptr));
+      for (int c = 0; c < nc; ++c) values[c] += tv[c];
+      if (grads)
+        for (size_t k = 0; k < nc * ps; ++k) grads[k] += tg[k];
+    }
+    apply_fidelity_cost(pts, nc, q, dim, nf, static_cast<int>(evs.size()), values, grads);
+  }
+};
+
+void check_ensemble(const cmoe_gp* const* gps, int num_gp) {
+  CMOE_REQUIRE(gps != nullptr && num_gp >= 1, CMOE_ERR_BOUNDS, "an ensemble needs at least one GP");
+  for (int m = 0; m < num_gp; ++m) {
+    CMOE_REQUIRE(gps[m] != nullptr, CMOE_ERR_INVALID_VALUE, "NULL GP in ensemble");
+    CMOE_REQUIRE(gps[m]->spec.dim == gps[0]->spec.dim && gps[m]->spec.g == gps[0]->spec.g &&
+                     gps[m]->device == gps[0]->device,
+                 CMOE_ERR_INVALID_VALUE, "ensemble members must share dim, derivative observations and device");
+  }
+}
+
+void make_kg_ensemble(KgEnsembleEvaluator& ens, const cmoe_gp* const* gps, int num_gp, int nf,
+                      const cmoe_gd_params* inner, const double* inner_bounds, const double* discrete_pts, int num_pts,
+                      int max_value_cands, int max_grad_cands, int q, const double* Xp, int p, int num_mc,
+                      const double* best_so_far, uint64_t seed) {
+  const int dim = gps[0]->spec.dim;
+  ens.q = q;
+  ens.dim = dim;
+  ens.nf = nf;
+  for (int m = 0; m < num_gp; ++m) {
+    ens.evs.emplace_back(new KgEvaluator());
+    make_kg_evaluator(*ens.evs.back(), gps[m], nf, inner, inner_bounds,
+                      discrete_pts + static_cast<size_t>(m) * num_pts * (dim - nf), num_pts, max_value_cands,
+                      max_grad_cands, q, Xp, p, num_mc, best_so_far[m], seed);
+  }
+}
+
+BatchEval make_ei_ensemble(const cmoe_gp* const* gps, int num_gp, int q, const double* Xp, int p, int num_mc,
+                           const double* best_so_far, uint64_t seed) {
+  std::vector<BatchEval> members;
+  for (int m = 0; m < num_gp; ++m) members.push_back(make_ei_eval(gps[m], q, Xp, p, num_mc, best_so_far[m], seed));
+  const size_t ps = static_cast<size_t>(q) * gps[0]->spec.dim;
+  return [members, ps, num_gp](const double* pts, int nc, double* values, double* grads) {
+    std::vector<double> tv(nc), tg(grads ? nc * ps : 0);
+    std::fill(values, values + nc, 0.0);
+    if (grads) std::fill(grads, grads + nc * ps, 0.0);
+    for (const BatchEval& f : members) {
+      f(pts, nc, tv.data(), grads ? tg.data() : nullptr);
+      for (int c = 0; c < nc; ++c) values[c] += tv[c];
+      if (grads)
+        for (size_t k = 0; k < nc * ps; ++k) grads[k] += tg[k];
+    }
+    for (int c = 0; c < nc; ++c) values[c] /= static_cast<double>(num_gp);
+    if (grads)
+      for (size_t k = 0; k < nc * ps; ++k) grads[k] /= static_cast<double>(num_gp);
+  };
+}
+
 void validate_bounds(const double* b, int dim) {
   for (int d = 0; d < dim; ++d)
     CMOE_REQUIRE(b[2 * d] <= b[2 * d + 1], CMOE_ERR_BOUNDS, "Tensor product region is EMPTY.");
@@ -305,6 +421,107 @@ int cmoe_ei_gradient_descent(const cmoe_gp* gp, const cmoe_gd_params* outer, con
     validate_bounds(domain_bounds, gp->spec.dim);
     BatchEval f = make_ei_eval(gp, q, points_being_sampled, p, num_mc, best_so_far, seed);
     gradient_descent_batch(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts, values_out, points_out);
+  });
+}
+
+int cmoe_kg_eval_mcmc(const cmoe_gp* const* gps, int num_gp, int num_fidelity, const cmoe_gd_params* inner,
+                      const double* inner_bounds, const double* discrete_pts, int num_pts, const double* candidates,
+                      int num_candidates, int q, const double* points_being_sampled, int p, int num_mc,
+                      const double* best_so_far, uint64_t seed, const double* normals_table, double* values,
+                      double* grads, int* info) {
+  return guarded(info, [&] {
+    check_ensemble(gps, num_gp);
+    CMOE_REQUIRE(num_candidates >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    const int dim = gps[0]->spec.dim;
+    const size_t ps = static_cast<size_t>(q) * dim;
+    std::vector<double> tv(num_candidates), tg(grads ? num_candidates * ps : 0);
+    std::fill(values, values + num_candidates, 0.0);
+    if (grads) std::fill(grads, grads + num_candidates * ps, 0.0);
+    for (int m = 0; m < num_gp; ++m) {
+      int inf = 0;
+      const int rc = cmoe_kg_eval(gps[m], num_fidelity, inner, inner_bounds,
+                                  discrete_pts + static_cast<size_t>(m) * num_pts * (dim - num_fidelity), num_pts,
+                                  candidates, num_candidates, q, points_being_sampled, p, num_mc, best_so_far[m], seed,
+                                  normals_table, tv.data(), grads ? tg.data() : nullptr, nullptr, &inf);
+      if (rc != CMOE_OK) throw Error(rc, cmoe_last_error(), inf);
+      for (int c = 0; c < num_candidates; ++c) values[c] += tv[c];
+      if (grads)
+        for (size_t k = 0; k < num_candidates * ps; ++k) grads[k] += tg[k];
+    }
+    apply_fidelity_cost(candidates, num_candidates, q, dim, num_fidelity, num_gp, values, grads);
+  });
+}
+
+int cmoe_ei_analytic(const cmoe_gp* gp, const double* points, int num_points, double best_so_far, double* values,
+                     double* grads, int* info) {
+  return guarded(info, [&] {
+    CMOE_REQUIRE(num_points >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gp->device);
+    analytic_ei(gp, points, num_points, best_so_far, values, grads);
+  });
+}
+
+int cmoe_ei_eval_mcmc(const cmoe_gp* const* gps, int num_gp, const double* candidates, int num_candidates, int q,
+                      const double* points_being_sampled, int p, int num_mc, const double* best_so_far, uint64_t seed,
+                      const double* normals_table, int analytic_single, double* values, double* grads, int* info) {
+  return guarded(info, [&] {
+    check_ensemble(gps, num_gp);
+    CMOE_REQUIRE(num_candidates >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gps[0]->device);
+    const size_t ps = static_cast<size_t>(q) * gps[0]->spec.dim;
+    std::vector<double> tv(num_candidates), tg(grads ? num_candidates * ps : 0);
+    std::fill(values, values + num_candidates, 0.0);
+    if (grads) std::fill(grads, grads + num_candidates * ps, 0.0);
+    for (int m = 0; m < num_gp; ++m) {
+      if (analytic_single && q == 1 && p == 0)
+        analytic_ei(gps[m], candidates, num_candidates, best_so_far[m], tv.data(), grads ? tg.data() : nullptr);
+      else
+        ei_eval_batch(*gps[m], candidates, num_candidates, q, points_being_sampled, p, num_mc, best_so_far[m], seed,
+                      normals_table, tv.data(), grads ? tg.data() : nullptr);
+      for (int c = 0; c < num_candidates; ++c) values[c] += tv[c];
+      if (grads)
+        for (size_t k = 0; k < num_candidates * ps; ++k) grads[k] += tg[k];
+    }
+    for (int c = 0; c < num_candidates; ++c) values[c] /= static_cast<double>(num_gp);
+    if (grads)
+      for (size_t k = 0; k < num_candidates * ps; ++k) grads[k] /= static_cast<double>(num_gp);
+  });
+}
+
+int cmoe_multistart_kg_mcmc(const cmoe_gp* const* gps, int num_gp, int num_fidelity, const cmoe_gd_params* outer,
+                            const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                            const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                            const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                            uint64_t seed, double* start_values, double* best_point, double* best_value,
+                            int* found_flag, int* info) {
+  return guarded(info, [&] {
+    check_ensemble(gps, num_gp);
+    CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gps[0]->device);
+    validate_bounds(domain_bounds, gps[0]->spec.dim);
+    KgEnsembleEvaluator ens;
+    make_kg_ensemble(ens, gps, num_gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_starts,
+                     std::min(kTopK, num_starts), q, points_being_sampled, p, num_mc, best_so_far, seed);
+    BatchEval f = std::ref(ens);
+    multistart_common(f, *outer, domain_bounds, q, gps[0]->spec.dim, starts, num_starts,
+                      -std::numeric_limits<double>::infinity(), start_values, best_point, best_value, found_flag);
+  });
+}
+
+int cmoe_multistart_ei_mcmc(const cmoe_gp* const* gps, int num_gp, const cmoe_gd_params* outer,
+                            const double* domain_bounds, const double* starts, int num_starts, int q,
+                            const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                            uint64_t seed, double* start_values, double* best_point, double* best_value,
+                            int* found_flag, int* info) {
+  return guarded(info, [&] {
+    check_ensemble(gps, num_gp);
+    CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gps[0]->device);
+    validate_bounds(domain_bounds, gps[0]->spec.dim);
+    BatchEval f = make_ei_ensemble(gps, num_gp, q, points_being_sampled, p, num_mc, best_so_far, seed);
+    // io_container starts from 0.0 in the MCMC drivers (gpp_expected_improvement_mcmc_optimization.hpp:914,968)
+    multistart_common(f, *outer, domain_bounds, q, gps[0]->spec.dim, starts, num_starts, 0.0, start_values, best_point,
+                      best_value, found_flag);
   });
 }
 

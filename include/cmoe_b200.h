@@ -183,6 +183,59 @@ int cmoe_ei_gradient_descent(const cmoe_gp* gp, const cmoe_gd_params* outer, con
                              int num_mc, double best_so_far, uint64_t seed, double* values_out, double* points_out,
                              int* info);
 
+/* Closed-form one-point EI and its gradient at num_points points (OnePotentialSampleExpectedImprovementEvaluator,
+ * gpp_math.cpp:2196-2253) — what EvaluateEIAtPointList and the multistart driver use when q = 1, p = 0
+ * (gpp_math.cpp:2317, gpp_math.hpp:1703-1749).  values[num_points]; grads[num_points][dim] or NULL. */
+int cmoe_ei_analytic(const cmoe_gp* gp, const double* points, int num_points, double best_so_far, double* values,
+                     double* grads, int* info);
+
+/* ---- ensembles of GPs: "MCMC-averaged" acquisition, one GP per hyper-parameter sample ----------------------------
+ * The reference's GaussianProcessMCMC is a list of GPs over the same data (gpp_knowledge_gradient_mcmc_optimization.cpp:
+ * 24-48); here it is an array of cmoe_gp handles (same dim / derivative observations / device).
+ * discrete_pts[num_gp][num_pts][dim-num_fidelity] and best_so_far[num_gp] are per member, as in the reference.
+ *
+ * cmoe_kg_eval_mcmc      KnowledgeGradientMCMCEvaluator::Compute{,Grad}KnowledgeGradient (..mcmc_optimization.cpp:137-180)
+ *                        = mean_m KG_m / cost,  cost = max_i prod_{j>=dim-nf} x_ij (1 when num_fidelity = 0, :87-104);
+ *                        gradient by the quotient rule (:162-180).  Python: compute_knowledge_gradient_mcmc,
+ *                        compute_grad_knowledge_gradient_mcmc, evaluate_KG_mcmc_at_point_list
+ *                        (gpp_python_knowledge_gradient_mcmc.cpp:80-198, 326-384).
+ * cmoe_ei_eval_mcmc      ExpectedImprovementMCMCEvaluator (gpp_expected_improvement_mcmc_optimization.cpp:47-85):
+ *                        mean_m of the Monte-Carlo q-EI; with analytic_single != 0 and q = 1, p = 0 the closed-form
+ *                        1-EI per member instead, as EvaluateEIMCMCAtPointList does (..mcmc_optimization.cpp:251).  Python: compute_expected_improvement_mcmc, ..grad.., evaluate_EI_mcmc_at_point_list.
+ * cmoe_multistart_*_mcmc ComputeKGMCMCOptimalPointsToSampleViaMultistartGradientDescent (..mcmc_optimization.hpp:665-745)
+ *                        and ComputeEIMCMC... (gpp_expected_improvement_mcmc_optimization.hpp:860-980): screen, top-20,
+ *                        restarted gradient descent, strict-> arg-max (initial best -inf for KG, 0.0 for EI; the EI
+ *                        driver uses analytic 1-EI per member when q = 1, p = 0).
+ * normals_table: as in cmoe_kg_eval / cmoe_ei_eval (NULL = Philox stream keyed by seed); shared by every member. */
+int cmoe_kg_eval_mcmc(const cmoe_gp* const* gps, int num_gp, int num_fidelity, const cmoe_gd_params* inner,
+                      const double* inner_bounds, const double* discrete_pts, int num_pts, const double* candidates,
+                      int num_candidates, int q, const double* points_being_sampled, int p, int num_mc,
+                      const double* best_so_far, uint64_t seed, const double* normals_table, double* values,
+                      double* grads, int* info);
+int cmoe_ei_eval_mcmc(const cmoe_gp* const* gps, int num_gp, const double* candidates, int num_candidates, int q,
+                      const double* points_being_sampled, int p, int num_mc, const double* best_so_far, uint64_t seed,
+                      const double* normals_table, int analytic_single, double* values, double* grads, int* info);
+int cmoe_multistart_kg_mcmc(const cmoe_gp* const* gps, int num_gp, int num_fidelity, const cmoe_gd_params* outer,
+                            const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                            const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                            const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                            uint64_t seed, double* start_values, double* best_point, double* best_value,
+                            int* found_flag, int* info);
+int cmoe_multistart_ei_mcmc(const cmoe_gp* const* gps, int num_gp, const cmoe_gd_params* outer,
+                            const double* domain_bounds, const double* starts, int num_starts, int q,
+                            const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                            uint64_t seed, double* start_values, double* best_point, double* best_value,
+                            int* found_flag, int* info);
+
+/* posterior_mean_optimization (gpp_python_knowledge_gradient.cpp:306-350): ComputeOptimalPosteriorMean
+ * (gpp_knowledge_gradient_optimization.cpp:420-472) from ONE start on the un-fantasised GP — line-search gradient
+ * descent on -mu(x) over the dim-num_fidelity free coordinates (fidelity coordinates pinned to 1.0).
+ * best_point[dim-num_fidelity]; best_value = -min mu found (the reference's best_function_value).
+ * With max_num_restarts <= 0 nothing is written and *found_flag = 0, as in the reference (:424-426). */
+int cmoe_posterior_mean_optimization(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* params,
+                                     const double* domain_bounds, const double* initial_guess, double* best_point,
+                                     double* best_value, int* found_flag);
+
 /* ---- building blocks exposed for parity tests and micro-benchmarks ------------------------------------------------ */
 /* Covariance build alone on device-resident inputs: returns device time (usec) of `repeats` builds of the n*n matrix. */
 int cmoe_bench_cov_build(const cmoe_gp* gp, int repeats, double* usec_per_build);

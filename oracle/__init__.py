@@ -95,6 +95,16 @@ class CpuGP:
         self.b._fn("gp_mean_additional")(self.h, _d(pts), pts.shape[0], _d(out))
         return out
 
+    def posterior_mean_optimization(self, initial_guess, gd, bounds, num_fidelity=0):
+        x0 = _f64(initial_guess).ravel()
+        gd = _f64(gd)
+        bounds = _f64(bounds).ravel()
+        best = np.zeros(self.dim - num_fidelity)
+        f = self.b._fn("posterior_mean_optimization")
+        f.restype = ctypes.c_double
+        v = f(self.h, int(num_fidelity), _d(gd), _d(bounds), _d(x0), _d(best))
+        return best, v
+
     def ei(self, Xq, Xp, num_mc, best_so_far, table, grad=False):
         Xq = _f64(Xq).reshape(-1, self.dim)
         Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
@@ -191,6 +201,72 @@ class CpuBackend:
         if not h:
             return None, lm.value
         return CpuGP(self, ctypes.c_void_p(h), kernel, dim, N, derivs), 0
+
+    # ---- MCMC-averaged acquisition over an ensemble of Matern-5/2 GPs (hypers[M][1+dim], noises[M][1+g]) ----
+    def _ensemble(self, hypers, noises, X, y, derivs):
+        hypers = _f64(hypers)
+        noises = _f64(noises)
+        gps = []
+        for m in range(hypers.shape[0]):
+            gp, lm = self.gp(1, hypers[m, 0], hypers[m, 1:], X, y, noises[m], derivs)
+            assert gp is not None, f"ensemble member {m} singular (leading minor {lm})"
+            gps.append(gp)
+        return gps
+
+    def kg_mcmc(self, hypers, noises, X, y, derivs, Xq, Xp, num_mc, best_so_far, table, gd, inner_bounds,
+                discrete_pts, num_fidelity=0, grad=False):
+        hypers, noises, X, y = _f64(hypers), _f64(noises), _f64(X), _f64(y)
+        derivs = _i32(derivs if derivs is not None else [])
+        dim = X.shape[1]
+        Xq = _f64(Xq).reshape(-1, dim)
+        Xp = _f64(Xp if Xp is not None else np.zeros((0, dim)))
+        q, p = Xq.shape[0], (Xp.size // dim)
+        best = _f64(best_so_far).ravel()
+        table = _f64(table).ravel()
+        gd = _f64(gd)
+        ib = _f64(inner_bounds).ravel()
+        D = _f64(discrete_pts)
+        M = hypers.shape[0]
+        num_pts = D.size // (M * (dim - num_fidelity))
+        g = np.zeros((q, dim)) if grad else None
+        gptr = _d(g) if grad else None
+        if self.prefix == "ref_":
+            f = self._fn("kg_mcmc")
+            f.restype = ctypes.c_double
+            v = f(_d(hypers), _d(noises), M, _d(X), _d(y), _i(derivs), derivs.size, dim, X.shape[0],
+                  int(num_fidelity), _d(gd), _d(ib), _d(D), num_pts, _d(Xq), _d(Xp), q, p, int(num_mc), _d(best),
+                  _d(table), table.size, gptr)
+        else:
+            gps = self._ensemble(hypers, noises, X, y, derivs)
+            arr = (ctypes.c_void_p * M)(*[gp.h for gp in gps])
+            f = self._fn("kg_mcmc")
+            f.restype = ctypes.c_double
+            v = f(arr, M, int(num_fidelity), _d(gd), _d(ib), _d(D), num_pts, _d(Xq), _d(Xp), q, p, int(num_mc),
+                  _d(best), _d(table), table.size, gptr)
+        return (v, g) if grad else v
+
+    def ei_mcmc(self, hypers, noises, X, y, derivs, Xq, Xp, num_mc, best_so_far, table, grad=False):
+        hypers, noises, X, y = _f64(hypers), _f64(noises), _f64(X), _f64(y)
+        derivs = _i32(derivs if derivs is not None else [])
+        dim = X.shape[1]
+        Xq = _f64(Xq).reshape(-1, dim)
+        Xp = _f64(Xp if Xp is not None else np.zeros((0, dim)))
+        q, p = Xq.shape[0], (Xp.size // dim)
+        best = _f64(best_so_far).ravel()
+        table = _f64(table).ravel()
+        M = hypers.shape[0]
+        g = np.zeros((q, dim)) if grad else None
+        gptr = _d(g) if grad else None
+        f = self._fn("ei_mcmc")
+        f.restype = ctypes.c_double
+        if self.prefix == "ref_":
+            v = f(_d(hypers), _d(noises), M, _d(X), _d(y), _i(derivs), derivs.size, dim, X.shape[0], _d(Xq), _d(Xp),
+                  q, p, int(num_mc), _d(best), _d(table), table.size, gptr)
+        else:
+            gps = self._ensemble(hypers, noises, X, y, derivs)
+            arr = (ctypes.c_void_p * M)(*[gp.h for gp in gps])
+            v = f(arr, M, _d(Xq), _d(Xp), q, p, int(num_mc), _d(best), _d(table), table.size, gptr)
+        return (v, g) if grad else v
 
     def max_threads(self):
         f = self._fn("max_threads")

@@ -945,6 +945,18 @@ done_early:
   return result;
 }
 
+/* ref: gpp_python_knowledge_gradient.cpp:306-350 -> ComputeOptimalPosteriorMean with one start on the GP itself */
+double oracle_posterior_mean_optimization(const oracle_gp* gp, int num_fidelity, const double* gd,
+                                          const double* bounds, const double* initial_guess, double* best_point) {
+  kg_ctx c;
+  c.base = gp;
+  c.nf = num_fidelity;
+  c.aug = *gp;
+  double best_value = 0.0;
+  optimal_posterior_mean(&c, gd, bounds, initial_guess, 1, best_point, &best_value);
+  return best_value;
+}
+
 double oracle_kg(const oracle_gp* gp, int num_fidelity, const double* gd, const double* inner_bounds,
                  const double* discrete_pts, int num_pts, const double* Xq, const double* Xp, int q, int p,
                  int num_mc, double best_so_far, const double* table, int table_len, double* grad,
@@ -1031,3 +1043,65 @@ void oracle_ei_at_point_list(const oracle_gp* gp, const double* candidates, cons
 }
 
 int oracle_max_threads(void) { return omp_get_max_threads(); }
+
+/* ---- MCMC-averaged acquisition over an ensemble of GPs ---------------------------------------------------------------
+ * ref: KnowledgeGradientMCMCEvaluator::ComputeCost / ComputeGradCost / ComputeKnowledgeGradient /
+ * ComputeGradKnowledgeGradient (gpp_knowledge_gradient_mcmc_optimization.cpp:87-180) and
+ * ExpectedImprovementMCMCEvaluator (gpp_expected_improvement_mcmc_optimization.cpp:47-85).
+ * discrete_pts[num_gp][num_pts][dim-nf], best_so_far[num_gp]; every member replays the same table. */
+double oracle_kg_mcmc(const oracle_gp* const* gps, int num_gp, int num_fidelity, const double* gd,
+                      const double* inner_bounds, const double* discrete_pts, int num_pts, const double* Xq,
+                      const double* Xp, int q, int p, int num_mc, const double* best_so_far, const double* table,
+                      int table_len, double* grad) {
+  const int dim = gps[0]->dim, ps = dim - num_fidelity;
+  double* tmp = dalloc((size_t)q * dim);
+  double total = 0.0;
+  if (grad) memset(grad, 0, (size_t)q * dim * sizeof(double));
+  for (int m = 0; m < num_gp; ++m) {
+    total += oracle_kg(gps[m], num_fidelity, gd, inner_bounds, discrete_pts + (size_t)m * num_pts * ps, num_pts, Xq, Xp,
+                       q, p, num_mc, best_so_far[m], table, table_len, grad ? tmp : NULL, NULL);
+    if (grad)
+      for (int k = 0; k < q * dim; ++k) grad[k] += tmp[k];
+  }
+  double cost = 1.0;
+  int index = -1;
+  if (num_fidelity > 0) {
+    cost = 0.0;
+    for (int i = 0; i < q; ++i) {
+      double point_cost = 1.0;
+      for (int j = ps; j < dim; ++j) point_cost *= Xq[i * dim + j];
+      if (cost < point_cost) {
+        cost = point_cost;
+        index = i;
+      }
+    }
+  }
+  if (grad) {
+    const double kg = total / (double)num_gp;
+    for (int k = 0; k < q * dim; ++k) {
+      double gradcost = 0.0;
+      if (index >= 0 && k / dim == index && k % dim >= ps) gradcost = cost / Xq[k];
+      const double ga = grad[k] / (double)num_gp;
+      grad[k] = (ga * cost - kg * gradcost) / (cost * cost);
+    }
+  }
+  free(tmp);
+  return total / ((double)num_gp * cost);
+}
+
+double oracle_ei_mcmc(const oracle_gp* const* gps, int num_gp, const double* Xq, const double* Xp, int q, int p,
+                      int num_mc, const double* best_so_far, const double* table, int table_len, double* grad) {
+  const int dim = gps[0]->dim;
+  double* tmp = dalloc((size_t)q * dim);
+  double total = 0.0;
+  if (grad) memset(grad, 0, (size_t)q * dim * sizeof(double));
+  for (int m = 0; m < num_gp; ++m) {
+    total += oracle_ei(gps[m], Xq, Xp, q, p, num_mc, best_so_far[m], table, table_len, grad ? tmp : NULL);
+    if (grad)
+      for (int k = 0; k < q * dim; ++k) grad[k] += tmp[k];
+  }
+  if (grad)
+    for (int k = 0; k < q * dim; ++k) grad[k] /= (double)num_gp;
+  free(tmp);
+  return total / (double)num_gp;
+}

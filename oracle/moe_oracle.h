@@ -47,6 +47,17 @@ double oracle_kg(const oracle_gp* gp, int num_fidelity, const double* gd, const 
                  int num_mc, double best_so_far, const double* table, int table_len, double* grad,
                  double* best_points);
 
+/* MCMC-averaged q-KG / q-EI over an ensemble (discrete_pts[num_gp][num_pts][dim-nf], best_so_far[num_gp]) */
+double oracle_kg_mcmc(const oracle_gp* const* gps, int num_gp, int num_fidelity, const double* gd,
+                      const double* inner_bounds, const double* discrete_pts, int num_pts, const double* Xq,
+                      const double* Xp, int q, int p, int num_mc, const double* best_so_far, const double* table,
+                      int table_len, double* grad);
+double oracle_ei_mcmc(const oracle_gp* const* gps, int num_gp, const double* Xq, const double* Xp, int q, int p,
+                      int num_mc, const double* best_so_far, const double* table, int table_len, double* grad);
+
+double oracle_posterior_mean_optimization(const oracle_gp* gp, int num_fidelity, const double* gd,
+                                          const double* bounds, const double* initial_guess, double* best_point);
+
 void oracle_limit_update(const double* bounds, int dim, double max_relative_change, const double* current_point,
                          double* update);
 

@@ -27,6 +27,8 @@
 #include "gpp_covariance.hpp"
 #include "gpp_domain.hpp"
 #include "gpp_exception.hpp"
+#include "gpp_expected_improvement_mcmc_optimization.hpp"
+#include "gpp_knowledge_gradient_mcmc_optimization.hpp"
 #include "gpp_knowledge_gradient_optimization.hpp"
 #include "gpp_linear_algebra.hpp"
 #include "gpp_optimization.hpp"
@@ -249,6 +251,64 @@ void ref_ei_grad_at_point_list(void* h, const double* candidates, const double* 
       ev.ComputeGradExpectedImprovement(&st, grads + static_cast<size_t>(c) * q * dim);
     }
   }
+}
+
+// ComputeOptimalPosteriorMean from one start on the un-fantasised GP (gpp_knowledge_gradient_optimization.cpp:420-472);
+// the body of the Python boundary's posterior_mean_optimization (gpp_python_knowledge_gradient.cpp:306-350).
+double ref_posterior_mean_optimization(void* h, int num_fidelity, const double* gd, const double* bounds,
+                                       const double* initial_guess, double* best_point) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  TensorProductDomain dom = MakeDomain(bounds, gp->dim() - num_fidelity);
+  GradientDescentParameters params = MakeGD(gd);
+  bool found = false;
+  double best_value = 0.0;
+  ComputeOptimalPosteriorMean(*gp, num_fidelity, params, dom, initial_guess, 1, &found, best_point, &best_value);
+  return best_value;
+}
+
+// ---- MCMC-averaged acquisition over an ensemble of Matern-5/2 GPs (one per hyper-parameter sample) ----
+// GaussianProcessMCMC (gpp_knowledge_gradient_mcmc_optimization.cpp:24-48): hypers[num_mcmc][1+dim] = (alpha, lengths),
+// noises[num_mcmc][1+g].  Table-fed normals, shared by every member (each evaluation rewinds the table).
+double ref_kg_mcmc(const double* hypers, const double* noises, int num_mcmc, const double* X, const double* y,
+                   const int* derivs, int g, int dim, int N, int num_fidelity, const double* gd,
+                   const double* inner_bounds, const double* discrete_pts, int num_pts, const double* Xq,
+                   const double* Xp, int q, int p, int num_mc, const double* best_so_far, const double* table,
+                   int table_len, double* grad) {
+  GaussianProcessMCMC gpm(hypers, noises, num_mcmc, X, y, derivs, g, dim, N);
+  std::vector<double> tab(table, table + table_len);
+  NormalRNGSimulator rng(tab);
+  TensorProductDomain dom = MakeDomain(inner_bounds, dim - num_fidelity);
+  GradientDescentParameters inner = MakeGD(gd);
+  std::vector<KnowledgeGradientState<TensorProductDomain>::EvaluatorType> evs;
+  KnowledgeGradientMCMCEvaluator<TensorProductDomain> ev(gpm, num_fidelity, discrete_pts, num_pts, num_mc, dom, inner,
+                                                         best_so_far, &evs);
+  std::vector<KnowledgeGradientEvaluator<TensorProductDomain>::StateType> states;
+  KnowledgeGradientMCMCEvaluator<TensorProductDomain>::StateType st(ev, Xq, Xp, q, p, num_pts, derivs, g,
+                                                                    grad != nullptr, &rng, &states);
+  const double v = ev.ComputeKnowledgeGradient(&st);
+  if (grad) {
+    std::fill(grad, grad + static_cast<size_t>(q) * dim, 0.0);  // the evaluator accumulates with += (:166)
+    ev.ComputeGradKnowledgeGradient(&st, grad);
+  }
+  return v;
+}
+
+double ref_ei_mcmc(const double* hypers, const double* noises, int num_mcmc, const double* X, const double* y,
+                   const int* derivs, int g, int dim, int N, const double* Xq, const double* Xp, int q, int p,
+                   int num_mc, const double* best_so_far, const double* table, int table_len, double* grad) {
+  GaussianProcessMCMC gpm(hypers, noises, num_mcmc, X, y, derivs, g, dim, N);
+  std::vector<double> tab(table, table + table_len);
+  NormalRNGSimulator rng(tab);
+  std::vector<ExpectedImprovementState::EvaluatorType> evs;
+  ExpectedImprovementMCMCEvaluator ev(gpm, num_mc, best_so_far, &evs);
+  std::vector<ExpectedImprovementEvaluator::StateType> states;
+  ExpectedImprovementMCMCEvaluator::StateType st(ev, Xq, Xp, q, p, derivs, g, grad != nullptr, &rng, &states);
+  const double v = ev.ComputeExpectedImprovement(&st);
+  if (grad) {
+    std::fill(grad, grad + static_cast<size_t>(q) * dim, 0.0);
+    ev.ComputeGradExpectedImprovement(&st, grad);
+  }
+  return v;
 }
 
 // LimitUpdate (gpp_domain.cpp:64-104) for pinning the restatement.

@@ -162,3 +162,61 @@ def test_kg_fidelity_dim(libs):
     vr, gr_ = gr.kg(*args, num_fidelity=1, grad=True)
     np.testing.assert_allclose(vo, vr, rtol=1e-9)
     np.testing.assert_allclose(go_, gr_, rtol=1e-6, atol=1e-9)
+
+
+def _ensemble_inputs(M, dim, g, seed):
+    rng = np.random.default_rng(seed)
+    hypers = np.concatenate([rng.uniform(0.8, 1.5, size=(M, 1)), rng.uniform(0.4, 0.9, size=(M, dim))], axis=1)
+    noises = rng.uniform(0.05, 0.15, size=(M, 1 + g))
+    return hypers, noises
+
+
+@pytest.mark.parametrize("q,p,g_idx,nf", [(1, 0, (), 0), (2, 1, (), 0), (2, 0, (0,), 0), (1, 0, (), 1), (2, 1, (), 1)])
+def test_kg_mcmc_table_fed(libs, q, p, g_idx, nf):
+    """MCMC-averaged q-KG incl. the fidelity-cost quotient rule (gpp_knowledge_gradient_mcmc_optimization.cpp:87-180)."""
+    o, r = libs
+    M, dim, mc, num_pts = 3, 3, 8, 4
+    prob = make_problem(12, dim, g_idx=g_idx, seed=31, noise=0.1)
+    hypers, noises = _ensemble_inputs(M, dim, len(g_idx), 5)
+    rng = np.random.default_rng(6)
+    Xq, Xp = rng.uniform(0.2, 0.9, size=(q, dim)), rng.uniform(size=(p, dim))
+    disc = rng.uniform(size=(M, num_pts, dim - nf))
+    best = rng.uniform(-0.5, 0.5, size=M)
+    table = rng.standard_normal((mc // 2) * (q + p) * (1 + len(g_idx)))
+    args = (hypers, noises, prob["X"], prob["y"], prob["derivs"], Xq, Xp, mc, best, table, EXAMPLE_INNER_GD,
+            unit_bounds(dim - nf), disc)
+    vo, go_ = o.kg_mcmc(*args, num_fidelity=nf, grad=True)
+    vr, gr_ = r.kg_mcmc(*args, num_fidelity=nf, grad=True)
+    np.testing.assert_allclose(vo, vr, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(go_, gr_, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(o.kg_mcmc(*args, num_fidelity=nf), vo, rtol=1e-12)
+
+
+@pytest.mark.parametrize("q,p", [(1, 0), (3, 2)])
+def test_ei_mcmc_table_fed(libs, q, p):
+    o, r = libs
+    M, dim, mc = 4, 3, 16
+    prob = make_problem(15, dim, seed=32, noise=0.05)
+    hypers, noises = _ensemble_inputs(M, dim, 0, 7)
+    rng = np.random.default_rng(8)
+    Xq, Xp = rng.uniform(size=(q, dim)), rng.uniform(size=(p, dim))
+    best = rng.uniform(0.5, 1.5, size=M)
+    table = rng.standard_normal(mc * (q + p))
+    args = (hypers, noises, prob["X"], prob["y"], prob["derivs"], Xq, Xp, mc, best, table)
+    vo, go_ = o.ei_mcmc(*args, grad=True)
+    vr, gr_ = r.ei_mcmc(*args, grad=True)
+    np.testing.assert_allclose(vo, vr, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(go_, gr_, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("kernel,g_idx,nf", [(0, (), 0), (1, (0, 2), 0), (1, (), 1)])
+def test_posterior_mean_optimization(libs, kernel, g_idx, nf):
+    """ComputeOptimalPosteriorMean from one start (gpp_knowledge_gradient_optimization.cpp:420-472)."""
+    prob = make_problem(20, 3, g_idx=g_idx, seed=3)
+    go, gr = _gp_pair(libs, kernel, prob)
+    gd = [1, 50, 3, 0, 0.7, 1.0, 0.2, 1e-8]
+    x0 = np.array([0.3, 0.6, 0.5])[: 3 - nf]
+    bo, vo = go.posterior_mean_optimization(x0, gd, unit_bounds(3 - nf), nf)
+    br, vr = gr.posterior_mean_optimization(x0, gd, unit_bounds(3 - nf), nf)
+    np.testing.assert_allclose(bo, br, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(vo, vr, rtol=1e-12)
