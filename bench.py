@@ -240,17 +240,27 @@ def main():
     ms_per_step = dev_ms / args.steps
     value = total_samples / (ms_per_step * 1e-3)
     e2e_value = total_samples / (e2e_s / args.steps)
-    # roofline of the dominant kernel: algorithmic FP64 flops it executed (from its own evaluation counter) / its time
+    # roofline of the dominant kernel: FP64 flops of the work it EXECUTED (from its own counters) / its time.
+    # Conventions of SURVEY.md 8(d): FMA = 2 flops, exp = 1 flop.  Per training/union row:
+    #   point evaluation (value + gradient at one query point): dot 2d, weight a_j 2q, exp 1, value 2, scale 1, gradient 2d
+    #   line batch (all KB = 8 backtracking trials of a step):  two dots 4d, weight 2q, two exps 2, scale 1,
+    #                                                            KB fma 2KB, KB-1 squarings
     rows = w["N"] + w["q"]
-    flops_per_eval = rows * (2 * w["dim"] + 2 * w["q"] + 2 * w["dim"] + 2 + 1 + 2)  # dot, a_j, grad acc, value acc, exp, scale
+    KB = 8
+    flops_point = rows * (2 * w["dim"] + 2 * w["q"] + 1 + 2 + 1 + 2 * w["dim"])
+    flops_line = rows * (4 * w["dim"] + 2 * w["q"] + 2 + 1 + 2 * KB + (KB - 1))
     fp64_fma, fp64_dmma = capi.fp64_peaks(device)
-    achieved = stats["posterior_evals"] * flops_per_eval / (mc_ms / args.steps * 1e-3) * 1e-12
+    executed = stats["point_evals"] * flops_point + stats["line_batches"] * flops_line
+    achieved = executed / (mc_ms / args.steps * 1e-3) * 1e-12
     roofline = {"bound": "fp64-fma (vector pipe; neither hbm nor tensor)", "achieved": achieved, "peak": fp64_fma,
                 "unit": "TFLOP/s", "frac": achieved / fp64_fma if fp64_fma else None, "traffic": None,
                 "kernel": "kg_mc_kernel", "kernel_share_of_step": mc_ms / dev_ms,
                 "peak_source": "measured live: DFMA chain microbenchmark (cmoe_bench_fp64_peaks)",
-                "posterior_evals_per_sample": stats["posterior_evals"] / max(1, stats["mc_samples"]),
-                "flops_per_eval": flops_per_eval}
+                "reference_evals_per_sample": stats["posterior_evals"] / max(1, stats["mc_samples"]),
+                "point_evals_per_sample": stats["point_evals"] / max(1, stats["mc_samples"]),
+                "line_batches_per_sample": stats["line_batches"] / max(1, stats["mc_samples"]),
+                "flops_per_point_eval": flops_point, "flops_per_line_batch": flops_line,
+                "executed_flops_per_sample": executed / max(1, stats["mc_samples"])}
     out = {"metric": METRIC, "value": value, "unit": "sample-evals/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,

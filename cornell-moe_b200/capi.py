@@ -63,7 +63,8 @@ class GDParams(ctypes.Structure):
 
 class KGStats(ctypes.Structure):
     _fields_ = [("mc_samples", ctypes.c_uint64), ("posterior_evals", ctypes.c_uint64),
-                ("line_search_steps", ctypes.c_uint64)]
+                ("line_search_steps", ctypes.c_uint64), ("point_evals", ctypes.c_uint64),
+                ("line_batches", ctypes.c_uint64)]
 
 
 _lib = None
@@ -264,7 +265,8 @@ class GaussianProcess:
             res.append(g)
         if stats:
             res.append({"mc_samples": st.mc_samples, "posterior_evals": st.posterior_evals,
-                        "line_search_steps": st.line_search_steps})
+                        "line_search_steps": st.line_search_steps, "point_evals": st.point_evals,
+                        "line_batches": st.line_batches})
         return res[0] if len(res) == 1 else tuple(res)
 
 
@@ -327,7 +329,8 @@ class KGPlan:
         st = KGStats()
         _check(lib().cmoe_kg_plan_download(self.h, _d(kg), _d(g), ctypes.byref(st)))
         return kg, g, {"mc_samples": st.mc_samples, "posterior_evals": st.posterior_evals,
-                       "line_search_steps": st.line_search_steps}
+                       "line_search_steps": st.line_search_steps, "point_evals": st.point_evals,
+                       "line_batches": st.line_batches}
 
     def timings(self):
         total, mc = ctypes.c_double(), ctypes.c_double()

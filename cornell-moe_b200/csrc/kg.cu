@@ -660,7 +660,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->dRecStart.alloc(static_cast<size_t>(B) * num_mc);
     pl->dOutVal.alloc(static_cast<size_t>(B) * num_mc);
     pl->dOutX.alloc(static_cast<size_t>(B) * num_mc * DIMP);
-    pl->dStats.alloc(2);
+    pl->dStats.alloc(4);
     if (pl->want_grad) {
       pl->dR.alloc(static_cast<size_t>(B) * QP * (n + Q));
       pl->dGu.alloc(static_cast<size_t>(B) * U * DIMP);
@@ -748,7 +748,7 @@ int cmoe_kg_plan_run(cmoe_kg_plan* plan) {
     cudaStream_t s = plan->gp->stream;
     const int l0 = launches_issued();
     plan->t_total.start(s);
-    CMOE_CUDA(cudaMemsetAsync(plan->dStats.p, 0, 2 * sizeof(unsigned long long), s));
+    CMOE_CUDA(cudaMemsetAsync(plan->dStats.p, 0, 4 * sizeof(unsigned long long), s));
     size_t ev = 0;
     for (int c0 = 0; c0 < plan->nc; c0 += plan->batch, ++ev)
       plan_run_batch(*plan, c0, std::min(plan->batch, plan->nc - c0), ev);
@@ -782,13 +782,15 @@ int cmoe_kg_plan_download(cmoe_kg_plan* plan, double* kg, double* grad_kg, cmoe_
       CMOE_REQUIRE(plan->want_grad, CMOE_ERR_INVALID_VALUE, "plan was created without gradients");
       plan->dGrad.download(grad_kg, static_cast<size_t>(plan->nc) * plan->q * plan->gp->spec.dim, s);
     }
-    unsigned long long st[2] = {0, 0};
+    unsigned long long st[4] = {0, 0, 0, 0};
     if (stats) CMOE_CUDA(cudaMemcpyAsync(st, plan->dStats.p, sizeof(st), cudaMemcpyDeviceToHost, s));
     CMOE_CUDA(cudaStreamSynchronize(s));
     if (stats) {
       stats->mc_samples = static_cast<uint64_t>(plan->nc) * plan->num_mc;
       stats->posterior_evals = st[0];
       stats->line_search_steps = st[1];
+      stats->point_evals = st[2];
+      stats->line_batches = st[3];
     }
   });
 }

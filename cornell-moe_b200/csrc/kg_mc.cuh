@@ -43,7 +43,7 @@ struct KgMcParams {
   const double* alpha0;  // [max_steps]  pre_mult * (i+1)^-gamma
   double* outVal;        // [nc][num_mc]   -mu+(x*)  (the reference's best_function_value)
   double* outX;          // [nc][num_mc][DIM] scaled minimiser
-  unsigned long long* stats;  // [2]: posterior evaluations, accepted steps
+  unsigned long long* stats;  // [4]: posterior evaluations, accepted steps, point rounds, line batches (per lane)
   double lo[CMOE_MAX_DIM], hi[CMOE_MAX_DIM], inv_len[CMOE_MAX_DIM], len[CMOE_MAX_DIM];
 };
 
@@ -185,6 +185,100 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
     for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
   }
   if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) SB = S0;
+}
+
+// Batched backtracking for the SquareExponential kernel.  The reference's line search tries x + a_k g for
+// a_k = a_0 2^-k one value-evaluation at a time (gpp_optimization.hpp:750-765).  Along a line the SE kernel factorises:
+//     ln k(x + a g, X_j) = ln k(x, X_j) + a p_j - a^2 |g~|^2 / 2 ,   p_j = g~ . (X~_j - x~)
+// so with F_j = exp(a_min p_j) the kernel at every trial point is k(x, X_j) F_j^(2^m) times a j-independent factor:
+// two exps per training point give all KB trial values by repeated squaring (1 mul + 1 fma per trial) instead of one
+// full evaluation (dot + weights + exp) per trial.  S[k] = sum_j a_j k(x, X_j) exp(a_k p_j) for a_k = a_min 2^(KB-1-k'),
+// returned in trial order (S[0] <-> largest step); pmax = max_j |p_j| lets the caller reject batches whose factors
+// could leave the double range (it then falls back to one-at-a-time evaluations).
+constexpr int kLineBatch = 8;
+
+template <int DIM, int QP, bool SMEM>
+__device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const double* __restrict__ Pk,
+                                          const double* __restrict__ Xu, int N, int U, const double (&xb)[DIM],
+                                          const double (&gt)[DIM], const double (&c)[QP], double alpha_min,
+                                          double (&S)[kLineBatch], double& pmax) {
+  double nq = 0.0, xg = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    nq = fma(xb[d], xb[d], nq);
+    xg = fma(xb[d], gt[d], xg);
+  }
+  const double hq = -0.5 * nq;
+  double ga[DIM];  // a_min g~ : p_j is only ever used scaled by a_min
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) ga[d] = alpha_min * gt[d];
+  const double xga = -alpha_min * xg;
+#pragma unroll
+  for (int k = 0; k < kLineBatch; ++k) S[k] = 0.0;
+  pmax = 0.0;
+#pragma unroll 2
+  for (int j = 0; j < N; ++j) {
+    const double* xj = Xt + j * DIM;
+    const double* pk = Pk + j * (QP + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<SMEM>(xj + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    const double2 h = ld2<SMEM>(pk);  // (e_j, beta_j)
+    double dot = 0.0, pj = xga;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      dot = fma(xb[d], xv[d], dot);
+      pj = fma(ga[d], xv[d], pj);
+    }
+    double a = h.y;
+#pragma unroll
+    for (int u = 0; u < QP; u += 2) {
+      const double2 b = ld2<SMEM>(pk + 2 + u);
+      a = fma(-b.x, c[u], a);
+      a = fma(-b.y, c[u + 1], a);
+    }
+    pmax = fmax(pmax, fabs(pj));
+    const double w = a * exp_fast(dot + (h.x + hq));
+    double G = exp_fast(pj);
+#pragma unroll
+    for (int k = kLineBatch - 1; k >= 0; --k) {
+      S[k] = fma(w, G, S[k]);
+      if (k > 0) G *= G;
+    }
+  }
+  for (int u = 0; u < U; ++u) {
+    const double* xu = Xu + u * (DIM + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<SMEM>(xu + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    const double2 h = ld2<SMEM>(xu + DIM);
+    double dot = 0.0, pj = xga;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      dot = fma(xb[d], xv[d], dot);
+      pj = fma(ga[d], xv[d], pj);
+    }
+    double cu = 0.0;
+#pragma unroll
+    for (int v = 0; v < QP; ++v)
+      if (v == u) cu = c[v];
+    pmax = fmax(pmax, fabs(pj));
+    const double w = cu * exp_fast(dot + (h.x + hq));
+    double G = exp_fast(pj);
+#pragma unroll
+    for (int k = kLineBatch - 1; k >= 0; --k) {
+      S[k] = fma(w, G, S[k]);
+      if (k > 0) G *= G;
+    }
+  }
 }
 
 // Kernel pieces for the general path: kv = k(x, X_j) (value row), kb = factor of the first-derivative rows,
@@ -329,7 +423,7 @@ __device__ __forceinline__ double limit_step(double step, double x, double lo, d
   return step;
 }
 
-enum : int { ST_FETCH = 0, ST_INIT = 1, ST_TRIAL = 2, ST_LIMIT = 3, ST_DONE = 4 };
+enum : int { ST_FETCH = 0, ST_INIT = 1, ST_TRIAL = 2, ST_LIMIT = 3, ST_DONE = 4, ST_LINE = 5 };
 
 #ifndef CMOE_MC_THREADS
 #define CMOE_MC_THREADS 128
@@ -341,10 +435,17 @@ constexpr int kMcThreads = CMOE_MC_THREADS;
 
 // The per-lane line-search state machine.  Live across evaluations: c, the base point xb with f and grad f there,
 // the step size and a few counters; the start point of the current restart run is parked in the sample's output slot.
+//
+// A round of the warp is either a POINT round (mu+ and its gradient at one query point per lane: INIT / TRIAL / LIMIT
+// lanes) or, for the SquareExponential fast path, a LINE round (all backtracking trials of a step at once, eval_line).
+// Which one runs is a warp vote; lanes waiting for the other kind idle for that round and are in phase again after it
+// (a sample alternates LINE, POINT, LINE, ... so the vote keeps a warp in lock-step once it is).
 template <int KERNEL, int DIM, int QP, bool SMEM, bool GEN>
 __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* __restrict__ Xt,
                                            const double* __restrict__ Pk, const double* __restrict__ Xu, int cand,
                                            int s_begin, int s_end, int* next_sample) {
+  constexpr bool LINE = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) && !GEN;
+  constexpr int ST_SEARCH = LINE ? ST_LINE : ST_TRIAL;  // how a step's backtracking starts
   const int N = prm.N, U = prm.U;
   const double* A = prm.A + static_cast<size_t>(cand) * prm.M * DIM;
   const double* recC = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
@@ -358,7 +459,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
   double cl[GEN ? QP : 1];  // general path: run-time indexable copy of c for the union rows (lives in local memory)
   double fb = 0.0, alpha_n = 0.0, gnorm = 0.0;
   int step_i = 0, restart_i = 0, search = 0;
-  unsigned n_evals = 0, n_steps = 0;
+  unsigned n_evals = 0, n_steps = 0, n_point = 0, n_line = 0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) xb[d] = gb[d] = 0.0;
 #pragma unroll
@@ -397,107 +498,163 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
     }
     if (__all_sync(0xffffffffu, state == ST_DONE)) break;
 
-    // ---- query point of this lane: base (INIT), base + alpha*grad (TRIAL), base + limited step (LIMIT) ----
-    double xq[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      double st = 0.0;
-      if (state == ST_TRIAL || state == ST_LIMIT) st = alpha_n * gb[d];
-      if (state == ST_LIMIT) st = (d < prm.ps) ? limit_step(st, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
-      xq[d] = (xb[d] + st) * prm.inv_len[d];
+    bool line_round = false;
+    if (LINE) {
+      const unsigned wl = __ballot_sync(0xffffffffu, state == ST_LINE);
+      const unsigned wp = __ballot_sync(0xffffffffu, state == ST_INIT || state == ST_TRIAL || state == ST_LIMIT);
+      line_round = __popc(wl) > __popc(wp);
     }
+    bool finish_run = false;
 
-    // ---- the expensive, warp-uniform part ----
-    double S0, SB, s[DIM];
-    double em[kMaxG];
-    if (GEN) {
-      eval_posterior_gen<KERNEL, DIM, QP>(prm, Xt, Pk, Xu, xq, c, cl, S0, SB, s, em);
-      // kb a~_jm lands on coordinate derivs[m]: fold it into s so that the common gradient formula below holds
-      // (grad_d = inv_len_d (s_d - x~_d SB)), using compile-time register indices only
+    if (LINE && line_round) {
+      // ---- all backtracking trials of this step in one pass (warp-uniform) ----
+      double xt[DIM], gt[DIM], S[kLineBatch], pmax;
+      double gg = 0.0;
 #pragma unroll
-      for (int m = 0; m < kMaxG; ++m)
-        if (m < prm.g) {
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            if (d == prm.derivs[m]) s[d] += em[m];
-        }
-    } else {
-      eval_posterior<KERNEL, DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
-    }
-    if (state != ST_DONE && state != ST_FETCH) n_evals += 1;
-    const double fq = -(prm.mean + S0);
-
-    // ---- per-lane transitions (cheap) ----
-    bool finish_run = false, accept = false;
-    if (state == ST_INIT) {
-      fb = fq;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) gb[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
-      if (prm.max_steps <= 0) {
-        finish_run = true;
-      } else {
-        step_i = -1;  // becomes 0 in the common "start a step" block below
-        accept = true;
+      for (int d = 0; d < DIM; ++d) {
+        xt[d] = xb[d] * prm.inv_len[d];
+        gt[d] = gb[d] * prm.inv_len[d];
+        gg = fma(gt[d], gt[d], gg);
       }
-    } else if (state == ST_TRIAL) {
-      // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
-      const bool ok = (fq - fb) > 0.5 * alpha_n * gnorm;
-      if (!ok) {
-        alpha_n *= 0.5;
-        search += 1;
-        if (search >= 30) finish_run = true;  // exhausted: reject and stop this run (:778-781)
-      } else {
-        // limit the accepted step to the domain; if unchanged, this evaluation IS the final evaluation of the step
-        bool same = true;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          const double raw = alpha_n * gb[d];
-          const double lim = (d < prm.ps) ? limit_step(raw, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
-          same = same && (lim == raw);
-        }
-        if (same) {
-          if (fq <= fb) {
-            finish_run = true;
-          } else {
-            accept = true;
-          }
+      constexpr double kTop = static_cast<double>(1 << (kLineBatch - 1));
+      eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax);
+      if (state == ST_LINE) {
+        n_line += 1;
+        if (!(pmax * kTop <= 650.0)) {
+          state = ST_TRIAL;  // factors could leave the double range: this step backtracks one evaluation at a time
         } else {
-          state = ST_LIMIT;  // one more evaluation at the limited point
-        }
-      }
-    } else if (state == ST_LIMIT) {
-      if (fq <= fb) {
-        finish_run = true;  // no increase: restore the base point and stop (:778-781)
-      } else {
-        accept = true;
-      }
-    }
-    if (accept) {
-      // the evaluated query point becomes the base point; start the next step (or finish the run)
-      double ns = 0.0;
-      if (state != ST_INIT) {
+          int kacc = -1;
+          double ak = alpha_n, a_acc = alpha_n;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          double st = alpha_n * gb[d];
-          if (state == ST_LIMIT) st = (d < prm.ps) ? limit_step(st, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
-          xb[d] += st;
-          ns = fma(st, st, ns);
+          for (int k = 0; k < kLineBatch; ++k) {
+            const double fq = -(prm.mean + exp_fast(-0.5 * ak * ak * gg) * S[k]);
+            // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
+            const bool ok = (search + k < 30) && ((fq - fb) > 0.5 * ak * gnorm);
+            if (kacc < 0 && ok) {
+              kacc = k;
+              a_acc = ak;
+            }
+            ak *= 0.5;
+          }
+          if (kacc >= 0) {
+            n_evals += kacc + 1;
+            search += kacc;
+            alpha_n = a_acc;
+            state = ST_LIMIT;  // value and gradient at the domain-limited point decide the step (:767-781)
+          } else {
+            n_evals += min(kLineBatch, 30 - search);
+            search += kLineBatch;
+            alpha_n *= 1.0 / (2.0 * kTop);
+            if (search >= 30) finish_run = true;  // exhausted: reject and stop this run (:778-781)
+          }
         }
+      }
+    } else {
+      // ---- query point of this lane: base (INIT), base + alpha*grad (TRIAL), base + limited step (LIMIT) ----
+      double xq[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        double st = 0.0;
+        if (state == ST_TRIAL || state == ST_LIMIT) st = alpha_n * gb[d];
+        if (state == ST_LIMIT) st = (d < prm.ps) ? limit_step(st, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+        xq[d] = (xb[d] + st) * prm.inv_len[d];
+      }
+
+      // ---- the expensive, warp-uniform part ----
+      double S0, SB, s[DIM];
+      double em[kMaxG];
+      if (GEN) {
+        eval_posterior_gen<KERNEL, DIM, QP>(prm, Xt, Pk, Xu, xq, c, cl, S0, SB, s, em);
+        // kb a~_jm lands on coordinate derivs[m]: fold it into s so that the common gradient formula below holds
+        // (grad_d = inv_len_d (s_d - x~_d SB)), using compile-time register indices only
+#pragma unroll
+        for (int m = 0; m < kMaxG; ++m)
+          if (m < prm.g) {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+              if (d == prm.derivs[m]) s[d] += em[m];
+          }
+      } else {
+        eval_posterior<KERNEL, DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xq, c, S0, SB, s);
+      }
+      if (state == ST_INIT || state == ST_TRIAL || state == ST_LIMIT) {
+        n_evals += 1;
+        n_point += 1;
+      }
+      const double fq = -(prm.mean + S0);
+
+      // ---- per-lane transitions (cheap) ----
+      bool accept = false;
+      if (state == ST_INIT) {
+        fb = fq;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) gb[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
-        fb = fq;
-        n_steps += 1;
-      }
-      step_i += 1;
-      if (state != ST_INIT && (sqrt(ns) < prm.step_tol || step_i >= prm.max_steps)) {
-        finish_run = true;
-      } else {
-        alpha_n = prm.alpha0[step_i];
-        search = 0;
-        gnorm = 0.0;
+        if (prm.max_steps <= 0) {
+          finish_run = true;
+        } else {
+          step_i = -1;  // becomes 0 in the common "start a step" block below
+          accept = true;
+        }
+      } else if (state == ST_TRIAL) {
+        // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
+        const bool ok = (fq - fb) > 0.5 * alpha_n * gnorm;
+        if (!ok) {
+          alpha_n *= 0.5;
+          search += 1;
+          if (search >= 30) finish_run = true;  // exhausted: reject and stop this run (:778-781)
+        } else {
+          // limit the accepted step to the domain; if unchanged, this evaluation IS the final evaluation of the step
+          bool same = true;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
-        state = ST_TRIAL;
+          for (int d = 0; d < DIM; ++d) {
+            const double raw = alpha_n * gb[d];
+            const double lim = (d < prm.ps) ? limit_step(raw, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+            same = same && (lim == raw);
+          }
+          if (same) {
+            if (fq <= fb) {
+              finish_run = true;
+            } else {
+              accept = true;
+            }
+          } else {
+            state = ST_LIMIT;  // one more evaluation at the limited point
+          }
+        }
+      } else if (state == ST_LIMIT) {
+        if (fq <= fb) {
+          finish_run = true;  // no increase: restore the base point and stop (:778-781)
+        } else {
+          accept = true;
+        }
+      }
+      if (accept) {
+        // the evaluated query point becomes the base point; start the next step (or finish the run)
+        double ns = 0.0;
+        if (state != ST_INIT) {
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            double st = alpha_n * gb[d];
+            if (state == ST_LIMIT) st = (d < prm.ps) ? limit_step(st, xb[d], prm.lo[d], prm.hi[d], prm.mrc) : 0.0;
+            xb[d] += st;
+            ns = fma(st, st, ns);
+          }
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gb[d] = (d < prm.ps) ? -prm.inv_len[d] * (s[d] - xq[d] * SB) : 0.0;
+          fb = fq;
+          n_steps += 1;
+        }
+        step_i += 1;
+        if (state != ST_INIT && (sqrt(ns) < prm.step_tol || step_i >= prm.max_steps)) {
+          finish_run = true;
+        } else {
+          alpha_n = prm.alpha0[step_i];
+          search = 0;
+          gnorm = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
+          state = ST_SEARCH;
+        }
       }
     }
     if (finish_run) {
@@ -524,16 +681,20 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         gnorm = 0.0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) gnorm = fma(gb[d], gb[d], gnorm);
-        state = ST_TRIAL;
+        state = ST_SEARCH;
       }
     }
   }
   // integer counters: atomics keep the totals deterministic
   n_evals = __reduce_add_sync(0xffffffffu, n_evals);
   n_steps = __reduce_add_sync(0xffffffffu, n_steps);
+  n_point = __reduce_add_sync(0xffffffffu, n_point);
+  n_line = __reduce_add_sync(0xffffffffu, n_line);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(prm.stats + 0, static_cast<unsigned long long>(n_evals));
     atomicAdd(prm.stats + 1, static_cast<unsigned long long>(n_steps));
+    atomicAdd(prm.stats + 2, static_cast<unsigned long long>(n_point));
+    atomicAdd(prm.stats + 3, static_cast<unsigned long long>(n_line));
   }
 }
 

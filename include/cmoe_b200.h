@@ -60,8 +60,12 @@ typedef struct cmoe_gd_params {
 /* Work counters reported by the fused q-KG kernel (it counts what it actually executed). */
 typedef struct cmoe_kg_stats {
   uint64_t mc_samples;         /* candidates * num_mc */
-  uint64_t posterior_evals;    /* posterior-mean (+gradient) evaluations inside the per-sample line search */
+  uint64_t posterior_evals;    /* posterior-mean evaluations the reference's line search would have made for the
+                                  same trajectory (trial points + domain-limited points + start points) */
   uint64_t line_search_steps;  /* accepted inner gradient steps */
+  uint64_t point_evals;        /* executed: value+gradient evaluations at one query point */
+  uint64_t line_batches;       /* executed: batched backtracking passes (SquareExponential fast path; all trial step
+                                  sizes of one step share one pass over the training points) */
 } cmoe_kg_stats;
 
 /* Human-readable description of the last error on the calling thread. */

@@ -711,6 +711,21 @@ static void pm_grad(const kg_ctx* c, pm_state* s, double* out) {
   for (int i = 0; i < c->aug.dim - c->nf; ++i) out[i] = -s->g[i];
 }
 
+/* Line-search statistics for sizing the device kernel (test infrastructure only):
+ * [0..30] histogram of backtracking counts per step, [32..47] histogram of steps taken per descent,
+ * [48] breaks on no-improvement, [49] breaks on 30 halvings, [50] breaks on the step tolerance, [51] ran all steps. */
+static long g_ls_stats[64];
+void oracle_debug_line_search_stats(long* out, int reset) {
+  for (int i = 0; i < 64; ++i) {
+    out[i] = g_ls_stats[i];
+    if (reset) g_ls_stats[i] = 0;
+  }
+}
+static void ls_count(int slot) {
+#pragma omp atomic
+  g_ls_stats[slot] += 1;
+}
+
 static void line_search_gd(const kg_ctx* c, const double* gd, const double* bounds, pm_state* s) {
   const int ps = c->aug.dim - c->nf;
   const int max_steps = (int)gd[1];
@@ -742,15 +757,26 @@ static void line_search_gd(const kg_ctx* c, const double* gd, const double* boun
     for (int j = 0; j < ps; ++j) trial[j] = next[j] + step[j];
     memcpy(s->x, trial, (size_t)ps * sizeof(double));
     obj = pm_obj(c, s);
+    ls_count(search);
     if (obj <= f0 || search == 30) {
       memcpy(s->x, next, (size_t)ps * sizeof(double));
+      ls_count(search == 30 ? 49 : 48);
+      ls_count(32 + (i < 15 ? i : 15));
       break;
     }
     for (int j = 0; j < ps; ++j) next[j] += step[j];
     memcpy(s->x, next, (size_t)ps * sizeof(double));
     double ns = 0.0;
     for (int j = 0; j < ps; ++j) ns += step[j] * step[j];
-    if (sqrt(ns) < step_tol) break;
+    if (sqrt(ns) < step_tol) {
+      ls_count(50);
+      ls_count(32 + (i + 1 < 15 ? i + 1 : 15));
+      break;
+    }
+    if (i == max_steps - 1) {
+      ls_count(51);
+      ls_count(32 + (i + 1 < 15 ? i + 1 : 15));
+    }
   }
   free(grad); free(step); free(trial); free(next);
 }

@@ -188,3 +188,37 @@ def test_kg_other_dimensions(capi, dim, q):
         v, g = ref.kg(cands[c], None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(dim), disc, grad=True)
         np.testing.assert_allclose(kg[c], v, rtol=1e-7, atol=1e-10)
         np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("case", ["second_batch", "out_of_range_factors", "exhausted_search"])
+def test_kg_line_batch_edge_paths(capi, case):
+    """The SquareExponential fast path evaluates all backtracking trials of a step in one pass (8 step sizes per batch).
+    Edge paths: more than 8 halvings (second batch), exponent factors that would leave the double range (falls back to
+    one evaluation per trial), and 30 halvings without acceptance (the reference stops the run)."""
+    if case == "second_batch":
+        prob = make_problem(16, 3, seed=9, noise=0.1)
+        gd = [1, 5, 2, 3, 0.0, 32.0, 0.5, 1e-10]          # a_0 = 32: 8-9 halvings before the Armijo test holds
+    elif case == "out_of_range_factors":
+        prob = make_problem(16, 3, seed=9, noise=0.1)
+        gd = [1, 5, 2, 3, 0.0, 4096.0, 0.5, 1e-10]        # a_0 |p_j| >> 650: exp(a_0 p_j) is not representable
+    else:
+        prob = make_problem(16, 3, seed=9, noise=0.1)
+        gd = [1, 3, 2, 3, 0.0, 1e12, 0.5, 1e-10]          # a_0 2^-29 is still far too large: search hits 30
+    gp, ref = _pair(capi, 0, prob)
+    rng = np.random.default_rng(41)
+    q, mc = 2, 32
+    cands = rng.uniform(size=(2, q, 3))
+    disc = rng.uniform(size=(5, 3))
+    table = rng.standard_normal((mc // 2) * q)
+    best = float(ref.mean_additional(disc).min())
+    kg, grad, st = gp.kg(cands, None, mc, best, gd, unit_bounds(3), disc, table=table, grad=True, stats=True)
+    print(case, st)
+    if case == "second_batch":
+        assert st["line_batches"] >= 1.5 * st["line_search_steps"]  # two batches for most steps ...
+        assert st["point_evals"] <= st["line_search_steps"] + 2 * (2 * mc) * 2  # ... and no one-at-a-time trials
+    if case == "out_of_range_factors":
+        assert st["point_evals"] > 5 * st["line_search_steps"]  # the trials were evaluated one at a time
+    for c in range(2):
+        v, g, bp = ref.kg(cands[c], None, mc, best, table, gd, unit_bounds(3), disc, grad=True, want_best_points=True)
+        np.testing.assert_allclose(kg[c], v, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
