@@ -277,6 +277,13 @@ def fp64_peaks(device=0):
     return float(t[0]), float(t[1])
 
 
+def fp64_mixed(device=0):
+    """cmoe_bench_fp64_mixed: total TFLOP/s with DFMA and DMMA interleaved in every warp."""
+    out = np.zeros(1)
+    _check(lib().cmoe_bench_fp64_mixed(int(device), _d(out)))
+    return float(out[0])
+
+
 class KGPlan:
     """Device-resident q-KG evaluation plan (cmoe_kg_plan_*): create -> upload -> run -> sync -> download."""
 

@@ -5,9 +5,9 @@
 //   BuildMixCovarianceMatrix                 gpp_math.cpp:309-335
 //   SquareExponential / MaternNu2p5 ::Covariance   gpp_covariance.cpp:121-164, 339-387
 //
-// Tiling: one CTA per 128x32 block of point pairs in the lower-triangular tile grid; the two point slabs are staged
-// through shared memory once and every thread produces 4 consecutive rows of a column, so each warp store instruction
-// writes 1 KB contiguous (coalesced 32 B per lane).  Only lower-triangular tiles are visited: the algorithmic traffic
+// Tiling: one CTA per 128x64 block of point pairs in the lower-triangular tile grid; the two point slabs are staged
+// through shared memory once and every thread produces a 4x4 register block (4 consecutive rows of 4 columns), so a
+// lane's stores are 32 contiguous bytes and a warp store covers 8 lanes x 32 B = 256 contiguous bytes per column.  Only lower-triangular tiles are visited: the algorithmic traffic
 // is 4*n*(n+1) bytes written + 8*N*dim read.
 #include "device_math.cuh"
 #include "internal.cuh"
@@ -16,20 +16,70 @@ namespace cmoe {
 
 namespace {
 
-constexpr int TR = 128;  // point rows per tile
-constexpr int TC = 32;   // point cols per sub-tile
-constexpr int TCW = 64;  // point cols per CTA tile (TCW / TC sub-tiles share the staged row slab)
+constexpr int TR = 128;  // point rows per CTA tile
+constexpr int TCW = 64;  // point cols per CTA tile
+#ifndef CMOE_COV_ROWS
+#define CMOE_COV_ROWS 4
+#endif
+#ifndef CMOE_COV_EXP_TABLE
+#define CMOE_COV_EXP_TABLE 1
+#endif
+#ifndef CMOE_COV_UNROLL
+#define CMOE_COV_UNROLL 2
+#endif
+constexpr int kCovUnroll = CMOE_COV_UNROLL;
+constexpr int RB = CMOE_COV_ROWS;      // rows per thread (4 or 8), 4 columns per thread
+constexpr int WR = TR / (8 * RB);      // warps along the rows (a warp covers 8*RB rows x 16 cols)
+constexpr int WC = 8 / WR;             // warps along the columns
+constexpr int TC = WC * 16;            // columns per pass over the staged slabs
+
+#if CMOE_COV_EXP_TABLE
+// 2^(i/64), the table of the reduced-range exp (see exp_tab in kg_mc.cuh: 10 FP64-pipe instructions instead of 15)
+__device__ const double kCovExp2Table[64] = {
+#include "exp2_table64.inc"
+};
+__device__ __forceinline__ double exp_tab_cov(double t, const double* __restrict__ tab) {
+  t = exp_guard_in(t);
+  const double kShift = 6755399441055744.0;
+  double nf = fma(t, 64.0 * 1.4426950408889634, kShift);
+  const int n = __double2loint(nf);
+  nf -= kShift;
+  double r = fma(nf, -6.93147180369123816490e-01 / 64.0, t);
+  r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
+  double p = 8.3333333333333332e-03;
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= tab[n & 63];
+  const int k = max(n >> 6, -1000);
+  return exp_guard_out(t, __double2hiint(p) + (k << 20), __double2loint(p));
+}
+#endif
 
 // g == 0 fast path: K[i + j*n] for i >= j (tile granularity), noise[0] on the diagonal.
-// Works on length-scaled coordinates Xs = X / l (so r^2 is a plain sum of squared differences: 2 FP64 ops per
-// dimension, no division) and the branch-free exp; both keep the entry within ~1 ulp of the reference's formula.
-__global__ void __launch_bounds__(256, 3) cov_build_g0_kernel(const __grid_constant__ KernelSpec spec,
-                                                           const double* __restrict__ Xs, int N,
-                                                           const double* __restrict__ noise, double* __restrict__ K) {
+// Works on length-scaled coordinates Xs = X / l with the expanded distance
+//     -r^2/2 = x_i . x_j - |x_i|^2/2 - |x_j|^2/2
+// (one FMA per dimension and entry; the absolute error of the expanded form is ~1e-16 (|x_i|^2 + |x_j|^2), a relative
+// perturbation of k of that size — far below the noise term).  The half-norms are accumulated in the same FMA order as
+// the dot product and scaled by the exact factor -1/2, so for coincident points the three terms cancel EXACTLY and
+// k = alpha exp(0) = alpha bit-for-bit, as in the reference: duplicate points with zero noise must make the Cholesky
+// fail at the same leading minor (tests/test_gpu_gp.py::test_gp_singular_reports_leading_minor).
+template <int KERNEL>
+__global__ void __launch_bounds__(256, RB == 4 ? 3 : 2)
+    cov_build_g0_kernel(const __grid_constant__ KernelSpec spec, const double* __restrict__ Xs, int N,
+                        const double* __restrict__ noise, double* __restrict__ K) {
   extern __shared__ double sm[];
   const int dim = spec.dim;
-  double* Xr = sm;               // [dim][TR]   coordinate-major: a lane's 4 rows are 32 contiguous bytes
-  double* Xc = sm + TR * dim;    // [dim][TCW]  (a warp shares its 4 columns: broadcast reads)
+  double* Xr = sm;                 // [dim][TR]   coordinate-major: a lane's RB rows are contiguous
+  double* Xc = sm + TR * dim;      // [dim][TCW]  (a warp shares its columns: broadcast reads)
+  double* Hr = Xc + TCW * dim;     // [TR]   -|x_i|^2/2
+  double* Hc = Hr + TR;            // [TCW]  -|x_j|^2/2
+#if CMOE_COV_EXP_TABLE
+  double* tab = Hc + TCW;          // [64]
+  if (threadIdx.x < 64) tab[threadIdx.x] = kCovExp2Table[threadIdx.x];
+#endif
   // linear block index -> (tile row tr, tile col tc) of the lower-triangular tile grid: tc*TCW <= tr*TR + TR - 1
   constexpr int kColsPerRow = TR / TCW;  // col tiles that fit under one row tile's diagonal extent
   int tr = static_cast<int>((sqrt(8.0 * (blockIdx.x / kColsPerRow) + 1.0) - 1.0) * 0.5);
@@ -52,79 +102,88 @@ __global__ void __launch_bounds__(256, 3) cov_build_g0_kernel(const __grid_const
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
-  for (int sub = 0; sub < TCW / TC; ++sub) {
-  const int col0 = colbase + sub * TC;
-  if (col0 > row0 + TR - 1 || col0 >= N) break;  // sub-tile entirely above the diagonal
-  // 2-D register blocking inside a warp: lane = (lr, lc) owns rows roff..roff+3 and cols coff..coff+3 of a 32x16 warp
-  // tile, so an LDS.128 of the row slab touches 8 distinct 16-byte chunks (1 wavefront) instead of 32 (4 wavefronts)
-  // and the kernel is FP64- rather than shared-memory-bound.  8 warps = 4 (rows) x 2 (cols) cover 128 x 32.
+  if (threadIdx.x < TR + TCW) {
+    const bool is_row = threadIdx.x < TR;
+    const double* src = is_row ? Xr + threadIdx.x : Xc + (threadIdx.x - TR);
+    const int stride = is_row ? TR : TCW;
+    double h = 0.0;
+    for (int k = 0; k < dim; ++k) h = fma(src[k * stride], src[k * stride], h);
+    h *= -0.5;
+    (is_row ? Hr : Hc)[is_row ? threadIdx.x : threadIdx.x - TR] = h;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int roff4 = ((warp & 3) * 32 + (lane & 7) * 4) / 4;   // in units of 4 rows
-  const int coff4 = ((warp >> 2) * 16 + (lane >> 3) * 4) / 4; // in units of 4 cols
-  const int rg = roff4, cg = coff4;
+  const int rloc = (warp % WR) * (8 * RB) + (lane & 7) * RB;  // first of this lane's RB rows inside the tile
   const double nz = noise[0];
-  const bool se = spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL;
-  // -r^2/2 = x_i.x_j - |x_i|^2/2 - |x_j|^2/2 : one FMA per dimension and entry (the absolute error of the expanded
-  // form is ~1e-16 * (|x_i|^2 + |x_j|^2), i.e. a relative perturbation of k of that size — far below the noise term)
-  double t[4][4], hc[4] = {0.0, 0.0, 0.0, 0.0};
-  double hr[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int k = 0; k < dim; ++k) {
-    const double2 ra = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4);
-    const double2 rb = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4 + 2);
-    hr[0] = fma(-0.5 * ra.x, ra.x, hr[0]);
-    hr[1] = fma(-0.5 * ra.y, ra.y, hr[1]);
-    hr[2] = fma(-0.5 * rb.x, rb.x, hr[2]);
-    hr[3] = fma(-0.5 * rb.y, rb.y, hr[3]);
-  }
+  double hr[RB];
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr)
+  for (int rr = 0; rr < RB; ++rr) hr[rr] = Hr[rloc + rr];
+  for (int sub = 0; sub < TCW / TC; ++sub) {
+    const int cloc = sub * TC + (warp / WR) * 16 + (lane >> 3) * 4;  // first of this lane's 4 cols inside the tile
+    const int col0 = colbase + sub * TC;
+    if (col0 > row0 + TR - 1 || col0 >= N) break;  // pass entirely above the diagonal
+    // 2-D register blocking inside a warp: lane = (lr, lc) owns RB rows x 4 cols of an (8 RB) x 16 warp tile, so an
+    // LDS.128 of the row slab touches 8 distinct 16-byte chunks (1 wavefront) and the column slab is a 4-way broadcast
+    double t[RB][4];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) t[rr][cc] = 0.0;
-#pragma unroll 2
-  for (int k = 0; k < dim; ++k) {
-    const double2 ra = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4);
-    const double2 rb = *reinterpret_cast<const double2*>(Xr + k * TR + rg * 4 + 2);
-    const double2 ca = *reinterpret_cast<const double2*>(Xc + k * TCW + sub * TC + cg * 4);
-    const double2 cb = *reinterpret_cast<const double2*>(Xc + k * TCW + sub * TC + cg * 4 + 2);
-    const double xr[4] = {ra.x, ra.y, rb.x, rb.y};
-    const double xc[4] = {ca.x, ca.y, cb.x, cb.y};
+    for (int rr = 0; rr < RB; ++rr)
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      hc[rr] = fma(-0.5 * xc[rr], xc[rr], hc[rr]);
+      for (int cc = 0; cc < 4; ++cc) t[rr][cc] = 0.0;
+#pragma unroll kCovUnroll
+    for (int k = 0; k < dim; ++k) {
+      double xr[RB], xc[4];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) t[rr][cc] = fma(xr[rr], xc[cc], t[rr][cc]);
-    }
-  }
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int gc = col0 + cg * 4 + cc;
-    if (gc >= N) continue;
-    double v[4];
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const double e = t[rr][cc] + (hr[rr] + hc[cc]);  // = -r^2/2
-      if (se) {
-        v[rr] = spec.alpha * exp_fast(e);
-      } else {
-        const double r2 = fmax(0.0, -2.0 * e);
-        const double arg = kSqrt5 * sqrt(r2);
-        v[rr] = spec.alpha * exp_fast(-arg) * (1.0 + arg + 5.0 / 3.0 * r2);
+      for (int rr = 0; rr < RB; rr += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(Xr + k * TR + rloc + rr);
+        xr[rr] = v.x;
+        xr[rr + 1] = v.y;
       }
-      if (row0 + rg * 4 + rr == gc) v[rr] = spec.alpha + nz;  // exact diagonal: k(x, x) = alpha
-    }
-    const int gr = row0 + rg * 4;
-    double* dst = K + static_cast<size_t>(gc) * N + gr;
-    if (gr + 3 < N && (N % 2 == 0)) {
-      // 16-byte aligned when N is even (gr is a multiple of 4)
-      reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
-      reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
-    } else {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr)
-        if (gr + rr < N) dst[rr] = v[rr];
+      for (int cc = 0; cc < 4; cc += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(Xc + k * TCW + cloc + cc);
+        xc[cc] = v.x;
+        xc[cc + 1] = v.y;
+      }
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) t[rr][cc] = fma(xr[rr], xc[cc], t[rr][cc]);
     }
-  }
-  }  // sub-tiles
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int gc = colbase + cloc + cc;
+      if (gc >= N) continue;
+      const double hcc = Hc[cloc + cc];
+      double v[RB];
+#pragma unroll
+      for (int rr = 0; rr < RB; ++rr) {
+        const double e = t[rr][cc] + (hr[rr] + hcc);  // = -r^2/2, exactly 0 for coincident points
+        if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
+#if CMOE_COV_EXP_TABLE
+          v[rr] = spec.alpha * exp_tab_cov(e, tab);
+#else
+          v[rr] = spec.alpha * exp_fast(e);
+#endif
+        } else {
+          const double r2 = fmax(0.0, -2.0 * e);
+          const double arg = kSqrt5 * sqrt(r2);
+          v[rr] = spec.alpha * exp_fast(-arg) * (1.0 + arg + 5.0 / 3.0 * r2);
+        }
+        if (row0 + rloc + rr == gc) v[rr] = spec.alpha + nz;  // exact diagonal: k(x, x) = alpha
+      }
+      const int gr = row0 + rloc;
+      double* dst = K + static_cast<size_t>(gc) * N + gr;
+      if (gr + RB - 1 < N && (N % 2 == 0)) {
+        // 16-byte aligned when N is even (gr is a multiple of 4)
+#pragma unroll
+        for (int rr = 0; rr < RB; rr += 2) reinterpret_cast<double2*>(dst)[rr / 2] = make_double2(v[rr], v[rr + 1]);
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr)
+          if (gr + rr < N) dst[rr] = v[rr];
+      }
+    }
+  }  // passes
 }
 
 // generic path (derivative observations): one thread per point pair, writes the (1+g)x(1+g) block
@@ -194,8 +253,12 @@ void build_covariance(const KernelSpec& spec, const double* X, const double* Xs,
   if (spec.g == 0) {
     const int trows = (N + TR - 1) / TR;
     dim3 grid(trows * (trows + 1) / 2 * (TR / TCW));
-    const size_t smem = static_cast<size_t>(TR + TCW) * spec.dim * sizeof(double);
-    cov_build_g0_kernel<<<grid, 256, smem, s>>>(spec, Xs, N, noise, K);
+    const size_t smem = (static_cast<size_t>(TR + TCW) * (spec.dim + 1) + 64) * sizeof(double);
+    if (spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
+      cov_build_g0_kernel<CMOE_KERNEL_SQUARE_EXPONENTIAL><<<grid, 256, smem, s>>>(spec, Xs, N, noise, K);
+    } else {
+      cov_build_g0_kernel<CMOE_KERNEL_MATERN_NU_2P5><<<grid, 256, smem, s>>>(spec, Xs, N, noise, K);
+    }
   } else {
     dim3 grid((N + 31) / 32, (N + 7) / 8);
     cov_build_generic_kernel<<<grid, 256, 0, s>>>(spec, X, N, noise, K);

@@ -432,13 +432,15 @@ struct cmoe_kg_plan {
   int DIMP = 0, QP = 0, batch = 0, nc = 0;
   int Q = 0, stride = 0;  // rows of the union block U*(1+g); doubles per training point in the operand pack
   bool use_smem = true;
+  bool smem_fits = true;      // the operand pack fits in shared memory
+  double rmax_static = 0.0;   // max scaled norm of training / pending / discrete points (see kFastPathRadius)
   int chunk = 0;
   // static device data
   DevBuf<double> dXt, dD, dKD, dMuD, dAlpha0, dTable, dXp, dCand;
   KgMcParams mcp{};
   // per-batch device scratch
   PosteriorBatch pb;
-  DevBuf<double> dPk, dXu, dA, dAfull, dKAu, dW, dMuA, dBestPost, dRecC, dOutVal, dOutX, dR, dGu, dGkB, dTp, dG1;
+  DevBuf<double> dPk, dXu, dA, dAfull, dKAu, dW, dMuA, dBestPost, dRecC, dOutVal, dOutX, dOutH, dR, dGu, dGkB, dTp, dG1;
   DevBuf<int> dWinner, dRecStart;
   DevBuf<unsigned long long> dStats;
   // results
@@ -504,6 +506,7 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   prm.recStart = pl.dRecStart.p;
   prm.outVal = pl.dOutVal.p;
   prm.outX = pl.dOutX.p;
+  prm.outH = pl.dOutH.p;
   prm.stats = pl.dStats.p;
   const int chunks = (mc + pl.chunk - 1) / pl.chunk;
   const size_t smem_mc = (!gen && pl.use_smem) ? pl.entry->smem_bytes(N, U) : 0;
@@ -529,6 +532,7 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
     ap.Xu = pl.dXu.p;
     ap.recC = pl.dRecC.p;
     ap.outX = pl.dOutX.p;
+    ap.outH = pl.dOutH.p;
     ap.R = pl.dR.p;
     ap.Gu = pl.dGu.p;
     ap.GkB = pl.dGkB.p;
@@ -633,7 +637,29 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem_need = pl->entry->smem_bytes(N, U);
-    pl->use_smem = spec.g == 0 && smem_need <= 200 * 1024;
+    pl->smem_fits = spec.g == 0 && smem_need <= 200 * 1024;
+    {
+      // The shared-memory fast path evaluates exp without per-call range guards; that is valid while every scaled
+      // coordinate vector it can meet lies within kFastPathRadius length scales of the origin (kg_mc.cuh).
+      auto upd = [&](const double* pts, size_t count, int stride, int nd) {
+        for (size_t i = 0; i < count; ++i) {
+          double r2 = 0.0;
+          for (int d = 0; d < nd; ++d) {
+            const double v = pts[i * stride + d] * spec.inv_len[d];
+            r2 += v * v;
+          }
+          pl->rmax_static = std::max(pl->rmax_static, std::sqrt(r2));
+        }
+      };
+      upd(gp->hX.data(), N, dim, dim);
+      upd(hD.data(), num_pts, dim, dim);
+      if (p) upd(hXp.data(), p, dim, dim);
+      for (int d = 0; d < ps; ++d) {  // the inner optimiser keeps its iterates inside the inner domain
+        const double c = std::max(std::fabs(inner_bounds[2 * d]), std::fabs(inner_bounds[2 * d + 1])) * spec.inv_len[d];
+        pl->rmax_static = std::max(pl->rmax_static, c * std::sqrt(static_cast<double>(dim)));
+      }
+    }
+    pl->use_smem = pl->smem_fits && pl->rmax_static < kFastPathRadius;
     // candidates per batch bounded by ~3 GiB of per-sample records
     const size_t per_cand = static_cast<size_t>(num_mc) * (QP + DIMP + 2) * sizeof(double) +
                             static_cast<size_t>(n) * Q * 4 * sizeof(double);
@@ -660,6 +686,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->dRecStart.alloc(static_cast<size_t>(B) * num_mc);
     pl->dOutVal.alloc(static_cast<size_t>(B) * num_mc);
     pl->dOutX.alloc(static_cast<size_t>(B) * num_mc * DIMP);
+    pl->dOutH.alloc(static_cast<size_t>(B) * num_mc);
     pl->dStats.alloc(4);
     if (pl->want_grad) {
       pl->dR.alloc(static_cast<size_t>(B) * QP * (n + Q));
@@ -736,6 +763,21 @@ int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_ca
                  "num_candidates exceeds the plan capacity");
     require_device(plan->gp->device);
     plan->nc = num_candidates;
+    {
+      const KernelSpec& spec = plan->gp->spec;
+      double rmax = plan->rmax_static;
+      const size_t pts = static_cast<size_t>(num_candidates) * plan->q;
+      for (size_t i = 0; i < pts && rmax < kFastPathRadius; ++i) {
+        double r2 = 0.0;
+        for (int d = 0; d < spec.dim; ++d) {
+          const double v = candidates[i * spec.dim + d] * spec.inv_len[d];
+          r2 += v * v;
+        }
+        rmax = std::max(rmax, std::sqrt(r2));
+      }
+      plan->use_smem = plan->smem_fits && rmax < kFastPathRadius;  // NaN-safe: a NaN norm fails the comparison
+      plan->mcp.use_smem = plan->use_smem ? 1 : 0;
+    }
     plan->dCand.upload(candidates, static_cast<size_t>(num_candidates) * plan->q * plan->gp->spec.dim,
                        plan->gp->stream);
   });

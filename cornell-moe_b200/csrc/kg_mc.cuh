@@ -19,6 +19,14 @@
 
 namespace cmoe {
 
+// Range contract of the shared-memory fast path.  Its exp (exp_tab, no per-call guard) needs |t| < 2^31 ln2 / 64 =
+// 2.3e7, t = -|x~ - X~_j|^2 / 2 + ln(alpha).  The host only selects the fast path while every scaled operand (training,
+// union, discrete points, inner-domain corners) lies within kFastPathRadius of the origin; a query point farther than
+// kFarRadius is then at least kFarRadius - kFastPathRadius = 2000 length scales from every operand, so all its kernel
+// values are exactly 0 and the evaluation is short-circuited; any other query point has |t| <= 6000^2 / 2 = 1.8e7.
+constexpr double kFastPathRadius = 2000.0;
+constexpr double kFarRadius = 4000.0;
+
 struct KgMcParams {
   int N;        // training points
   int U;        // union points (= rows, g == 0)
@@ -43,6 +51,7 @@ struct KgMcParams {
   const double* alpha0;  // [max_steps]  pre_mult * (i+1)^-gamma
   double* outVal;        // [nc][num_mc]   -mu+(x*)  (the reference's best_function_value)
   double* outX;          // [nc][num_mc][DIM] scaled minimiser
+  double* outH;          // [nc][num_mc]      -|scaled minimiser|^2 / 2 (consumed by kg_acc_kernel)
   unsigned long long* stats;  // [4]: posterior evaluations, accepted steps, point rounds, line batches (per lane)
   double lo[CMOE_MAX_DIM], hi[CMOE_MAX_DIM], inv_len[CMOE_MAX_DIM], len[CMOE_MAX_DIM];
 };
@@ -54,6 +63,7 @@ struct KgAccParams {
   const double* Xu;     // [nc][U][DIM+2]
   const double* recC;   // [nc][num_mc][QP]
   const double* outX;   // [nc][num_mc][DIM]
+  const double* outH;   // [nc][num_mc]  -|x*|^2/2
   double* R;            // [nc][QP][N+U]   R[a][row] = sum_i c_ia k(row, x*_i)
   double* Gu;           // [nc][U][DIM]    sum_i c_iu Bpart(Xu_u, x*_i) x~*_i
   double* GkB;          // [nc][U]         sum_i c_iu Bpart(Xu_u, x*_i)
@@ -88,12 +98,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+#ifndef CMOE_EXP_TABLE
+#define CMOE_EXP_TABLE 1
+#endif
+#if CMOE_EXP_TABLE
+// exp(t) = 2^k * 2^(i/64) * e^r with |r| <= ln2/128: 64-entry table in shared memory + degree-5 Taylor polynomial
+// (truncation r^6/720 <= 3.5e-17 relative).  10 FP64-pipe instructions instead of 15 for exp_fast; same integer-side
+// clamp of the exponent, NO guard for |t| >= 2.3e7 (see kFastPathRadius).  Used by the shared-memory fast path of the fused q-KG kernel (+11 % throughput on the north-star shape).
+__device__ const double kExp2Table[64] = {
+#include "exp2_table64.inc"
+};
+__shared__ double g_exp_tab[64];
+__device__ __forceinline__ void exp_table_stage() {
+  if (threadIdx.x < 64) g_exp_tab[threadIdx.x] = kExp2Table[threadIdx.x];
+  __syncthreads();
+}
+__device__ __forceinline__ double exp_tab(double t) {
+  const double kShift = 6755399441055744.0;
+  double nf = fma(t, 64.0 * 1.4426950408889634, kShift);
+  const int n = __double2loint(nf);
+  nf -= kShift;
+  double r = fma(nf, -6.93147180369123816490e-01 / 64.0, t);
+  r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
+  double p = 8.3333333333333332e-03;
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  p *= g_exp_tab[n & 63];
+  const int k = max(n >> 6, -1000);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+#endif
+template <bool TAB>
+__device__ __forceinline__ double exp_sel(double t) {
+#if CMOE_EXP_TABLE
+  if (TAB) return exp_tab(t);
+#endif
+  return exp_fast(t);
+}
+
 // Kernel-specific pieces.  pk0 holds e_j = ln(alpha) - |x~_j|^2/2 for SE and |x~_j|^2 for Matern; hq = -|x~|^2/2.
 // Returns the value weight kv (k(x, X_j)) and the gradient weight kb (d k / d x_d = kb * (x~_jd - x~_d) / l_d).
-template <int KERNEL>
+template <int KERNEL, bool TAB = false>
 __device__ __forceinline__ void kernel_pair(double dot, double pk0, double hq, double alpha, double& kv, double& kb) {
   if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
-    kv = exp_fast(dot + (pk0 + hq));
+    kv = exp_sel<TAB>(dot + (pk0 + hq));
     kb = kv;
   } else {
     const double r2 = fmax(0.0, pk0 - 2.0 * (hq + dot));
@@ -112,6 +163,49 @@ __device__ __forceinline__ double2 ld2(const double* p) {
   } else {
     return __ldg(reinterpret_cast<const double2*>(p));
   }
+}
+
+// x . y and beta - B . c over the staged operands.  CMOE_SPLIT_CHAINS = 1 accumulates even and odd terms separately
+// (two half-length dependent DFMA chains + one DADD) to expose more instruction-level parallelism.
+template <int DIM>
+__device__ __forceinline__ double dot_dim(const double (&x)[DIM], const double (&y)[DIM], double init) {
+#if CMOE_SPLIT_CHAINS
+  double d0 = init, d1 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; d += 2) {
+    d0 = fma(x[d], y[d], d0);
+    d1 = fma(x[d + 1], y[d + 1], d1);
+  }
+  return d0 + d1;
+#else
+  double dot = init;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) dot = fma(x[d], y[d], dot);
+  return dot;
+#endif
+}
+
+template <int QP, bool SMEM>
+__device__ __forceinline__ double weight_row(const double* __restrict__ pk, double beta, const double (&c)[QP]) {
+#if CMOE_SPLIT_CHAINS
+  double a0 = beta, a1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < QP; u += 2) {
+    const double2 b = ld2<SMEM>(pk + 2 + u);
+    a0 = fma(-b.x, c[u], a0);
+    a1 = fma(-b.y, c[u + 1], a1);
+  }
+  return a0 + a1;
+#else
+  double a = beta;
+#pragma unroll
+  for (int u = 0; u < QP; u += 2) {
+    const double2 b = ld2<SMEM>(pk + 2 + u);
+    a = fma(-b.x, c[u], a);
+    a = fma(-b.y, c[u + 1], a);
+  }
+  return a;
+#endif
 }
 
 // mu+(xq) - m  and  the scaled-gradient accumulators, for one query point (scaled coordinates xq).
@@ -141,18 +235,10 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
       xv[d + 1] = v.y;
     }
     const double2 h = ld2<SMEM>(pk);  // (e_j, beta_j)
-    double dot = 0.0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
-    double a = h.y;
-#pragma unroll
-    for (int u = 0; u < QP; u += 2) {
-      const double2 b = ld2<SMEM>(pk + 2 + u);
-      a = fma(-b.x, c[u], a);
-      a = fma(-b.y, c[u + 1], a);
-    }
+    const double dot = dot_dim<DIM>(xq, xv, 0.0);
+    const double a = weight_row<QP, SMEM>(pk, h.y, c);
     double kv, kb;
-    kernel_pair<KERNEL>(dot, h.x, hq, alpha, kv, kb);
+    kernel_pair<KERNEL, SMEM>(dot, h.x, hq, alpha, kv, kb);
     S0 = fma(a, kv, S0);
     const double wb = a * kb;
     if (KERNEL != CMOE_KERNEL_SQUARE_EXPONENTIAL) SB += wb;
@@ -173,7 +259,7 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
 #pragma unroll
     for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
     double kv, kb;
-    kernel_pair<KERNEL>(dot, h.x, hq, alpha, kv, kb);
+    kernel_pair<KERNEL, SMEM>(dot, h.x, hq, alpha, kv, kb);
     double cu = 0.0;
 #pragma unroll
     for (int v = 0; v < QP; ++v)
@@ -185,6 +271,13 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
     for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
   }
   if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) SB = S0;
+  if (SMEM && nq > kFarRadius * kFarRadius) {
+    // farther than kFarRadius length scales from everything: every kernel value is exactly 0 (see kFastPathRadius)
+    S0 = 0.0;
+    SB = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) s[d] = 0.0;
+  }
 }
 
 // Batched backtracking for the SquareExponential kernel.  The reference's line search tries x + a_k g for
@@ -193,15 +286,24 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
 // so with F_j = exp(a_min p_j) the kernel at every trial point is k(x, X_j) F_j^(2^m) times a j-independent factor:
 // two exps per training point give all KB trial values by repeated squaring (1 mul + 1 fma per trial) instead of one
 // full evaluation (dot + weights + exp) per trial.  S[k] = sum_j a_j k(x, X_j) exp(a_k p_j) for a_k = a_min 2^(KB-1-k'),
-// returned in trial order (S[0] <-> largest step); pmax = max_j |p_j| lets the caller reject batches whose factors
-// could leave the double range (it then falls back to one-at-a-time evaluations).
-constexpr int kLineBatch = 8;
+// returned in trial order (S[0] <-> largest step); pmax_hi (high word of max_j |a_min p_j|) lets the caller reject
+// batches whose factors could leave the double range (it then falls back to one-at-a-time evaluations).
+#ifndef CMOE_LINE_BATCH
+#define CMOE_LINE_BATCH 8
+#endif
+#ifndef CMOE_PMAX_FP
+#define CMOE_PMAX_FP 0
+#endif
+#ifndef CMOE_SPLIT_CHAINS
+#define CMOE_SPLIT_CHAINS 0
+#endif
+constexpr int kLineBatch = CMOE_LINE_BATCH;
 
 template <int DIM, int QP, bool SMEM>
 __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const double* __restrict__ Pk,
                                           const double* __restrict__ Xu, int N, int U, const double (&xb)[DIM],
                                           const double (&gt)[DIM], const double (&c)[QP], double alpha_min,
-                                          double (&S)[kLineBatch], double& pmax) {
+                                          double (&S)[kLineBatch], int& pmax_hi) {
   double nq = 0.0, xg = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
@@ -215,7 +317,10 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
   const double xga = -alpha_min * xg;
 #pragma unroll
   for (int k = 0; k < kLineBatch; ++k) S[k] = 0.0;
-  pmax = 0.0;
+#if CMOE_PMAX_FP
+  double pmax_fp = 0.0;
+#endif
+  pmax_hi = 0;  // max over rows of the high word of |a_min p_j| (integer ALU; monotone in |p|, NaN/inf sort last)
 #pragma unroll 2
   for (int j = 0; j < N; ++j) {
     const double* xj = Xt + j * DIM;
@@ -228,22 +333,16 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
       xv[d + 1] = v.y;
     }
     const double2 h = ld2<SMEM>(pk);  // (e_j, beta_j)
-    double dot = 0.0, pj = xga;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      dot = fma(xb[d], xv[d], dot);
-      pj = fma(ga[d], xv[d], pj);
-    }
-    double a = h.y;
-#pragma unroll
-    for (int u = 0; u < QP; u += 2) {
-      const double2 b = ld2<SMEM>(pk + 2 + u);
-      a = fma(-b.x, c[u], a);
-      a = fma(-b.y, c[u + 1], a);
-    }
-    pmax = fmax(pmax, fabs(pj));
-    const double w = a * exp_fast(dot + (h.x + hq));
-    double G = exp_fast(pj);
+    const double dot = dot_dim<DIM>(xb, xv, 0.0);
+    const double pj = dot_dim<DIM>(ga, xv, xga);
+    const double a = weight_row<QP, SMEM>(pk, h.y, c);
+#if CMOE_PMAX_FP
+    pmax_fp = fmax(pmax_fp, fabs(pj));
+#else
+    pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
+#endif
+    const double w = a * exp_sel<SMEM>(dot + (h.x + hq));
+    double G = exp_sel<SMEM>(pj);
 #pragma unroll
     for (int k = kLineBatch - 1; k >= 0; --k) {
       S[k] = fma(w, G, S[k]);
@@ -270,15 +369,22 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
 #pragma unroll
     for (int v = 0; v < QP; ++v)
       if (v == u) cu = c[v];
-    pmax = fmax(pmax, fabs(pj));
-    const double w = cu * exp_fast(dot + (h.x + hq));
-    double G = exp_fast(pj);
+#if CMOE_PMAX_FP
+    pmax_fp = fmax(pmax_fp, fabs(pj));
+#else
+    pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
+#endif
+    const double w = cu * exp_sel<SMEM>(dot + (h.x + hq));
+    double G = exp_sel<SMEM>(pj);
 #pragma unroll
     for (int k = kLineBatch - 1; k >= 0; --k) {
       S[k] = fma(w, G, S[k]);
       if (k > 0) G *= G;
     }
   }
+#if CMOE_PMAX_FP
+  pmax_hi = __double2hiint(pmax_fp) & 0x7fffffff;
+#endif
 }
 
 // Kernel pieces for the general path: kv = k(x, X_j) (value row), kb = factor of the first-derivative rows,
@@ -452,6 +558,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
   const int* recStart = prm.recStart + static_cast<size_t>(cand) * prm.num_mc;
   double* outVal = prm.outVal + static_cast<size_t>(cand) * prm.num_mc;
   double* outX = prm.outX + static_cast<size_t>(cand) * prm.num_mc * DIM;
+  double* outH = prm.outH + static_cast<size_t>(cand) * prm.num_mc;
 
   int state = ST_FETCH;
   int sample = s_begin + threadIdx.x;
@@ -488,8 +595,13 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
           // ComputeOptimalPosteriorMean returns without touching its outputs (...optimization.cpp:424-426):
           // best_function_value stays 0 and the best point keeps its fill value 1.0
           outVal[sample] = 0.0;
+          double nx = 0.0;
 #pragma unroll
-          for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = 1.0 * prm.inv_len[d];
+          for (int d = 0; d < DIM; ++d) {
+            outX[static_cast<size_t>(sample) * DIM + d] = 1.0 * prm.inv_len[d];
+            nx = fma(prm.inv_len[d], prm.inv_len[d], nx);
+          }
+          outH[sample] = -0.5 * nx;
           sample = atomicAdd(next_sample, 1);
         }
       } else {
@@ -508,7 +620,8 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
 
     if (LINE && line_round) {
       // ---- all backtracking trials of this step in one pass (warp-uniform) ----
-      double xt[DIM], gt[DIM], S[kLineBatch], pmax;
+      double xt[DIM], gt[DIM], S[kLineBatch];
+      int pmax_hi;
       double gg = 0.0;
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
@@ -517,10 +630,14 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         gg = fma(gt[d], gt[d], gg);
       }
       constexpr double kTop = static_cast<double>(1 << (kLineBatch - 1));
-      eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax);
+      eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax_hi);
       if (state == ST_LINE) {
         n_line += 1;
-        if (!(pmax * kTop <= 650.0)) {
+        // safe iff a_0 |p_j| = 2^(KB-1) |a_min p_j| < 512 for every row: every factor exp(a_k p_j) stays in range
+        double nb2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) nb2 = fma(xt[d], xt[d], nb2);
+        if (pmax_hi >= __double2hiint(512.0 / kTop) || !(nb2 <= kFarRadius * kFarRadius)) {
           state = ST_TRIAL;  // factors could leave the double range: this step backtracks one evaluation at a time
         } else {
           int kacc = -1;
@@ -668,8 +785,14 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
       restart_i += 1;
       if (sqrt(nd2) <= prm.tol || restart_i >= prm.max_restarts || prm.max_steps <= 0) {
         outVal[sample] = fb;
+        double nx = 0.0;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) outX[static_cast<size_t>(sample) * DIM + d] = xb[d] * prm.inv_len[d];
+        for (int d = 0; d < DIM; ++d) {
+          const double xs = xb[d] * prm.inv_len[d];
+          outX[static_cast<size_t>(sample) * DIM + d] = xs;
+          nx = fma(xs, xs, nx);
+        }
+        outH[sample] = -0.5 * nx;
         sample = atomicAdd(next_sample, 1);
         state = ST_FETCH;
       } else {
@@ -711,6 +834,9 @@ __global__ void __launch_bounds__(kMcThreads, CMOE_MC_MINBLOCKS) kg_mc_kernel(co
   const double* gPk = prm.Pk + static_cast<size_t>(cand) * N * (QP + 2);
   const double* gXu = prm.Xu + static_cast<size_t>(cand) * U * (DIM + 2);
   if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
+#if CMOE_EXP_TABLE
+  exp_table_stage();
+#endif
   if (prm.use_smem) {
     // stage the per-candidate operands with TMA bulk copies (UBLKCP) signalled through an mbarrier
     double* sXt = reinterpret_cast<double*>(smem_raw);
@@ -788,19 +914,29 @@ __global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgA
   for (int d = 0; d < DIM; ++d) gu[d] = 0.0;
   const double* xs = prm.outX + static_cast<size_t>(cand) * prm.num_mc * DIM;
   const double* cs = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
+  const double* hs = prm.outH + static_cast<size_t>(cand) * prm.num_mc;
   const int uu = is_u ? (row - N) : 0;
+  // every lane reads the same sample record: warp-broadcast 16-byte loads through the read-only path
+#pragma unroll 2
   for (int i = 0; i < prm.num_mc; ++i) {
-    const double* xi = xs + static_cast<size_t>(i) * DIM;
-    const double* ci = cs + static_cast<size_t>(i) * QP;
-    double dot = 0.0, nq = 0.0;
+    double xi[DIM], ci[QP];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      const double v = xi[d];
-      dot = fma(v, xr[d], dot);
-      nq = fma(v, v, nq);
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(xs + static_cast<size_t>(i) * DIM + d));
+      xi[d] = v.x;
+      xi[d + 1] = v.y;
     }
+#pragma unroll
+    for (int a = 0; a < QP; a += 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(cs + static_cast<size_t>(i) * QP + a));
+      ci[a] = v.x;
+      ci[a + 1] = v.y;
+    }
+    double dot = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) dot = fma(xi[d], xr[d], dot);
     double kv, kb;
-    kernel_pair<KERNEL>(dot, pk0, -0.5 * nq, prm.alpha, kv, kb);
+    kernel_pair<KERNEL>(dot, pk0, __ldg(hs + i), prm.alpha, kv, kb);
 #pragma unroll
     for (int a = 0; a < QP; ++a) acc[a] = fma(ci[a], kv, acc[a]);
     if (is_u) {

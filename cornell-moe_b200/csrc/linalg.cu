@@ -20,81 +20,176 @@ constexpr int LDT = NB + 4;   // smem leading dimension: 68 = 4 (mod 16) makes t
 constexpr double kPivotTol = 1.0e-16;  // gpp_linear_algebra.cpp:118
 
 // --------------------------------------------------------------------------------------------------------------
-// potf2: factor one nb x nb diagonal block in shared memory (single CTA), and emit inv(L_kk) for the panel update.
+// Diagonal-block factorisation + panel solve.  The column recurrence sqrt -> scale -> update is the latency-critical
+// chain of the whole factorisation (n/64 dependent block steps), so it runs out of REGISTERS: a warp factors a 32x32
+// block with lane r holding row r and the pivot / multiplier columns travelling by shuffle — no barriers, no shared
+// memory round trips inside the recurrence.
 // --------------------------------------------------------------------------------------------------------------
-// Factor the nb x nb block held in shared memory S (row r, col c at S[r][c], lower part) in place; returns 0 or the
-// global leading-minor index of the failing pivot.  256 threads: thread = (row r, column residue class cq).
-__device__ __forceinline__ int factor_block(double (*S)[NB + 1], int nb, int k0, int r, int cq, int fast_chain) {
-  // The column recurrence sqrt -> divide -> update is the latency-critical chain of the whole factorisation, so every
-  // thread evaluates the pivot test and the square root itself (uniform outcome, no flag round trip) and there are
-  // only three barriers per column.
-  for (int j = 0; j < nb; ++j) {
-    const double piv = S[j][j];
-    if (!(piv > kPivotTol)) return k0 + j + 1;  // gpp_linear_algebra.cpp:118, 141-142
-    double ljj, lrj;
-    if (fast_chain) {
-      // sqrt and divide through one reciprocal square root + Newton corrections: same results as sqrt()/"/" to the
-      // last bit in all but rare halfway cases (and exactly when the true results are representable), at a third
-      // of the dependent latency.  Used for multi-block factorisations, where this chain is the critical path.
+constexpr int PT = 128;  // threads of the panel kernel: one panel row per thread
+
+// In-register Cholesky of a 32x32 block: on entry a[c] = A[lane][c] (c <= lane meaningful), on exit a[c] = L[lane][c].
+// Returns 0 or the 1-based index of the first pivot that fails `> 1e-16` (gpp_linear_algebra.cpp:118,141-142); the
+// outcome is warp-uniform and only evaluated at the end (no divergent exits inside the recurrence; the arithmetic
+// after a failed pivot is discarded).  The finished column is broadcast through a double-buffered 32-entry shared
+// column (one STS + one __syncwarp per column, 16-byte broadcast loads) rather than by shuffles.
+// FAST: sqrt and divide through one reciprocal square root + Newton corrections — the same results as sqrt()/"/" to
+// the last bit in all but rare halfway cases (and exactly when the true results are representable) at a third of the
+// dependent latency; small systems (known-answer cases) keep IEEE sqrt / divide.
+template <bool FAST>
+__device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __restrict__ colbuf /* [2][32] */) {
+  int fail = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double piv = __shfl_sync(0xffffffffu, a[j], j);
+    fail = (fail == 0 && !(piv > kPivotTol)) ? j + 1 : fail;
+    double l, q;
+    if (FAST) {
       const double y = rsqrt(piv);
-      double l = piv * y;
+      l = piv * y;
       l = fma(0.5 * y, fma(-l, l, piv), l);
-      ljj = l;
-      const double a = S[r][j];
-      double qv = a * y;
-      qv = fma(fma(-qv, l, a), y, qv);
-      lrj = qv;
+      q = a[j] * y;
+      q = fma(fma(-q, l, a[j]), y, q);
     } else {
-      ljj = sqrt(piv);
-      lrj = S[r][j] / ljj;
+      l = sqrt(piv);
+      q = a[j] / l;
     }
-    __syncthreads();  // everybody has read column j and the pivot
-    if (cq == 0) {
-      if (r == j) S[j][j] = ljj;
-      if (r > j && r < nb) S[r][j] = lrj;
+    a[j] = (lane == j) ? l : q;
+    if (j < 31) {
+      double* col = colbuf + (j & 1) * 32;
+      col[lane] = a[j];
+      __syncwarp();
+      if (((j + 1) & 1) != 0) a[j + 1] = fma(-a[j], col[j + 1], a[j + 1]);
+#pragma unroll
+      for (int k = (j + 2) & ~1; k < 32; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(col + k);
+        a[k] = fma(-a[j], v.x, a[k]);
+        a[k + 1] = fma(-a[j], v.y, a[k + 1]);
+      }
     }
-    __syncthreads();
-    // trailing update of the lower triangle: S[r][c] -= l_rj * l_cj for my columns c in (j, nb), r >= c
-    const int c0 = j + 1 + ((cq - (j + 1)) & 3);
-#pragma unroll 4
-    for (int c = c0; c < nb; c += 4)
-      if (r >= c && r < nb) S[r][c] = S[r][c] - lrj * S[c][j];
-    __syncthreads();
   }
-  return 0;
+  return fail;
 }
 
-// One launch per 64-column block step: CTA 0 factors the diagonal block and writes it back; every other CTA owns 64
-// rows of the panel below it, factors the (L2-resident) diagonal block redundantly in its own shared memory — cheaper
-// than a second dependent launch — and then solves  X L_kk^T = A_ik  by column-oriented substitution (one barrier
-// per column).  Failure (pivot <= 1e-16) is detected identically by every CTA; CTA 0 records k+1 in *flag.
-__global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                          int* __restrict__ flag, int* __restrict__ loaded,
-                                                          int fast_chain) {
-  extern __shared__ double dyn_smem[];
-  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
-  double (*R)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  __shared__ double rdiag[NB];
+// x <- x L^-T for one row held in registers (right-looking substitution: independent FMAs per column step).
+// LT[k*LTS + c] = L[c][k] (transposed copy, even row stride so pairs of multipliers come as one 16-byte broadcast).
+constexpr int LTS = NB + 2;
+template <int W, bool FAST>
+__device__ __forceinline__ void solve_row(double (&x)[W], const double* __restrict__ LT, const double* __restrict__ rd) {
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    x[k] = FAST ? x[k] * rd[k] : x[k] / rd[k];
+    const double* lt = LT + k * LTS;
+    if (((k + 1) & 1) != 0 && k + 1 < W) x[k + 1] = fma(-x[k], lt[k + 1], x[k + 1]);
+#pragma unroll
+    for (int c = (k + 2) & ~1; c < W; c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(lt + c);
+      x[c] = fma(-x[k], v.x, x[c]);
+      x[c + 1] = fma(-x[k], v.y, x[c + 1]);
+    }
+  }
+}
+
+// Factor the 64x64 block in shared memory S (row r, col c at S[r][c]; rows/cols beyond the matrix padded with the
+// identity) in place: [L11 0; L21 L22] via chol32(A11), L21 = A21 L11^-T, A22 -= L21 L21^T, chol32(A22).
+// Also fills LT (transposed factor) and rd[k] = 1/L_kk (FAST) or L_kk.  Called by all PT threads; returns 0 or the
+// failing 1-based pivot index.
+template <bool FAST>
+__device__ __forceinline__ int factor_block64(double (*S)[NB + 1], double* __restrict__ LT, double* __restrict__ rd,
+                                              double* __restrict__ colbuf, int* __restrict__ sfail) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
+    const int f = chol32_warp<FAST>(a, lane, colbuf);
+    double diag = 1.0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c <= lane) LT[c * LTS + lane] = a[c];
+      if (c == lane) diag = a[c];
+    }
+    rd[lane] = FAST ? 1.0 / diag : diag;
+    if (lane == 0) *sfail = f;
+    __syncwarp();
+    if (!f) {
+      // L21 = A21 L11^-T: lane r solves row 32+r
+      double x[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = S[32 + lane][c];
+      solve_row<32, FAST>(x, LT, rd);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        S[32 + lane][c] = x[c];
+        LT[c * LTS + 32 + lane] = x[c];
+      }
+    }
+  }
+  __syncthreads();
+  if (*sfail) return *sfail;
+  {
+    // A22 -= L21 L21^T: warp w owns columns 8w..8w+7, lane r row 32+r
+    double xr[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) xr[k] = S[32 + lane][k];
+#pragma unroll
+    for (int cc = 0; cc < 32 / (PT / 32); ++cc) {
+      const int c = warp * (32 / (PT / 32)) + cc;
+      double acc = S[32 + lane][32 + c];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fma(-xr[k], S[32 + c][k], acc);
+      S[32 + lane][32 + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][32 + c];
+    const int f = chol32_warp<FAST>(a, lane, colbuf);
+    double diag = 1.0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c <= lane) LT[(32 + c) * LTS + 32 + lane] = a[c];
+      if (c == lane) diag = a[c];
+    }
+    rd[32 + lane] = FAST ? 1.0 / diag : diag;
+    if (lane == 0) *sfail = f ? 32 + f : 0;
+  }
+  __syncthreads();
+  return *sfail;
+}
+
+// One launch per 64-column block step: CTA 0 factors the diagonal block and writes it back; every other CTA owns PT
+// rows of the panel below it (one row per thread, held in registers), factors the (L2-resident) diagonal block
+// redundantly in its own shared memory — cheaper than a second dependent launch — and then solves  X L_kk^T = A_ik
+// by right-looking substitution in registers.  Failure (pivot <= 1e-16) is detected identically by every CTA; CTA 0
+// records k+1 in *flag.
+template <bool FAST>
+__global__ void __launch_bounds__(PT) potrf_panel_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
+                                                         int* __restrict__ flag, int* __restrict__ loaded) {
+  extern __shared__ __align__(16) double panel_smem[];
+  double* LT = panel_smem;                                                   // [NB][LTS]
+  double* colbuf = LT + NB * LTS;                                            // [2][32]
+  double* rd = colbuf + 64;                                                  // [NB]
+  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(rd + NB);       // [NB][NB+1]
+  __shared__ int sfail;
   if (*flag != 0) return;
   const int tid = threadIdx.x;
-  const int r = tid & (NB - 1);   // row owned by this thread
-  const int cq = tid >> 6;        // column residue class (columns cq, cq+4, ...)
   double* Ab = A + static_cast<size_t>(k0) * lda + k0;
+  {
+    const int r = tid & (NB - 1);
 #pragma unroll 4
-  for (int c = cq; c < NB; c += 4) S[r][c] = (r < nb && c < nb && r >= c) ? Ab[static_cast<size_t>(c) * lda + r] : 0.0;
-  const int row0 = k0 + nb + (static_cast<int>(blockIdx.x) - 1) * NB;
-  const int rows = (blockIdx.x == 0) ? 0 : min(NB, n - row0);
-  if (blockIdx.x > 0) {
-    const double* Ar = A + static_cast<size_t>(k0) * lda + row0;
-#pragma unroll 4
-    for (int c = cq; c < NB; c += 4) R[r][c] = (r < rows && c < nb) ? Ar[static_cast<size_t>(c) * lda + r] : 0.0;
+    for (int c = tid >> 6; c < NB; c += PT / NB)
+      S[r][c] = (r < nb && c < nb && r >= c) ? Ab[static_cast<size_t>(c) * lda + r] : ((r == c && r >= nb) ? 1.0 : 0.0);
   }
+  const int myrow = k0 + nb + (static_cast<int>(blockIdx.x) - 1) * PT + tid;
+  const bool valid = blockIdx.x > 0 && myrow < n;
   __syncthreads();
   // CTA 0 overwrites the diagonal block in place; it must not do so before every panel CTA has read the original
   if (blockIdx.x > 0 && tid == 0) atomicAdd(loaded, 1);
-  const int failed = factor_block(S, nb, k0, r, cq, fast_chain);
+  const int failed = factor_block64<FAST>(S, LT, rd, colbuf, &sfail);
   if (failed) {
-    if (blockIdx.x == 0 && tid == 0) *flag = failed;
+    if (blockIdx.x == 0 && tid == 0) *flag = k0 + failed;
     return;
   }
   if (blockIdx.x == 0) {
@@ -103,25 +198,25 @@ __global__ void __launch_bounds__(256) potrf_panel_kernel(double* __restrict__ A
       while (atomicAdd(loaded, 0) < expect) __nanosleep(100);
     }
     __syncthreads();
+    const int r = tid & (NB - 1);
 #pragma unroll 4
-    for (int c = cq; c < NB; c += 4)
-      if (r < nb && c < nb && r >= c) Ab[static_cast<size_t>(c) * lda + r] = S[r][c];
+    for (int c = tid >> 6; c < NB; c += PT / NB)
+      if (r < nb && c < nb && r >= c) Ab[static_cast<size_t>(c) * lda + r] = LT[c * LTS + r];
     return;
   }
-  if (cq == 0) rdiag[r] = (r < nb) ? 1.0 / S[r][r] : 0.0;
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    const double xj = R[r][j] * rdiag[j];
-    if (cq == (j & 3)) R[r][j] = xj;  // the owner of column j keeps the solved value
-    const int c0 = j + 1 + ((cq - (j + 1)) & 3);
-#pragma unroll 4
-    for (int c = c0; c < nb; c += 4) R[r][c] = R[r][c] - xj * S[c][j];
-    __syncthreads();
+  double x[NB];
+  {
+    const double* Ar = A + static_cast<size_t>(k0) * lda + myrow;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] = (valid && c < nb) ? Ar[static_cast<size_t>(c) * lda] : 0.0;
   }
-  double* Aw = A + static_cast<size_t>(k0) * lda + row0;
-#pragma unroll 4
-  for (int c = cq; c < NB; c += 4)
-    if (r < rows && c < nb) Aw[static_cast<size_t>(c) * lda + r] = R[r][c];
+  solve_row<NB, FAST>(x, LT, rd);
+  if (valid) {
+    double* Aw = A + static_cast<size_t>(k0) * lda + myrow;
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c < nb) Aw[static_cast<size_t>(c) * lda] = x[c];
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -548,8 +643,10 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
   const size_t smem = 2 * NB * LDT * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  const size_t smem_panel = 2 * NB * (NB + 1) * sizeof(double);
-  CMOE_CUDA(cudaFuncSetAttribute(potrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem_panel = (static_cast<size_t>(NB) * LTS + 64 + NB + NB * (NB + 1)) * sizeof(double);
+  CMOE_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem_panel)));
+  CMOE_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_panel)));
   const size_t smem_gemm = static_cast<size_t>(GT) * GLD * sizeof(double);  // >= 2*GST*GK*GLD doubles as well
   static_assert(GT * GLD >= 2 * GST * GK * GLD, "accumulator staging must cover the pipeline buffers");
@@ -568,7 +665,12 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
       const int nb = min(NB, n - k0);
       const int rem = n - k0 - nb;
       const int row_tiles = (rem + NB - 1) / NB;
-      potrf_panel_kernel<<<1 + row_tiles, 256, smem_panel, s>>>(A, n, n, k0, nb, flag, loaded + k0 / NB, fast_chain);
+      const int panel_ctas = 1 + (rem + PT - 1) / PT;
+      if (fast_chain) {
+        potrf_panel_kernel<true><<<panel_ctas, PT, smem_panel, s>>>(A, n, n, k0, nb, flag, loaded + k0 / NB);
+      } else {
+        potrf_panel_kernel<false><<<panel_ctas, PT, smem_panel, s>>>(A, n, n, k0, nb, flag, loaded + k0 / NB);
+      }
       count_launch();
       // inner trailing update: only the columns that still belong to this outer panel
       const int col_tiles = (pend - (k0 + nb) + NB - 1) / NB;

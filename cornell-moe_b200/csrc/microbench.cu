@@ -37,6 +37,32 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Do the FP64 vector pipe (DFMA) and the FP64 tensor sub-pipe (DMMA) run concurrently?  Every warp interleaves equal
+// amounts of both (8 x m8n8k4 = 2048 FMA and 64 DFMA x 32 lanes = 2048 FMA per iteration).
+__global__ void __launch_bounds__(256) mixed_peak_kernel(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = threadIdx.x * 1e-9 + i * 1e-9;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9, m = 0.999999, k = 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fma(v[j], m, k);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 }  // namespace cmoe
 
@@ -70,6 +96,32 @@ extern "C" int cmoe_bench_fp64_peaks(int device, double* tflops) {
       }
       tflops[which] = best;
     }
+    CMOE_CUDA(cudaGetLastError());
+    cudaStreamDestroy(s);
+  });
+}
+
+// tflops[0] = total FP64 TFLOP/s with DFMA and DMMA interleaved 1:1 (by flops) in every warp.  ~= the larger of the two
+// peaks if the pipes share hardware, ~= their sum if they run concurrently.
+extern "C" int cmoe_bench_fp64_mixed(int device, double* tflops) {
+  return guarded(nullptr, [&] {
+    require_device(device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    DevBuf<double> out(static_cast<size_t>(blocks) * threads);
+    cudaStream_t s;
+    CMOE_CUDA(cudaStreamCreate(&s));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+      EventTimer t;
+      t.start(s);
+      mixed_peak_kernel<<<blocks, threads, 0, s>>>(out.p, iters);
+      t.stop(s);
+      const double flops = 2.0 * (2048.0 + 2048.0) * iters * static_cast<double>(blocks) * (threads / 32);
+      if (rep > 0) best = std::max(best, flops / (t.ms() * 1e-3) * 1e-12);
+    }
+    tflops[0] = best;
     CMOE_CUDA(cudaGetLastError());
     cudaStreamDestroy(s);
   });

@@ -247,6 +247,9 @@ int cmoe_bench_cov_build(const cmoe_gp* gp, int repeats, double* usec_per_build)
 int cmoe_bench_cholesky(const cmoe_gp* gp, int repeats, double* usec_per_factor);
 /* Measured FP64 peaks of this GPU: tflops[0] = DFMA vector pipe, tflops[1] = DMMA tensor pipe (m8n8k4). */
 int cmoe_bench_fp64_peaks(int device, double* tflops);
+/* tflops[0] = total FP64 TFLOP/s when every warp interleaves DFMA and DMMA 1:1 by flops (do the vector pipe and the
+ * tensor sub-pipe overlap?). */
+int cmoe_bench_fp64_mixed(int device, double* tflops);
 /* In-place lower Cholesky of a host matrix through the device path (ComputeCholeskyFactorL, gpp_linear_algebra.cpp:109). */
 int cmoe_cholesky(int n, double* a, int device, int* info);
 /* Solve (L L^T) X = B for nrhs right-hand sides (CholeskyFactorLMatrixMatrixSolve, gpp_linear_algebra.hpp:247). */

@@ -190,7 +190,7 @@ def test_kg_other_dimensions(capi, dim, q):
         np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
 
 
-@pytest.mark.parametrize("case", ["second_batch", "out_of_range_factors", "exhausted_search"])
+@pytest.mark.parametrize("case", ["second_batch", "out_of_range_factors", "exhausted_search", "tiny_length_scale"])
 def test_kg_line_batch_edge_paths(capi, case):
     """The SquareExponential fast path evaluates all backtracking trials of a step in one pass (8 step sizes per batch).
     Edge paths: more than 8 halvings (second batch), exponent factors that would leave the double range (falls back to
@@ -201,6 +201,11 @@ def test_kg_line_batch_edge_paths(capi, case):
     elif case == "out_of_range_factors":
         prob = make_problem(16, 3, seed=9, noise=0.1)
         gd = [1, 5, 2, 3, 0.0, 4096.0, 0.5, 1e-10]        # a_0 |p_j| >> 650: exp(a_0 p_j) is not representable
+    elif case == "tiny_length_scale":
+        # scaled coordinates up to ~8e3 length scales: outside the shared-memory fast path's range contract
+        # (kFastPathRadius), so the host must route the step through the fully guarded kernel
+        prob = make_problem(16, 3, seed=9, noise=0.1, length=2e-4)
+        gd = [1, 4, 2, 3, 0.0, 1e-6, 0.5, 1e-10]
     else:
         prob = make_problem(16, 3, seed=9, noise=0.1)
         gd = [1, 3, 2, 3, 0.0, 1e12, 0.5, 1e-10]          # a_0 2^-29 is still far too large: search hits 30
@@ -215,7 +220,7 @@ def test_kg_line_batch_edge_paths(capi, case):
     print(case, st)
     if case == "second_batch":
         assert st["line_batches"] >= 1.5 * st["line_search_steps"]  # two batches for most steps ...
-        assert st["point_evals"] <= st["line_search_steps"] + 2 * (2 * mc) * 2  # ... and no one-at-a-time trials
+        assert st["point_evals"] < st["posterior_evals"] / 3  # ... and few one-at-a-time trials
     if case == "out_of_range_factors":
         assert st["point_evals"] > 5 * st["line_search_steps"]  # the trials were evaluated one at a time
     for c in range(2):
