@@ -8,6 +8,9 @@
 //   CholeskyFactorLMatrix{Vector,Matrix}Solve  gpp_linear_algebra.hpp:220,247
 //
 // Layout: column-major, only the lower triangle of the factor is defined (as in the reference).
+#include <algorithm>
+#include <vector>
+
 #include "device_math.cuh"
 #include "internal.cuh"
 
@@ -27,72 +30,96 @@ constexpr double kPivotTol = 1.0e-16;  // gpp_linear_algebra.cpp:118
 // --------------------------------------------------------------------------------------------------------------
 constexpr int PT = 128;  // threads of the panel kernel: one panel row per thread
 
-// In-register Cholesky of a 32x32 block: on entry a[c] = A[lane][c] (c <= lane meaningful), on exit a[c] = L[lane][c].
+// The register-resident recurrences below are written as SHORT LOOPS over a rotating register window (after step k
+// the window is shifted so that slot 0 is always the pivot column) instead of fully unrolled triangles: straight-line
+// code of thousands of instructions that execute once each runs at instruction-fetch speed (measured: 18 us for a
+// 64x64 factorisation, 25 us for the panel solve), a loop body of a few hundred instructions stays in the I-cache.
+// Slots that rotate past the end of the row compute on padding and are never stored.
+
+// In-register Cholesky of a 32x32 block: on entry a[c] = A[lane][c] (c <= lane meaningful).  The finished column j of
+// L is written to LT[(col0 + j) * LTS + col0 + lane] (transposed factor) and rd[col0 + j] = 1/L_jj (FAST) or L_jj.
 // Returns 0 or the 1-based index of the first pivot that fails `> 1e-16` (gpp_linear_algebra.cpp:118,141-142); the
-// outcome is warp-uniform and only evaluated at the end (no divergent exits inside the recurrence; the arithmetic
-// after a failed pivot is discarded).  The finished column is broadcast through a double-buffered 32-entry shared
-// column (one STS + one __syncwarp per column, 16-byte broadcast loads) rather than by shuffles.
+// outcome is warp-uniform and only evaluated at the end (the arithmetic after a failed pivot is discarded).
+// The finished column is broadcast through a double-buffered shared column (one STS + one __syncwarp per column).
 // FAST: sqrt and divide through one reciprocal square root + Newton corrections — the same results as sqrt()/"/" to
 // the last bit in all but rare halfway cases (and exactly when the true results are representable) at a third of the
 // dependent latency; small systems (known-answer cases) keep IEEE sqrt / divide.
+constexpr int LTS = NB + 2;  // row stride of the transposed factor (even: 16-byte aligned rows)
 template <bool FAST>
-__device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __restrict__ colbuf /* [2][32] */) {
+__device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __restrict__ colbuf /* [2][64], [32..63] = 0 */,
+                                           double* __restrict__ LT, double* __restrict__ rd, int col0) {
   int fail = 0;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 32; ++j) {
-    const double piv = __shfl_sync(0xffffffffu, a[j], j);
+    const double piv = __shfl_sync(0xffffffffu, a[0], j);
     fail = (fail == 0 && !(piv > kPivotTol)) ? j + 1 : fail;
     double l, q;
     if (FAST) {
       const double y = rsqrt(piv);
       l = piv * y;
       l = fma(0.5 * y, fma(-l, l, piv), l);
-      q = a[j] * y;
-      q = fma(fma(-q, l, a[j]), y, q);
+      q = a[0] * y;
+      q = fma(fma(-q, l, a[0]), y, q);
     } else {
       l = sqrt(piv);
-      q = a[j] / l;
+      q = a[0] / l;
     }
-    a[j] = (lane == j) ? l : q;
-    if (j < 31) {
-      double* col = colbuf + (j & 1) * 32;
-      col[lane] = a[j];
-      __syncwarp();
-      if (((j + 1) & 1) != 0) a[j + 1] = fma(-a[j], col[j + 1], a[j + 1]);
+    const double lj = (lane == j) ? l : q;
+    if (lane >= j) LT[(col0 + j) * LTS + col0 + lane] = lj;
+    if (FAST) {
+      double r = rsqrt(piv);            // ~ 1/l
+      r = fma(fma(-l, r, 1.0), r, r);   // one Newton step on 1/l: no divide on the per-column critical path
+      if (lane == j) rd[col0 + j] = r;
+    } else {
+      if (lane == j) rd[col0 + j] = l;
+    }
+    double* col = colbuf + (j & 1) * 64;
+    col[lane] = lj;
+    __syncwarp();
+    // window slot k <-> column j + k; multipliers L[j+k][j] = col[j+k] (zero beyond the block)
 #pragma unroll
-      for (int k = (j + 2) & ~1; k < 32; k += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(col + k);
-        a[k] = fma(-a[j], v.x, a[k]);
-        a[k + 1] = fma(-a[j], v.y, a[k + 1]);
-      }
-    }
+    for (int k = 1; k < 32; ++k) a[k - 1] = fma(-lj, col[j + k], a[k]);
+    a[31] = 0.0;
   }
   return fail;
 }
 
-// x <- x L^-T for one row held in registers (right-looking substitution: independent FMAs per column step).
-// LT[k*LTS + c] = L[c][k] (transposed copy, even row stride so pairs of multipliers come as one 16-byte broadcast).
-constexpr int LTS = NB + 2;
-template <int W, bool FAST>
-__device__ __forceinline__ void solve_row(double (&x)[W], const double* __restrict__ LT, const double* __restrict__ rd) {
+// STEPS steps of  x <- x L^-T  for one row held in a rotating register window of W slots: slot i holds column
+// cbase + i on entry and column cbase + STEPS + i on exit.  The solved value of column k is handed to emit(k, value).
+// LT[k*LTS + c] = L[c][k]; cbase and UNR are multiples of 2 and LTS is even, so pairs of multipliers come as one
+// 16-byte broadcast load; rows of LT must be followed by readable padding (slots past the end of the row read it and
+// are never emitted).
+template <int W, int STEPS, int UNR, bool FAST, typename Emit>
+__device__ __forceinline__ void solve_steps_rot(double (&x)[W], const double* __restrict__ LT,
+                                                const double* __restrict__ rd, int cbase, Emit&& emit) {
+  static_assert(STEPS % UNR == 0 && UNR % 2 == 0 && W % 2 == 0, "even windows, whole bodies");
+#pragma unroll 1
+  for (int kb = 0; kb < STEPS; kb += UNR) {
 #pragma unroll
-  for (int k = 0; k < W; ++k) {
-    x[k] = FAST ? x[k] * rd[k] : x[k] / rd[k];
-    const double* lt = LT + k * LTS;
-    if (((k + 1) & 1) != 0 && k + 1 < W) x[k + 1] = fma(-x[k], lt[k + 1], x[k + 1]);
+    for (int s = 0; s < UNR; ++s) {
+      const int k = cbase + kb + s;
+      const double xk = FAST ? x[s] * rd[k] : x[s] / rd[k];
+      emit(k, xk);
+      const double* lt = LT + k * LTS + cbase + kb;  // 16-byte aligned
+      if (((s + 1) & 1) != 0) x[s + 1] = fma(-xk, lt[s + 1], x[s + 1]);
 #pragma unroll
-    for (int c = (k + 2) & ~1; c < W; c += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(lt + c);
-      x[c] = fma(-x[k], v.x, x[c]);
-      x[c + 1] = fma(-x[k], v.y, x[c + 1]);
+      for (int i = (s + 2) & ~1; i < W; i += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(lt + i);
+        x[i] = fma(-xk, v.x, x[i]);
+        x[i + 1] = fma(-xk, v.y, x[i + 1]);
+      }
     }
+#pragma unroll
+    for (int i = 0; i + UNR < W; ++i) x[i] = x[i + UNR];
+#pragma unroll
+    for (int i = W - UNR; i < W; ++i) x[i] = 0.0;
   }
 }
 
 // Factor the 64x64 block in shared memory S (row r, col c at S[r][c]; rows/cols beyond the matrix padded with the
-// identity) in place: [L11 0; L21 L22] via chol32(A11), L21 = A21 L11^-T, A22 -= L21 L21^T, chol32(A22).
-// Also fills LT (transposed factor) and rd[k] = 1/L_kk (FAST) or L_kk.  Called by all PT threads; returns 0 or the
-// failing 1-based pivot index.
+// identity): [L11 0; L21 L22] via chol32(A11), L21 = A21 L11^-T, A22 -= L21 L21^T, chol32(A22).  The factor is left
+// in LT (transposed) with rd[k] = 1/L_kk (FAST) or L_kk.  Called by all PT threads; returns 0 or the failing 1-based
+// pivot index.
 template <bool FAST>
 __device__ __forceinline__ int factor_block64(double (*S)[NB + 1], double* __restrict__ LT, double* __restrict__ rd,
                                               double* __restrict__ colbuf, int* __restrict__ sfail) {
@@ -101,58 +128,43 @@ __device__ __forceinline__ int factor_block64(double (*S)[NB + 1], double* __res
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = S[lane][c];
-    const int f = chol32_warp<FAST>(a, lane, colbuf);
-    double diag = 1.0;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      if (c <= lane) LT[c * LTS + lane] = a[c];
-      if (c == lane) diag = a[c];
-    }
-    rd[lane] = FAST ? 1.0 / diag : diag;
+    const int f = chol32_warp<FAST>(a, lane, colbuf, LT, rd, 0);
     if (lane == 0) *sfail = f;
     __syncwarp();
     if (!f) {
-      // L21 = A21 L11^-T: lane r solves row 32+r
+      // L21 = A21 L11^-T: lane r solves row 32+r; the result goes to S (row access for the SYRK) and LT
       double x[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) x[c] = S[32 + lane][c];
-      solve_row<32, FAST>(x, LT, rd);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        S[32 + lane][c] = x[c];
-        LT[c * LTS + 32 + lane] = x[c];
-      }
+      solve_steps_rot<32, 32, 4, FAST>(x, LT, rd, 0, [&](int k, double v) {
+        S[32 + lane][k] = v;
+        LT[k * LTS + 32 + lane] = v;
+      });
     }
   }
   __syncthreads();
   if (*sfail) return *sfail;
   {
     // A22 -= L21 L21^T: warp w owns columns 8w..8w+7, lane r row 32+r
-    double xr[32];
+    constexpr int CW = 32 / (PT / 32);
+    double acc[CW];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) xr[k] = S[32 + lane][k];
+    for (int cc = 0; cc < CW; ++cc) acc[cc] = S[32 + lane][32 + warp * CW + cc];
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+      const double xr = S[32 + lane][k];
 #pragma unroll
-    for (int cc = 0; cc < 32 / (PT / 32); ++cc) {
-      const int c = warp * (32 / (PT / 32)) + cc;
-      double acc = S[32 + lane][32 + c];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) acc = fma(-xr[k], S[32 + c][k], acc);
-      S[32 + lane][32 + c] = acc;
+      for (int cc = 0; cc < CW; ++cc) acc[cc] = fma(-xr, LT[k * LTS + 32 + warp * CW + cc], acc[cc]);
     }
+#pragma unroll
+    for (int cc = 0; cc < CW; ++cc) S[32 + lane][32 + warp * CW + cc] = acc[cc];
   }
   __syncthreads();
   if (warp == 0) {
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = S[32 + lane][32 + c];
-    const int f = chol32_warp<FAST>(a, lane, colbuf);
-    double diag = 1.0;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      if (c <= lane) LT[(32 + c) * LTS + 32 + lane] = a[c];
-      if (c == lane) diag = a[c];
-    }
-    rd[32 + lane] = FAST ? 1.0 / diag : diag;
+    const int f = chol32_warp<FAST>(a, lane, colbuf, LT, rd, 32);
     if (lane == 0) *sfail = f ? 32 + f : 0;
   }
   __syncthreads();
@@ -168,9 +180,9 @@ template <bool FAST>
 __global__ void __launch_bounds__(PT) potrf_panel_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
                                                          int* __restrict__ flag, int* __restrict__ loaded) {
   extern __shared__ __align__(16) double panel_smem[];
-  double* LT = panel_smem;                                                   // [NB][LTS]
-  double* colbuf = LT + NB * LTS;                                            // [2][32]
-  double* rd = colbuf + 64;                                                  // [NB]
+  double* LT = panel_smem;                                                   // [NB][LTS] + NB padding
+  double* colbuf = LT + NB * LTS + NB;                                       // [2][64]
+  double* rd = colbuf + 128;                                                 // [NB]
   double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(rd + NB);       // [NB][NB+1]
   __shared__ int sfail;
   if (*flag != 0) return;
@@ -181,9 +193,17 @@ __global__ void __launch_bounds__(PT) potrf_panel_kernel(double* __restrict__ A,
 #pragma unroll 4
     for (int c = tid >> 6; c < NB; c += PT / NB)
       S[r][c] = (r < nb && c < nb && r >= c) ? Ab[static_cast<size_t>(c) * lda + r] : ((r == c && r >= nb) ? 1.0 : 0.0);
+    for (int e = tid; e < NB * LTS + NB + 128; e += PT) LT[e] = 0.0;  // factor, its padding and the column buffers
   }
   const int myrow = k0 + nb + (static_cast<int>(blockIdx.x) - 1) * PT + tid;
   const bool valid = blockIdx.x > 0 && myrow < n;
+  double x[NB];
+  if (blockIdx.x > 0) {
+    // issue the panel-row loads before the factorisation: their latency hides behind it
+    const double* Ar = A + static_cast<size_t>(k0) * lda + myrow;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] = (valid && c < nb) ? Ar[static_cast<size_t>(c) * lda] : 0.0;
+  }
   __syncthreads();
   // CTA 0 overwrites the diagonal block in place; it must not do so before every panel CTA has read the original
   if (blockIdx.x > 0 && tid == 0) atomicAdd(loaded, 1);
@@ -204,19 +224,16 @@ __global__ void __launch_bounds__(PT) potrf_panel_kernel(double* __restrict__ A,
       if (r < nb && c < nb && r >= c) Ab[static_cast<size_t>(c) * lda + r] = LT[c * LTS + r];
     return;
   }
-  double x[NB];
-  {
-    const double* Ar = A + static_cast<size_t>(k0) * lda + myrow;
+  double* Aw = A + static_cast<size_t>(k0) * lda + myrow;
+  auto emit = [&](int k, double v) {
+    if (valid && k < nb) Aw[static_cast<size_t>(k) * lda] = v;
+  };
+  // first half with the full window, second half with a window of the 32 columns that are left
+  solve_steps_rot<NB, NB / 2, 4, FAST>(x, LT, rd, 0, emit);
+  double xh[NB / 2];
 #pragma unroll
-    for (int c = 0; c < NB; ++c) x[c] = (valid && c < nb) ? Ar[static_cast<size_t>(c) * lda] : 0.0;
-  }
-  solve_row<NB, FAST>(x, LT, rd);
-  if (valid) {
-    double* Aw = A + static_cast<size_t>(k0) * lda + myrow;
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-      if (c < nb) Aw[static_cast<size_t>(c) * lda] = x[c];
-  }
+  for (int i = 0; i < NB / 2; ++i) xh[i] = x[i];
+  solve_steps_rot<NB / 2, NB / 2, 4, FAST>(xh, LT, rd, NB / 2, emit);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -338,89 +355,101 @@ constexpr int GLD = GT + 4;   // 132 = 4 (mod 16): conflict-free fragment loads
 
 constexpr int GTHREADS = 512;  // 16 warps = 4 x 4 warp tiles of 32 x 32 (4 warps per scheduler keep the DMMA pipe fed)
 
+// Trailing update A[t0:, t0:] -= P P^T, P = A[t0:, p0:p0+W], restricted to the column tiles [tj_lo, tj_hi) of the
+// lower-triangular 128x128 tile grid.  Persistent: CTA b works on tiles b, b + gridDim.x, ... (column-major tile
+// order), so a launch can be confined to a subset of the SMs while the next panel's factorisation uses the others.
 __global__ void __launch_bounds__(GTHREADS, 1) dmma_gemm_kernel(double* __restrict__ A, int lda, int n, int p0, int W,
-                                                                const int* __restrict__ flag) {
+                                                                int tj_lo, int tj_hi, const int* __restrict__ flag) {
   extern __shared__ double gsm[];
   if (*flag != 0) return;
   const int t0 = p0 + W;
-  const int b = blockIdx.x;
-  int ti = static_cast<int>((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
-  while (ti * (ti + 1) / 2 > b) --ti;
-  while ((ti + 1) * (ti + 2) / 2 <= b) ++ti;
-  const int tj = b - ti * (ti + 1) / 2;
-  const int row0 = t0 + ti * GT, col0 = t0 + tj * GT;
-  const int rows = min(GT, n - row0), cols = min(GT, n - col0);
-  double* As = gsm;                    // [GST][GK][GLD]
-  double* Bs = gsm + GST * GK * GLD;   // [GST][GK][GLD]
-  const double* Ag = A + static_cast<size_t>(p0) * lda + row0;
-  const double* Bg = A + static_cast<size_t>(p0) * lda + col0;
+  const int tiles = (n - t0 + GT - 1) / GT;
+  tj_hi = min(tj_hi, tiles);
+  // tiles in column tj: row tiles tj .. tiles-1
+  int total = 0;
+  for (int tj = tj_lo; tj < tj_hi; ++tj) total += tiles - tj;
   const int tid = threadIdx.x;
   const int nchunks = W / GK;
-
-  auto load_chunk = [&](int kc, int stage) {
-    double* as = As + stage * GK * GLD;
-    double* bs = Bs + stage * GK * GLD;
-#pragma unroll
-    for (int e = tid; e < GT * GK; e += GTHREADS) {
-      const int m = e % GT, k = e / GT;
-      cp_async8(as + k * GLD + m, m < rows ? Ag + static_cast<size_t>(kc * GK + k) * lda + m : Ag, m < rows);
-      cp_async8(bs + k * GLD + m, m < cols ? Bg + static_cast<size_t>(kc * GK + k) * lda + m : Bg, m < cols);
-    }
-  };
-
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
   const int lr = lane >> 2, lc = lane & 3;
-  double acc[4][4][2];
+  double* As = gsm;                    // [GST][GK][GLD]
+  double* Bs = gsm + GST * GK * GLD;   // [GST][GK][GLD]
+  for (int b = blockIdx.x; b < total; b += gridDim.x) {
+    int tj = tj_lo, rem = b;
+    while (rem >= tiles - tj) {
+      rem -= tiles - tj;
+      ++tj;
+    }
+    const int ti = tj + rem;
+    const int row0 = t0 + ti * GT, col0 = t0 + tj * GT;
+    const int rows = min(GT, n - row0), cols = min(GT, n - col0);
+    const double* Ag = A + static_cast<size_t>(p0) * lda + row0;
+    const double* Bg = A + static_cast<size_t>(p0) * lda + col0;
+
+    auto load_chunk = [&](int kc, int stage) {
+      double* as = As + stage * GK * GLD;
+      double* bs = Bs + stage * GK * GLD;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+      for (int e = tid; e < GT * GK; e += GTHREADS) {
+        const int m = e % GT, k = e / GT;
+        cp_async8(as + k * GLD + m, m < rows ? Ag + static_cast<size_t>(kc * GK + k) * lda + m : Ag, m < rows);
+        cp_async8(bs + k * GLD + m, m < cols ? Bg + static_cast<size_t>(kc * GK + k) * lda + m : Bg, m < cols);
+      }
+    };
+
+    double acc[4][4][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
-  for (int st = 0; st < GST - 1; ++st) {
-    if (st < nchunks) load_chunk(st, st);
-    cp_async_commit();
-  }
-  for (int kc = 0; kc < nchunks; ++kc) {
-    cp_async_wait<GST - 2>();
+    for (int st = 0; st < GST - 1; ++st) {
+      if (st < nchunks) load_chunk(st, st);
+      cp_async_commit();
+    }
+    for (int kc = 0; kc < nchunks; ++kc) {
+      cp_async_wait<GST - 2>();
+      __syncthreads();
+      const int nxt = kc + GST - 1;
+      if (nxt < nchunks) load_chunk(nxt, nxt % GST);
+      cp_async_commit();
+      const double* as = As + (kc % GST) * GK * GLD;
+      const double* bs = Bs + (kc % GST) * GK * GLD;
+#pragma unroll
+      for (int kk = 0; kk < GK; kk += 4) {
+        double a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = as[(kk + lc) * GLD + wm + i * 8 + lr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = bs[(kk + lc) * GLD + wn + j * 8 + lr];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+      }
+    }
+    cp_async_wait<0>();
     __syncthreads();
-    const int nxt = kc + GST - 1;
-    if (nxt < nchunks) load_chunk(nxt, nxt % GST);
-    cp_async_commit();
-    const double* as = As + (kc % GST) * GK * GLD;
-    const double* bs = Bs + (kc % GST) * GK * GLD;
+    // stage the accumulator tile: Cs[c][r] (column-major, ld GLD), then coalesced C -= Cs
+    double* Cs = gsm;
 #pragma unroll
-    for (int kk = 0; kk < GK; kk += 4) {
-      double a[4], bb[4];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = as[(kk + lc) * GLD + wm + i * 8 + lr];
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = bs[(kk + lc) * GLD + wn + j * 8 + lr];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+        for (int h = 0; h < 2; ++h) Cs[(wn + j * 8 + lc * 2 + h) * GLD + wm + i * 8 + lr] = acc[i][j][h];
+    __syncthreads();
+    double* Cg = A + static_cast<size_t>(col0) * lda + row0;
+    for (int e = tid; e < GT * GT; e += GTHREADS) {
+      const int r = e % GT, c = e / GT;
+      if (r < rows && c < cols) {
+        double* dst = Cg + static_cast<size_t>(c) * lda + r;
+        *dst = *dst - Cs[c * GLD + r];
+      }
     }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-  // stage the accumulator tile: Cs[c][r] (column-major, ld GLD), then coalesced C -= Cs
-  double* Cs = gsm;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) Cs[(wn + j * 8 + lc * 2 + h) * GLD + wm + i * 8 + lr] = acc[i][j][h];
-  __syncthreads();
-  double* Cg = A + static_cast<size_t>(col0) * lda + row0;
-  for (int e = tid; e < GT * GT; e += GTHREADS) {
-    const int r = e % GT, c = e / GT;
-    if (r < rows && c < cols) {
-      double* dst = Cg + static_cast<size_t>(c) * lda + r;
-      *dst = *dst - Cs[c * GLD + r];
-    }
+    __syncthreads();  // Cs aliases the pipeline buffers of the next tile
   }
 }
 
@@ -638,12 +667,42 @@ void trsv_blocked(const double* L, int n, double* x, bool trans, cudaStream_t s)
 int launches_issued() { return g_launches; }
 void count_launch(int n) { g_launches += n; }
 
+// Side stream + events for the look-ahead schedule, created once per host thread and device.
+struct LookaheadCtx {
+  int device = -1;
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> chain_done, rest_done;
+  void ensure(int dev, size_t panels) {
+    if (device != dev) {
+      // contexts of other devices are left to process teardown; a handle is bound to one device for its lifetime
+      device = dev;
+      side = nullptr;
+      chain_done.clear();
+      rest_done.clear();
+    }
+    if (!side) CMOE_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    while (chain_done.size() < panels) {
+      cudaEvent_t a, b;
+      CMOE_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      CMOE_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      chain_done.push_back(a);
+      rest_done.push_back(b);
+    }
+  }
+};
+
+// Right-looking blocked Cholesky with two-level blocking and one-panel look-ahead:
+//   for every 256-column outer panel: four 64-column steps (fused diagonal factorisation + panel solve, then the
+//   DMMA update of the columns still inside the outer panel), then the 128x128-tiled DMMA trailing update, split into
+//   (a) the next outer panel's columns — on the main stream, the factorisation chain continues as soon as it is done —
+//   and (b) everything to the right of it, on a side stream confined to a subset of the SMs so that it overlaps the
+//   next panel's latency-bound chain.  (a) of panel p waits for (b) of panel p-1 (both touch the same columns).
 void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
   constexpr int W = 256;  // outer panel width (4 inner blocks of NB)
   const size_t smem = 2 * NB * LDT * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  const size_t smem_panel = (static_cast<size_t>(NB) * LTS + 64 + NB + NB * (NB + 1)) * sizeof(double);
+  const size_t smem_panel = (static_cast<size_t>(NB) * LTS + NB + 128 + NB + NB * (NB + 1)) * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_panel)));
   CMOE_CUDA(cudaFuncSetAttribute(potrf_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -658,7 +717,16 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
   int* loaded = loaded_buf.p;
   CMOE_CUDA(cudaMemsetAsync(loaded, 0, nsteps * sizeof(int), s));
   const int fast_chain = n > 4 * NB ? 1 : 0;  // small systems keep IEEE sqrt / divide (exact known-answer cases)
-  for (int p0 = 0; p0 < n; p0 += W) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int npanels = (n + W - 1) / W;
+  const bool lookahead = npanels >= 4;  // below ~1000 rows the trailing updates are too small to be worth overlapping
+  static thread_local LookaheadCtx ctx;
+  if (lookahead) ctx.ensure(dev, npanels);
+  const int rest_ctas = std::max(32, sms - 40);  // SMs left to the chain kernels while (b) runs
+  int last_rest = -1;
+  for (int p0 = 0, pi = 0; p0 < n; p0 += W, ++pi) {
     const int pw = min(W, n - p0);         // this panel's width
     const int pend = p0 + pw;
     for (int k0 = p0; k0 < pend; k0 += NB) {
@@ -682,10 +750,32 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
     const int rem = n - pend;
     if (rem > 0 && pw == W) {
       const int tiles = (rem + GT - 1) / GT;
-      dmma_gemm_kernel<<<tiles * (tiles + 1) / 2, GTHREADS, smem_gemm, s>>>(A, n, n, p0, W, flag);
-      count_launch();
+      constexpr int kNextTiles = W / GT;  // column tiles of the next outer panel
+      if (!lookahead || tiles <= kNextTiles) {
+        if (last_rest >= 0) {
+          CMOE_CUDA(cudaStreamWaitEvent(s, ctx.rest_done[last_rest], 0));
+          last_rest = -1;
+        }
+        dmma_gemm_kernel<<<tiles * (tiles + 1) / 2, GTHREADS, smem_gemm, s>>>(A, n, n, p0, W, 0, tiles, flag);
+        count_launch();
+      } else {
+        CMOE_CUDA(cudaEventRecord(ctx.chain_done[pi], s));
+        if (last_rest >= 0) CMOE_CUDA(cudaStreamWaitEvent(s, ctx.rest_done[last_rest], 0));
+        const int next_total = kNextTiles * tiles - kNextTiles * (kNextTiles - 1) / 2;
+        dmma_gemm_kernel<<<next_total, GTHREADS, smem_gemm, s>>>(A, n, n, p0, W, 0, kNextTiles, flag);
+        count_launch();
+        CMOE_CUDA(cudaStreamWaitEvent(ctx.side, ctx.chain_done[pi], 0));
+        const int rt = tiles - kNextTiles;
+        const int rest_total = rt * (rt + 1) / 2;
+        dmma_gemm_kernel<<<std::min(rest_total, rest_ctas), GTHREADS, smem_gemm, ctx.side>>>(A, n, n, p0, W, kNextTiles,
+                                                                                            tiles, flag);
+        count_launch();
+        CMOE_CUDA(cudaEventRecord(ctx.rest_done[pi], ctx.side));
+        last_rest = pi;
+      }
     }
   }
+  if (last_rest >= 0) CMOE_CUDA(cudaStreamWaitEvent(s, ctx.rest_done[last_rest], 0));
   CMOE_CUDA(cudaGetLastError());
   CMOE_CUDA(cudaStreamSynchronize(s));  // the counter scratch is freed on return
 }
