@@ -278,26 +278,48 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
   const int row0 = t0 + ti * NB;
   const int rows = min(NB, n - row0);
   const double* Asrc = A + static_cast<size_t>(k0) * lda + row0;
-  load_tile(As, Asrc, lda, rows, nb);
   int col0 = 0, cols = 0;
-  if (mode == 0) {
-    load_tile(Bs, invL, NB, nb, nb);  // B(n, k) = invL(n, k): C = A * invL^T
-    cols = nb;
-  } else {
-    col0 = t0 + tj * NB;
-    cols = min(NB, n - col0);
-    load_tile(Bs, A + static_cast<size_t>(k0) * lda + col0, lda, cols, nb);
-  }
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
   const int lr = lane >> 2, lc = lane & 3;
   double acc[4][4][2];
+  if (mode == 0) {
+    load_tile(As, Asrc, lda, rows, nb);
+    load_tile(Bs, invL, NB, nb, nb);  // B(n, k) = invL(n, k): C = A * invL^T
+    cols = nb;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  } else {
+    // both operand tiles in flight at once (LDGSTS), and the C tile is fetched while they land: the launch is
+    // latency-bound (one 64x64x64 product per CTA), so the three global round trips must overlap
+    col0 = t0 + tj * NB;
+    cols = min(NB, n - col0);
+    const double* Bsrc = A + static_cast<size_t>(k0) * lda + col0;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+      const int r = e % NB, c = e / NB;
+      const bool oka = r < rows && c < nb, okb = r < cols && c < nb;
+      cp_async8(As + c * LDT + r, oka ? Asrc + static_cast<size_t>(c) * lda + r : Asrc, oka);
+      cp_async8(Bs + c * LDT + r, okb ? Bsrc + static_cast<size_t>(c) * lda + r : Bsrc, okb);
+    }
+    cp_async_commit();
+    // accumulate -A B^T on top of the old C: acc starts at -C so that the epilogue is a plain store of -acc
+    const double* Csrc = A + static_cast<size_t>(col0) * lda + row0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = wm + i * 8 + lr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = wn + j * 8 + lc * 2 + h;
+          acc[i][j][h] = (r < rows && c < cols) ? -Csrc[static_cast<size_t>(c) * lda + r] : 0.0;
+        }
+    }
+    cp_async_wait<0>();
+  }
+  __syncthreads();
 
 #pragma unroll 4
   for (int kk = 0; kk < NB; kk += 4) {
@@ -330,11 +352,7 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
         const int c = wn + j * 8 + lc * 2 + h;
         if (r < rows && c < cols) {
           double* dst = Cdst + static_cast<size_t>(c) * ldc + r;
-          if (mode == 0) {
-            *dst = acc[i][j][h];
-          } else {
-            *dst = *dst - acc[i][j][h];
-          }
+          *dst = (mode == 0) ? acc[i][j][h] : -acc[i][j][h];
         }
       }
     }
@@ -564,12 +582,16 @@ int g_launches = 0;
 // --------------------------------------------------------------------------------------------------------------
 constexpr int VB = 128;
 
+// Solves the VB x VB diagonal block for one right-hand side.  Four 32-unknown sub-blocks in sequence: the owning warp
+// solves its sub-block out of registers (lane i holds unknown i and its row of the 32x32 triangle; each solved unknown
+// is broadcast by shuffle — no block barrier inside the recurrence), then the warps that are still waiting fold the 32
+// new unknowns into their right-hand sides.  Four barriers per block instead of one per unknown.
 template <bool TRANS>
 __global__ void __launch_bounds__(VB) trsv_diag_kernel(const double* __restrict__ L, int n, int b0,
                                                        double* __restrict__ x) {
   extern __shared__ double S[];  // [VB][VB+1] lower block of L (row r, col c at S[r*(VB+1)+c])
   __shared__ double xs[VB];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int nb = min(VB, n - b0);
 #pragma unroll 8
   for (int c = 0; c < VB; ++c) {
@@ -580,18 +602,30 @@ __global__ void __launch_bounds__(VB) trsv_diag_kernel(const double* __restrict_
   double v = (t < nb) ? x[b0 + t] : 0.0;
   const double rd = (t < nb) ? 1.0 / L[static_cast<size_t>(b0 + t) * n + b0 + t] : 0.0;  // off the critical chain
   __syncthreads();
-  for (int s = 0; s < nb; ++s) {
-    const int c = TRANS ? (nb - 1 - s) : s;
-    if (t == c) {
-      v = v * rd;
-      xs[c] = v;
+#pragma unroll 1
+  for (int sb = 0; sb < VB / 32; ++sb) {
+    const int q = TRANS ? (VB / 32 - 1 - sb) : sb;
+    if (warp == q) {
+      double lr[32];  // forward: L[32q+lane][32q+j] (j < lane);  backward: L[32q+j][32q+lane] (j > lane)
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        lr[j] = TRANS ? S[(32 * q + j) * (VB + 1) + 32 * q + lane] : S[(32 * q + lane) * (VB + 1) + 32 * q + j];
+#pragma unroll
+      for (int st = 0; st < 32; ++st) {
+        const int c = TRANS ? (31 - st) : st;
+        const double xc = __shfl_sync(0xffffffffu, v * rd, c);
+        if (lane == c) v = xc;
+        if (TRANS ? (lane < c) : (lane > c)) v = v - xc * lr[c];
+      }
+      xs[32 * q + lane] = v;
     }
     __syncthreads();
-    const double xc = xs[c];
-    if (!TRANS) {
-      if (t > c && t < nb) v = v - xc * S[t * (VB + 1) + c];
-    } else {
-      if (t < c) v = v - S[c * (VB + 1) + t] * xc;
+    if (TRANS ? (warp < q) : (warp > q)) {
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        const double l = TRANS ? S[(32 * q + c) * (VB + 1) + t] : S[t * (VB + 1) + 32 * q + c];
+        v = v - xs[32 * q + c] * l;
+      }
     }
   }
   if (t < nb) x[b0 + t] = v;

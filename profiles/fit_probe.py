@@ -12,4 +12,6 @@ X = rng.uniform(size=(N, d))
 y = np.sin(3 * X).sum(axis=1) + 0.1 * rng.standard_normal(N)
 gp = capi.GaussianProcess(capi.SQUARE_EXPONENTIAL, 1.0, np.full(d, 0.5), X, y, [1e-2])
 print("fit usec (cov, chol, solve):", gp.fit_timings_usec())
+gp2 = capi.GaussianProcess(capi.SQUARE_EXPONENTIAL, 1.0, np.full(d, 0.5), X, y, [1e-2])
+print("second fit in the same process (kernels loaded) usec (cov, chol, solve):", gp2.fit_timings_usec())
 print("warm: cov usec", gp.bench_cov_build(20), " chol usec", gp.bench_cholesky(5))
