@@ -533,6 +533,7 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
     ap.recC = pl.dRecC.p;
     ap.outX = pl.dOutX.p;
     ap.outH = pl.dOutH.p;
+    ap.fast_exp = pl.use_smem ? 1 : 0;
     ap.R = pl.dR.p;
     ap.Gu = pl.dGu.p;
     ap.GkB = pl.dGkB.p;

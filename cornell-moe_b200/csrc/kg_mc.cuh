@@ -58,6 +58,7 @@ struct KgMcParams {
 
 struct KgAccParams {
   int N, U, dim, num_mc;
+  int fast_exp;  // 1: the range contract of the table exp holds (see kFastPathRadius)
   double alpha;
   const double* Xt;     // [N][DIM]
   const double* Xu;     // [nc][U][DIM+2]
@@ -880,8 +881,13 @@ __global__ void __launch_bounds__(kMcThreads, 2) kg_mc_gen_kernel(const __grid_c
 //   Gu[u][d]  = sum_i c_iu kb(Xu_u, x*_i) x~*_id ,  GkB[u] = sum_i c_iu kb(Xu_u, x*_i)
 // grid (row blocks, candidates); one thread per row.
 // ---------------------------------------------------------------------------------------------------------------
-template <int KERNEL, int DIM, int QP>
-__global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgAccParams prm) {
+constexpr int kAccTile = 64;  // samples per shared-memory tile of kg_acc_kernel
+
+// One thread per row of [training points; union points]; the samples' records (minimiser, c, -|x*|^2/2) stream through
+// shared memory in double-buffered tiles (LDGSTS, 16-byte chunks) and are read back as warp-broadcast LDS.128.
+// TAB selects the table exp under the fast path's range contract (kFastPathRadius).
+template <int KERNEL, int DIM, int QP, bool TAB>
+__device__ __forceinline__ void kg_acc_body(const KgAccParams& prm, double* __restrict__ sbuf) {
   const int cand = blockIdx.y;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = prm.N, U = prm.U;
@@ -916,39 +922,74 @@ __global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgA
   const double* cs = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
   const double* hs = prm.outH + static_cast<size_t>(cand) * prm.num_mc;
   const int uu = is_u ? (row - N) : 0;
-  // every lane reads the same sample record: warp-broadcast 16-byte loads through the read-only path
+  constexpr int TS = kAccTile;
+  constexpr int kBuf = TS * (DIM + QP + 1);  // doubles per buffer: [TS][DIM] | [TS][QP] | [TS]
+  const int num_mc = prm.num_mc;
+  const int ntiles = (num_mc + TS - 1) / TS;
+  auto load_tile = [&](int tile, int buf) {
+    double* sx = sbuf + buf * kBuf;
+    double* sc = sx + TS * DIM;
+    double* sh = sc + TS * QP;
+    const int i0 = tile * TS;
+    for (int e = threadIdx.x; e < TS * DIM / 2; e += blockDim.x) {
+      const bool ok = i0 + (2 * e) / DIM < num_mc;
+      cp_async16(sx + 2 * e, ok ? xs + static_cast<size_t>(i0) * DIM + 2 * e : xs, ok);
+    }
+    for (int e = threadIdx.x; e < TS * QP / 2; e += blockDim.x) {
+      const bool ok = i0 + (2 * e) / QP < num_mc;
+      cp_async16(sc + 2 * e, ok ? cs + static_cast<size_t>(i0) * QP + 2 * e : cs, ok);
+    }
+    for (int e = threadIdx.x; e < TS; e += blockDim.x) {
+      const bool ok = i0 + e < num_mc;
+      cp_async8(sh + e, ok ? hs + i0 + e : hs, ok);
+    }
+  };
+  load_tile(0, 0);
+  cp_async_commit();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) load_tile(tile + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const double* sx = sbuf + buf * kBuf;
+    const double* sc = sx + TS * DIM;
+    const double* sh = sc + TS * QP;
+    const int cnt = min(TS, num_mc - tile * TS);
 #pragma unroll 2
-  for (int i = 0; i < prm.num_mc; ++i) {
-    double xi[DIM], ci[QP];
+    for (int i = 0; i < cnt; ++i) {
+      double xi[DIM], ci[QP];
 #pragma unroll
-    for (int d = 0; d < DIM; d += 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(xs + static_cast<size_t>(i) * DIM + d));
-      xi[d] = v.x;
-      xi[d + 1] = v.y;
+      for (int d = 0; d < DIM; d += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(sx + i * DIM + d);
+        xi[d] = v.x;
+        xi[d + 1] = v.y;
+      }
+#pragma unroll
+      for (int a = 0; a < QP; a += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(sc + i * QP + a);
+        ci[a] = v.x;
+        ci[a + 1] = v.y;
+      }
+      double dot = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) dot = fma(xi[d], xr[d], dot);
+      double kv, kb;
+      kernel_pair<KERNEL, TAB>(dot, pk0, sh[i], prm.alpha, kv, kb);
+#pragma unroll
+      for (int a = 0; a < QP; ++a) acc[a] = fma(ci[a], kv, acc[a]);
+      if (is_u) {
+        double cu = 0.0;
+#pragma unroll
+        for (int a = 0; a < QP; ++a)
+          if (a == uu) cu = ci[a];
+        const double w = cu * kb;
+        gkb += w;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gu[d] = fma(w, xi[d], gu[d]);
+      }
     }
-#pragma unroll
-    for (int a = 0; a < QP; a += 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(cs + static_cast<size_t>(i) * QP + a));
-      ci[a] = v.x;
-      ci[a + 1] = v.y;
-    }
-    double dot = 0.0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) dot = fma(xi[d], xr[d], dot);
-    double kv, kb;
-    kernel_pair<KERNEL>(dot, pk0, __ldg(hs + i), prm.alpha, kv, kb);
-#pragma unroll
-    for (int a = 0; a < QP; ++a) acc[a] = fma(ci[a], kv, acc[a]);
-    if (is_u) {
-      double cu = 0.0;
-#pragma unroll
-      for (int a = 0; a < QP; ++a)
-        if (a == uu) cu = ci[a];
-      const double w = cu * kb;
-      gkb += w;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) gu[d] = fma(w, xi[d], gu[d]);
-    }
+    __syncthreads();  // the buffer is refilled two tiles later
   }
   if (!active) return;
   double* R = prm.R + static_cast<size_t>(cand) * QP * (N + U);
@@ -959,6 +1000,19 @@ __global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgA
 #pragma unroll
     for (int d = 0; d < DIM; ++d) prm.Gu[(static_cast<size_t>(cand) * U + uu) * DIM + d] = gu[d];
   }
+}
+
+template <int KERNEL, int DIM, int QP>
+__global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgAccParams prm) {
+  extern __shared__ __align__(16) double acc_smem[];
+#if CMOE_EXP_TABLE
+  if (prm.fast_exp) {
+    exp_table_stage();
+    kg_acc_body<KERNEL, DIM, QP, true>(prm, acc_smem);
+    return;
+  }
+#endif
+  kg_acc_body<KERNEL, DIM, QP, false>(prm, acc_smem);
 }
 
 // launchers instantiated per (DIM) translation unit
@@ -989,7 +1043,13 @@ void launch_kg_mc_gen(const KgMcParams& p, dim3 grid, size_t, cudaStream_t s) {
 }
 template <int KERNEL, int DIM, int QP>
 void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {
-  kg_acc_kernel<KERNEL, DIM, QP><<<grid, 128, 0, s>>>(p);
+  const size_t smem = 2 * static_cast<size_t>(kAccTile) * (DIM + QP + 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(kg_acc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  kg_acc_kernel<KERNEL, DIM, QP><<<grid, 128, smem, s>>>(p);
 }
 template <int DIM, int QP>
 size_t kg_smem_bytes(int N, int U) {
