@@ -513,6 +513,128 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
   }
 }
 
+// Batched backtracking with derivative observations (SquareExponential): along x + a g the value rows scale as in
+// eval_line and the derivative rows' factor (x~_t - X~_jt) is linear in a, so with
+//     u_j = sum_m a~_jm (x~_t - X~_jt),  v_j = sum_m a~_jm g~_t,  k0_j = k(x, X_j),  G_jk = exp(a_k p_j)
+// the trial values are  E_k [ sum_j k0_j G_jk (a_j0 + u_j) + a_k sum_j k0_j G_jk v_j ]:  S[k] and T[k] below.
+// The (1+g) Q weight FMAs per point — the dominant cost of this path — are paid once per step instead of once per trial.
+template <int DIM, int QP>
+__device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const double* __restrict__ Xt,
+                                              const double* __restrict__ Pk, const double* __restrict__ Xu,
+                                              const double (&xb)[DIM], const double (&gt)[DIM], const double (&c)[QP],
+                                              const double* __restrict__ cl, double alpha_min,
+                                              double (&S)[kLineBatch], double (&T)[kLineBatch], int& pmax_hi) {
+  const int N = prm.N, U = prm.U, g = prm.g, stride = prm.pk_stride;
+  double nq = 0.0, xg = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    nq = fma(xb[d], xb[d], nq);
+    xg = fma(xb[d], gt[d], xg);
+  }
+  const double hq = -0.5 * nq;
+  double ga[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) ga[d] = alpha_min * gt[d];
+  const double xga = -alpha_min * xg;
+  // base coordinates and direction at the derivative indices (compile-time register indexing only)
+  double xm[kMaxG], gm[kMaxG];
+#pragma unroll
+  for (int m = 0; m < kMaxG; ++m) {
+    xm[m] = 0.0;
+    gm[m] = 0.0;
+    if (m < g) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        if (d == prm.derivs[m]) {
+          xm[m] = xb[d];
+          gm[m] = gt[d];
+        }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kLineBatch; ++k) S[k] = T[k] = 0.0;
+  pmax_hi = 0;
+  for (int j = 0; j < N; ++j) {
+    const double* xj = Xt + static_cast<size_t>(j) * DIM;
+    const double* pk = Pk + static_cast<size_t>(j) * stride;
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<false>(xj + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    double dot = 0.0, pj = xga;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      dot = fma(xb[d], xv[d], dot);
+      pj = fma(ga[d], xv[d], pj);
+    }
+    double a0 = __ldg(pk + 1);
+#pragma unroll
+    for (int u = 0; u < QP; ++u) a0 = fma(-__ldg(pk + 2 + u), c[u], a0);
+    double us = 0.0, vs = 0.0;
+#pragma unroll
+    for (int m = 0; m < kMaxG; ++m) {
+      if (m < g) {
+        const double* row = pk + 1 + (m + 1) * (QP + 1);
+        double am = __ldg(row);
+#pragma unroll
+        for (int u = 0; u < QP; ++u) am = fma(-__ldg(row + 1 + u), c[u], am);
+        us = fma(am, xm[m] - __ldg(xj + prm.derivs[m]), us);
+        vs = fma(am, gm[m], vs);
+      }
+    }
+    pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
+    const double k0 = exp_fast(dot + (__ldg(pk) + hq));
+    const double w = k0 * (a0 + us), wv = k0 * vs;
+    double G = exp_fast(pj);
+#pragma unroll
+    for (int k = kLineBatch - 1; k >= 0; --k) {
+      S[k] = fma(w, G, S[k]);
+      T[k] = fma(wv, G, T[k]);
+      if (k > 0) G *= G;
+    }
+  }
+  const int bs = 1 + g;
+  for (int u = 0; u < U; ++u) {
+    const double* xu = Xu + static_cast<size_t>(u) * (DIM + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<false>(xu + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    double dot = 0.0, pj = xga;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      dot = fma(xb[d], xv[d], dot);
+      pj = fma(ga[d], xv[d], pj);
+    }
+    const double a0 = cl[u * bs];
+    double us = 0.0, vs = 0.0;
+#pragma unroll
+    for (int m = 0; m < kMaxG; ++m) {
+      if (m < g) {
+        const double am = cl[u * bs + 1 + m] * prm.inv_len[prm.derivs[m]];
+        us = fma(am, xm[m] - __ldg(xu + prm.derivs[m]), us);
+        vs = fma(am, gm[m], vs);
+      }
+    }
+    pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
+    const double k0 = exp_fast(dot + (__ldg(xu + DIM) + hq));
+    const double w = k0 * (a0 + us), wv = k0 * vs;
+    double G = exp_fast(pj);
+#pragma unroll
+    for (int k = kLineBatch - 1; k >= 0; --k) {
+      S[k] = fma(w, G, S[k]);
+      T[k] = fma(wv, G, T[k]);
+      if (k > 0) G *= G;
+    }
+  }
+}
+
 // TensorProductDomain::LimitUpdate, gpp_domain.cpp:64-104, for one coordinate
 __device__ __forceinline__ double limit_step(double step, double x, double lo, double hi, double mrc) {
   double dist = fmin(x - lo, hi - x);
@@ -551,7 +673,7 @@ template <int KERNEL, int DIM, int QP, bool SMEM, bool GEN>
 __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* __restrict__ Xt,
                                            const double* __restrict__ Pk, const double* __restrict__ Xu, int cand,
                                            int s_begin, int s_end, int* next_sample) {
-  constexpr bool LINE = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) && !GEN;
+  constexpr bool LINE = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL);
   constexpr int ST_SEARCH = LINE ? ST_LINE : ST_TRIAL;  // how a step's backtracking starts
   const int N = prm.N, U = prm.U;
   const double* A = prm.A + static_cast<size_t>(cand) * prm.M * DIM;
@@ -631,7 +753,13 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         gg = fma(gt[d], gt[d], gg);
       }
       constexpr double kTop = static_cast<double>(1 << (kLineBatch - 1));
-      eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax_hi);
+      double T[GEN ? kLineBatch : 1];
+      if (GEN) {
+        eval_line_gen<DIM, QP>(prm, Xt, Pk, Xu, xt, gt, c, cl, alpha_n * (1.0 / kTop), S,
+                               reinterpret_cast<double (&)[kLineBatch]>(T), pmax_hi);
+      } else {
+        eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax_hi);
+      }
       if (state == ST_LINE) {
         n_line += 1;
         // safe iff a_0 |p_j| = 2^(KB-1) |a_min p_j| < 512 for every row: every factor exp(a_k p_j) stays in range
@@ -645,7 +773,8 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
           double ak = alpha_n, a_acc = alpha_n;
 #pragma unroll
           for (int k = 0; k < kLineBatch; ++k) {
-            const double fq = -(prm.mean + exp_fast(-0.5 * ak * ak * gg) * S[k]);
+            const double sk = GEN ? fma(ak, T[GEN ? k : 0], S[k]) : S[k];
+            const double fq = -(prm.mean + exp_fast(-0.5 * ak * ak * gg) * sk);
             // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
             const bool ok = (search + k < 30) && ((fq - fb) > 0.5 * ak * gnorm);
             if (kacc < 0 && ok) {
