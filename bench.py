@@ -252,9 +252,19 @@ def main():
     fp64_fma, fp64_dmma = capi.fp64_peaks(device)
     executed = stats["point_evals"] * flops_point + stats["line_batches"] * flops_line
     achieved = executed / (mc_ms / args.steps * 1e-3) * 1e-12
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write); the capture
+    # ran 256 candidates per launch and the traffic is per-sample records, so it scales with the candidates of a launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_kg_mc_kernel_ncu.json")) as f:
+            cap = json.load(f)
+        traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * len(my) / cap["candidates_per_launch"]
+        traffic_src = "profiles/r1_kg_mc_kernel_ncu.json (ncu --set full, scaled by candidates per launch)"
+    except Exception:
+        pass
     roofline = {"bound": "fp64-fma (vector pipe; neither hbm nor tensor)", "achieved": achieved, "peak": fp64_fma,
-                "unit": "TFLOP/s", "frac": achieved / fp64_fma if fp64_fma else None, "traffic": None,
-                "kernel": "kg_mc_kernel", "kernel_share_of_step": mc_ms / dev_ms,
+                "unit": "TFLOP/s", "frac": achieved / fp64_fma if fp64_fma else None, "traffic": traffic,
+                "traffic_source": traffic_src, "kernel": "kg_mc_kernel", "kernel_share_of_step": mc_ms / dev_ms,
                 "peak_source": "measured live: DFMA chain microbenchmark (cmoe_bench_fp64_peaks)",
                 "reference_evals_per_sample": stats["posterior_evals"] / max(1, stats["mc_samples"]),
                 "point_evals_per_sample": stats["point_evals"] / max(1, stats["mc_samples"]),
