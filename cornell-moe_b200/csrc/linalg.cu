@@ -257,14 +257,17 @@ __device__ __forceinline__ void load_tile(double* __restrict__ T, const double* 
   }
 }
 
+// mode 1 with kdepth > nb: the operand panel is kdepth (a multiple of NB) columns wide starting at column k0, the
+// trailing matrix starts at k0 + kdepth — used for the look-ahead update of the next outer panel's columns, where many
+// small tiles (one wave of 64x64 CTAs, 3 per SM) finish sooner than a few 128x128 ones.
 __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
                                                         const double* __restrict__ invL, int mode, int col_tiles,
-                                                        const int* __restrict__ flag) {
+                                                        const int* __restrict__ flag, int kdepth) {
   extern __shared__ double smem[];
   if (*flag != 0) return;
   double* As = smem;
   double* Bs = smem + NB * LDT;
-  const int t0 = k0 + nb;  // first row/col of the trailing matrix
+  const int t0 = k0 + max(nb, kdepth);  // first row/col of the trailing matrix
   int ti, tj;
   if (mode == 0) {
     ti = blockIdx.x;
@@ -293,17 +296,9 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   } else {
     // both operand tiles in flight at once (LDGSTS), and the C tile is fetched while they land: the launch is
-    // latency-bound (one 64x64x64 product per CTA), so the three global round trips must overlap
+    // latency-bound (one 64x64xK product per CTA), so the three global round trips must overlap
     col0 = t0 + tj * NB;
     cols = min(NB, n - col0);
-    const double* Bsrc = A + static_cast<size_t>(k0) * lda + col0;
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-      const int r = e % NB, c = e / NB;
-      const bool oka = r < rows && c < nb, okb = r < cols && c < nb;
-      cp_async8(As + c * LDT + r, oka ? Asrc + static_cast<size_t>(c) * lda + r : Asrc, oka);
-      cp_async8(Bs + c * LDT + r, okb ? Bsrc + static_cast<size_t>(c) * lda + r : Bsrc, okb);
-    }
-    cp_async_commit();
     // accumulate -A B^T on top of the old C: acc starts at -C so that the epilogue is a plain store of -acc
     const double* Csrc = A + static_cast<size_t>(col0) * lda + row0;
 #pragma unroll
@@ -317,21 +312,37 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
           acc[i][j][h] = (r < rows && c < cols) ? -Csrc[static_cast<size_t>(c) * lda + r] : 0.0;
         }
     }
-    cp_async_wait<0>();
   }
-  __syncthreads();
+  const int nchunks = (mode == 0) ? 1 : max(1, kdepth / NB);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (mode != 0) {
+      if (ch > 0) __syncthreads();  // everybody is done with the previous chunk's tiles
+      const int kw = (kdepth > nb) ? NB : nb;  // columns of this chunk
+      const double* Ac = Asrc + static_cast<size_t>(ch) * NB * lda;
+      const double* Bc = A + static_cast<size_t>(k0 + ch * NB) * lda + col0;
+      for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+        const int r = e % NB, c = e / NB;
+        const bool oka = r < rows && c < kw, okb = r < cols && c < kw;
+        cp_async8(As + c * LDT + r, oka ? Ac + static_cast<size_t>(c) * lda + r : Ac, oka);
+        cp_async8(Bs + c * LDT + r, okb ? Bc + static_cast<size_t>(c) * lda + r : Bc, okb);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    __syncthreads();
 
 #pragma unroll 4
-  for (int kk = 0; kk < NB; kk += 4) {
-    double a[4], b[4];
+    for (int kk = 0; kk < NB; kk += 4) {
+      double a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = As[(kk + lc) * LDT + wm + i * 8 + lr];
+      for (int i = 0; i < 4; ++i) a[i] = As[(kk + lc) * LDT + wm + i * 8 + lr];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + lc) * LDT + wn + j * 8 + lr];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + lc) * LDT + wn + j * 8 + lr];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
   }
 
   // epilogue
@@ -777,7 +788,7 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
       // inner trailing update: only the columns that still belong to this outer panel
       const int col_tiles = (pend - (k0 + nb) + NB - 1) / NB;
       if (rem > 0 && col_tiles > 0) {
-        dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, nullptr, 1, col_tiles, flag);
+        dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, nullptr, 1, col_tiles, flag, nb);
         count_launch();
       }
     }
@@ -795,8 +806,10 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
       } else {
         CMOE_CUDA(cudaEventRecord(ctx.chain_done[pi], s));
         if (last_rest >= 0) CMOE_CUDA(cudaStreamWaitEvent(s, ctx.rest_done[last_rest], 0));
-        const int next_total = kNextTiles * tiles - kNextTiles * (kNextTiles - 1) / 2;
-        dmma_gemm_kernel<<<next_total, GTHREADS, smem_gemm, s>>>(A, n, n, p0, W, 0, kNextTiles, flag);
+        // (a): one wave of 64x64 tiles, K = 256 in four chunks — finishes in a fraction of the time a few 128x128
+        // CTAs need, and this update sits on the critical path of the chain
+        const int nrt = (rem + NB - 1) / NB, nct = std::min(W / NB, nrt);
+        dmma_tile_kernel<<<nrt * nct, 128, smem, s>>>(A, n, n, p0, NB, nullptr, 1, nct, flag, W);
         count_launch();
         CMOE_CUDA(cudaStreamWaitEvent(ctx.side, ctx.chain_done[pi], 0));
         const int rt = tiles - kNextTiles;
