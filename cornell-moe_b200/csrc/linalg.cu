@@ -684,6 +684,165 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
   if (lane == 0) x[i] = x[i] - acc;
 }
 
+// --------------------------------------------------------------------------------------------------------------
+// Single-launch triangular solve for one right-hand side ("chained" trsv): one CTA per block of VB unknowns, all
+// co-resident.  CTA b accumulates  sum_j L_bj x_j  over the blocks it depends on as soon as each x_j is published
+// (ready[j], release/acquire through L2), then solves its diagonal block with the warp-level recurrence and publishes
+// x_b.  The critical path per block is one 128x128 matrix-vector product + one diagonal solve instead of two dependent
+// kernel launches, and the off-critical products run ahead while the CTA waits.  Deadlock-free: CTA b only waits on
+// blocks that wait on strictly fewer blocks, and every CTA is resident (grid <= #SMs, checked by the host).  A bounded
+// spin turns a lost dependency into an error code instead of a hang.
+// --------------------------------------------------------------------------------------------------------------
+constexpr int CT = 512;  // threads of the chained solver
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_ready(const int* flag, int* abort_flag) {
+  for (unsigned spins = 0; ld_acquire(flag) == 0; ++spins) {
+    if (spins > (1u << 22)) {  // ~1 s: far beyond any legitimate wait
+      atomicExch(abort_flag, 1);
+      break;
+    }
+    __nanosleep(20);
+  }
+}
+
+template <bool TRANS>
+__global__ void __launch_bounds__(CT) trsv_chain_kernel(const double* __restrict__ L, int n, const double* __restrict__ rhs,
+                                                        double* __restrict__ xout, int* __restrict__ ready,
+                                                        int* __restrict__ abort_flag, int nblk) {
+  extern __shared__ double S[];  // [VB][VB+1] lower diagonal block (row r, col c at S[r*(VB+1)+c])
+  __shared__ double xs[VB];
+  __shared__ double part[CT / VB][VB];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = TRANS ? (nblk - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
+  const int b0 = b * VB, nb = min(VB, n - b0);
+  // diagonal block: thread (r, quarter) loads 32 columns of its row
+  {
+    const int r = t & (VB - 1), q = t >> 7;
+#pragma unroll 8
+    for (int c = q * 32; c < q * 32 + 32; ++c) {
+      double v = 0.0;
+      if (r < nb && c <= r) v = L[static_cast<size_t>(b0 + c) * n + b0 + r];
+      S[r * (VB + 1) + c] = v;
+    }
+  }
+  double v = 0.0;
+  if (!TRANS) {
+    // row r = t & 127, column quarter q of every dependency block: coalesced down the columns
+    const int r = t & (VB - 1), q = t >> 7;
+    double acc = 0.0;
+    for (int j = 0; j < b; ++j) {
+      wait_ready(ready + j, abort_flag);
+      const double* col = L + static_cast<size_t>(j * VB + q * 32) * n + b0 + r;
+      const double* xj = xout + j * VB + q * 32;
+      if (r < nb) {
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) acc = fma(col[static_cast<size_t>(c) * n], __ldcg(xj + c), acc);
+      }
+    }
+    part[q][r] = acc;
+    __syncthreads();
+    if (t < VB) v = (t < nb) ? rhs[b0 + t] - ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])) : 0.0;
+  } else {
+    // warp w owns columns 8w..8w+7 of this block; lanes run down the rows of every dependency block (contiguous)
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+    for (int j = nblk - 1; j > b; --j) {
+      wait_ready(ready + j, abort_flag);
+      const int j0 = j * VB, jn = min(VB, n - j0);
+      double xr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xr[k] = (lane + 32 * k < jn) ? __ldcg(xout + j0 + lane + 32 * k) : 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = warp * 8 + i;
+        if (c < nb) {
+          const double* col = L + static_cast<size_t>(b0 + c) * n + j0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (lane + 32 * k < jn) acc[i] = fma(col[lane + 32 * k], xr[k], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double sum = warp_sum(acc[i]);
+      if (lane == 0) part[0][warp * 8 + i] = sum;
+    }
+    __syncthreads();
+    if (t < VB) v = (t < nb) ? rhs[b0 + t] - part[0][t] : 0.0;
+  }
+  const double rd = (t < nb) ? 1.0 / L[static_cast<size_t>(b0 + t) * n + b0 + t] : 0.0;
+  __syncthreads();  // S complete
+  // warp-level solve of the diagonal block by the first VB threads (see trsv_diag_kernel); all threads hit the barriers
+#pragma unroll 1
+  for (int sb = 0; sb < VB / 32; ++sb) {
+    const int q = TRANS ? (VB / 32 - 1 - sb) : sb;
+    if (t < VB && warp == q) {
+      double lr[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        lr[j] = TRANS ? S[(32 * q + j) * (VB + 1) + 32 * q + lane] : S[(32 * q + lane) * (VB + 1) + 32 * q + j];
+#pragma unroll
+      for (int st = 0; st < 32; ++st) {
+        const int c = TRANS ? (31 - st) : st;
+        const double xc = __shfl_sync(0xffffffffu, v * rd, c);
+        if (lane == c) v = xc;
+        if (TRANS ? (lane < c) : (lane > c)) v = v - xc * lr[c];
+      }
+      xs[32 * q + lane] = v;
+    }
+    __syncthreads();
+    if (t < VB && (TRANS ? (warp < q) : (warp > q))) {
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        const double l = TRANS ? S[(32 * q + c) * (VB + 1) + t] : S[t * (VB + 1) + 32 * q + c];
+        v = v - xs[32 * q + c] * l;
+      }
+    }
+  }
+  if (t < nb) xout[b0 + t] = v;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) st_release(ready + b, 1);
+}
+
+// returns false if the chained kernel cannot be used (more blocks than SMs)
+bool trsv_chained(const double* L, int n, double* x, bool trans, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nblk = (n + VB - 1) / VB;
+  if (nblk > sms) return false;
+  const size_t smem = static_cast<size_t>(VB) * (VB + 1) * sizeof(double);
+  CMOE_CUDA(cudaFuncSetAttribute(trsv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CMOE_CUDA(cudaFuncSetAttribute(trsv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  DevBuf<int> flags(nblk + 1);
+  DevBuf<double> out(n);
+  CMOE_CUDA(cudaMemsetAsync(flags.p, 0, (nblk + 1) * sizeof(int), s));
+  if (trans) {
+    trsv_chain_kernel<true><<<nblk, CT, smem, s>>>(L, n, x, out.p, flags.p, flags.p + nblk, nblk);
+  } else {
+    trsv_chain_kernel<false><<<nblk, CT, smem, s>>>(L, n, x, out.p, flags.p, flags.p + nblk, nblk);
+  }
+  count_launch();
+  CMOE_CUDA(cudaGetLastError());
+  CMOE_CUDA(cudaMemcpyAsync(x, out.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  int aborted = 0;
+  CMOE_CUDA(cudaMemcpyAsync(&aborted, flags.p + nblk, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaStreamSynchronize(s));  // scratch is freed on return
+  if (aborted) throw Error(CMOE_ERR_RUNTIME, "chained triangular solve lost a dependency (internal error)");
+  return true;
+}
+
 void trsv_blocked(const double* L, int n, double* x, bool trans, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(VB) * (VB + 1) * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(trsv_diag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -830,7 +989,10 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
 void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s) {
   if (n == 0 || nrhs == 0) return;
   if (nrhs <= 4 && n >= 1024) {
-    for (int r = 0; r < nrhs; ++r) trsv_blocked(L, n, X + static_cast<size_t>(r) * ldx, trans, s);
+    for (int r = 0; r < nrhs; ++r) {
+      double* xr = X + static_cast<size_t>(r) * ldx;
+      if (!trsv_chained(L, n, xr, trans, s)) trsv_blocked(L, n, xr, trans, s);
+    }
     return;
   }
   const int grid = (nrhs + kTrsmNB - 1) / kTrsmNB;
