@@ -293,6 +293,8 @@ def main():
         Xl = rng.uniform(size=(Nl, dl))
         yl = np.sin(3 * Xl).sum(axis=1) + 0.1 * rng.standard_normal(Nl)
         gpl = capi.GaussianProcess(capi.SQUARE_EXPONENTIAL, 1.0, np.full(dl, 0.5), Xl, yl, [1e-2], device=device)
+        del gpl  # first fit of the process = kernel loading; the reported fit is the second one
+        gpl = capi.GaussianProcess(capi.SQUARE_EXPONENTIAL, 1.0, np.full(dl, 0.5), Xl, yl, [1e-2], device=device)
         t_cov = gpl.bench_cov_build(20)
         t_chol = gpl.bench_cholesky(3)
         cov_bytes = 4.0 * Nl * (Nl + 1) + 8.0 * Nl * dl
@@ -302,7 +304,7 @@ def main():
             "cholesky_N5000": {"bound": "tensor (FP64 DMMA)", "usec": t_chol, "achieved": Nl ** 3 / 3.0 / t_chol * 1e-6,
                                "peak": fp64_dmma, "unit": "TFLOP/s", "frac": Nl ** 3 / 3.0 / t_chol * 1e-6 / fp64_dmma,
                                "peak_source": "measured live: DMMA m8n8k4 microbenchmark"},
-            "gp_fit_N5000_usec": [float(x) for x in gpl.fit_timings_usec()]}
+            "gp_fit_N5000_usec_cov_chol_solve": [float(x) for x in gpl.fit_timings_usec()]}
 
     if not args.no_cpu_baseline and world == 1:
         try:
