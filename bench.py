@@ -133,12 +133,17 @@ def main():
         if rank != 0:
             return
         backend = cpu_reference_step()
-        threads = backend.max_threads()
         best = best_so_far_from_cpu(backend, wl)
+        # give the reference its best thread count: all hardware threads or one per physical core (SMT often hurts
+        # this FP64-heavy loop); calibrated on a short run, which doubles as the warm-up
+        tmax = backend.max_threads()
+        trial = {}
+        for tt in sorted({tmax, max(1, tmax // 2)}):
+            cc = np.resize(wl["cands"], (tt,) + wl["cands"].shape[1:])
+            trial[tt] = run_cpu(backend, wl, cc, 64, tt, best)[0]
+        threads = max(trial, key=trial.get)
         sample_c, sample_mc = threads, 256
         cands = wl["cands"][:sample_c] if sample_c <= len(wl["cands"]) else np.resize(wl["cands"], (sample_c,) + wl["cands"].shape[1:])
-        for _ in range(min(args.warmup, 1)):
-            run_cpu(backend, wl, cands, 64, threads, best)
         vals = [run_cpu(backend, wl, cands, sample_mc, threads, best) for _ in range(args.steps)]
         total_t = sum(v[1] for v in vals)
         value = sample_c * sample_mc * args.steps / total_t
