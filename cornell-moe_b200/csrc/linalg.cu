@@ -237,9 +237,12 @@ __global__ void __launch_bounds__(PT) potrf_panel_kernel(double* __restrict__ A,
 }
 
 // --------------------------------------------------------------------------------------------------------------
-// DMMA tile product:  C(64x64) = alpha * A(64xNB) * B(64xNB)^T + beta * C  with A, B, C blocks of one matrix.
-//   mode 0 (panel):  C = A_ik <- A_ik * inv(L_kk)^T            (B = invL scratch, beta = 0, in place)
-//   mode 1 (syrk):   C = A_ij <- A_ij - A_ik * A_jk^T, i >= j  (lower-triangular tile grid)
+// DMMA tile update:  C(64x64) -= A(64xK) * B(64xK)^T  with A, B, C blocks of one matrix, lower-triangular tile grid
+// (row tiles x col_tiles; tiles above the diagonal exit).  The operand panel is the `kdepth` columns starting at k0
+// (in chunks of NB); the trailing matrix starts right after it.  Two uses:
+//   * inner update of a 64-column step (kdepth = nb <= 64), restricted to the columns still inside the outer panel;
+//   * look-ahead update of the next outer panel's columns (kdepth = 256): many small tiles (one wave, 3 CTAs/SM)
+//     finish sooner than a few 128x128 ones, and this update sits on the critical path of the chain.
 // 4 warps, each owning a 32x32 sub-tile = 4x4 m8n8k4 fragments.
 // --------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -248,89 +251,51 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                : "d"(a), "d"(b));
 }
 
-// loads a (rows x NB) block whose (r, c) element sits at src[c*ld + r] into smem T[c*LDT + r], zero padded
-__device__ __forceinline__ void load_tile(double* __restrict__ T, const double* __restrict__ src, int ld, int rows,
-                                          int cols) {
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e % NB, c = e / NB;
-    T[c * LDT + r] = (r < rows && c < cols) ? src[static_cast<size_t>(c) * ld + r] : 0.0;
-  }
-}
-
-// mode 1 with kdepth > nb: the operand panel is kdepth (a multiple of NB) columns wide starting at column k0, the
-// trailing matrix starts at k0 + kdepth — used for the look-ahead update of the next outer panel's columns, where many
-// small tiles (one wave of 64x64 CTAs, 3 per SM) finish sooner than a few 128x128 ones.
 __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
-                                                        const double* __restrict__ invL, int mode, int col_tiles,
-                                                        const int* __restrict__ flag, int kdepth) {
+                                                        int col_tiles, const int* __restrict__ flag, int kdepth) {
   extern __shared__ double smem[];
   if (*flag != 0) return;
   double* As = smem;
   double* Bs = smem + NB * LDT;
   const int t0 = k0 + max(nb, kdepth);  // first row/col of the trailing matrix
-  int ti, tj;
-  if (mode == 0) {
-    ti = blockIdx.x;
-    tj = 0;
-  } else {
-    // rectangular grid (row tiles x the col tiles that remain inside the outer panel); keep the lower triangle
-    ti = blockIdx.x / col_tiles;
-    tj = blockIdx.x % col_tiles;
-    if (tj > ti) return;
-  }
-  const int row0 = t0 + ti * NB;
-  const int rows = min(NB, n - row0);
+  const int ti = blockIdx.x / col_tiles, tj = blockIdx.x % col_tiles;
+  if (tj > ti) return;
+  const int row0 = t0 + ti * NB, col0 = t0 + tj * NB;
+  const int rows = min(NB, n - row0), cols = min(NB, n - col0);
   const double* Asrc = A + static_cast<size_t>(k0) * lda + row0;
-  int col0 = 0, cols = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
   const int lr = lane >> 2, lc = lane & 3;
+  // accumulate +A B^T on top of -C: the epilogue is then a plain store of -acc, and the C tile is fetched while the
+  // operand tiles land (the launch is latency-bound: the global round trips must overlap)
   double acc[4][4][2];
-  if (mode == 0) {
-    load_tile(As, Asrc, lda, rows, nb);
-    load_tile(Bs, invL, NB, nb, nb);  // B(n, k) = invL(n, k): C = A * invL^T
-    cols = nb;
+  double* Cg = A + static_cast<size_t>(col0) * lda + row0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm + i * 8 + lr;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  } else {
-    // both operand tiles in flight at once (LDGSTS), and the C tile is fetched while they land: the launch is
-    // latency-bound (one 64x64xK product per CTA), so the three global round trips must overlap
-    col0 = t0 + tj * NB;
-    cols = min(NB, n - col0);
-    // accumulate -A B^T on top of the old C: acc starts at -C so that the epilogue is a plain store of -acc
-    const double* Csrc = A + static_cast<size_t>(col0) * lda + row0;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = wm + i * 8 + lr;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = wn + j * 8 + lc * 2 + h;
-          acc[i][j][h] = (r < rows && c < cols) ? -Csrc[static_cast<size_t>(c) * lda + r] : 0.0;
-        }
-    }
-  }
-  const int nchunks = (mode == 0) ? 1 : max(1, kdepth / NB);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    if (mode != 0) {
-      if (ch > 0) __syncthreads();  // everybody is done with the previous chunk's tiles
-      const int kw = (kdepth > nb) ? NB : nb;  // columns of this chunk
-      const double* Ac = Asrc + static_cast<size_t>(ch) * NB * lda;
-      const double* Bc = A + static_cast<size_t>(k0 + ch * NB) * lda + col0;
-      for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-        const int r = e % NB, c = e / NB;
-        const bool oka = r < rows && c < kw, okb = r < cols && c < kw;
-        cp_async8(As + c * LDT + r, oka ? Ac + static_cast<size_t>(c) * lda + r : Ac, oka);
-        cp_async8(Bs + c * LDT + r, okb ? Bc + static_cast<size_t>(c) * lda + r : Bc, okb);
+      for (int h = 0; h < 2; ++h) {
+        const int c = wn + j * 8 + lc * 2 + h;
+        acc[i][j][h] = (r < rows && c < cols) ? -Cg[static_cast<size_t>(c) * lda + r] : 0.0;
       }
-      cp_async_commit();
-      cp_async_wait<0>();
+  }
+  const int nchunks = max(1, kdepth / NB);
+  const int kw = (kdepth > nb) ? NB : nb;  // columns per chunk
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch > 0) __syncthreads();  // everybody is done with the previous chunk's tiles
+    const double* Ac = Asrc + static_cast<size_t>(ch) * NB * lda;
+    const double* Bc = A + static_cast<size_t>(k0 + ch * NB) * lda + col0;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+      const int r = e % NB, c = e / NB;
+      const bool oka = r < rows && c < kw, okb = r < cols && c < kw;
+      cp_async8(As + c * LDT + r, oka ? Ac + static_cast<size_t>(c) * lda + r : Ac, oka);
+      cp_async8(Bs + c * LDT + r, okb ? Bc + static_cast<size_t>(c) * lda + r : Bc, okb);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
-
 #pragma unroll 4
     for (int kk = 0; kk < NB; kk += 4) {
       double a[4], b[4];
@@ -344,29 +309,16 @@ __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, 
         for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
-
-  // epilogue
-  double* Cdst;
-  int ldc = lda;
-  if (mode == 0) {
-    Cdst = A + static_cast<size_t>(k0) * lda + row0;  // overwrite A_ik (whole tile already staged in smem)
-  } else {
-    Cdst = A + static_cast<size_t>(col0) * lda + row0;
-  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = wm + i * 8 + lr;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = wn + j * 8 + lc * 2 + h;
-        if (r < rows && c < cols) {
-          double* dst = Cdst + static_cast<size_t>(c) * ldc + r;
-          *dst = (mode == 0) ? acc[i][j][h] : -acc[i][j][h];
-        }
+        if (r < rows && c < cols) Cg[static_cast<size_t>(c) * lda + r] = -acc[i][j][h];
       }
-    }
   }
 }
 
@@ -947,7 +899,7 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
       // inner trailing update: only the columns that still belong to this outer panel
       const int col_tiles = (pend - (k0 + nb) + NB - 1) / NB;
       if (rem > 0 && col_tiles > 0) {
-        dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, nullptr, 1, col_tiles, flag, nb);
+        dmma_tile_kernel<<<row_tiles * col_tiles, 128, smem, s>>>(A, n, n, k0, nb, col_tiles, flag, nb);
         count_launch();
       }
     }
@@ -968,7 +920,7 @@ void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
         // (a): one wave of 64x64 tiles, K = 256 in four chunks — finishes in a fraction of the time a few 128x128
         // CTAs need, and this update sits on the critical path of the chain
         const int nrt = (rem + NB - 1) / NB, nct = std::min(W / NB, nrt);
-        dmma_tile_kernel<<<nrt * nct, 128, smem, s>>>(A, n, n, p0, NB, nullptr, 1, nct, flag, W);
+        dmma_tile_kernel<<<nrt * nct, 128, smem, s>>>(A, n, n, p0, NB, nct, flag, W);
         count_launch();
         CMOE_CUDA(cudaStreamWaitEvent(ctx.side, ctx.chain_done[pi], 0));
         const int rt = tiles - kNextTiles;
