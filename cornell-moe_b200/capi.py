@@ -547,3 +547,40 @@ class GaussianProcessEnsemble:
                                            _d(best), ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
         _check(rc, info.value)
         return best, bv.value, bool(found.value), vals
+
+    def kg_gradient_descent(self, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds,
+                            discrete_pts, num_fidelity=0, seed=0):
+        """cmoe_kg_gradient_descent_mcmc: returns (values [ns], points [ns, q, dim])."""
+        starts = _f64(starts)
+        ns, q, dim = starts.shape
+        _, Xp = self._cands(starts, Xp)
+        M = len(self.members)
+        disc = _f64(discrete_pts).reshape(M, -1, self.dim - num_fidelity)
+        best_in = _f64(best_so_far).ravel()
+        outer, inner = GDParams.from_seq(outer), GDParams.from_seq(inner)
+        db, ib = _f64(domain_bounds).ravel(), _f64(inner_bounds).ravel()
+        vals, pts = np.empty(ns), np.empty((ns, q, dim))
+        info = ctypes.c_int()
+        rc = lib().cmoe_kg_gradient_descent_mcmc(self._handles(), M, int(num_fidelity), ctypes.byref(outer),
+                                                 ctypes.byref(inner), _d(db), _d(ib), _d(disc), disc.shape[1],
+                                                 _d(starts), ns, q, _d(Xp), Xp.shape[0], int(num_mc), _d(best_in),
+                                                 ctypes.c_uint64(seed), _d(vals), _d(pts), ctypes.byref(info))
+        _check(rc, info.value)
+        return vals, pts
+
+    def ei_gradient_descent(self, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0):
+        """cmoe_ei_gradient_descent_mcmc: returns (values [ns], points [ns, q, dim])."""
+        starts = _f64(starts)
+        ns, q, dim = starts.shape
+        _, Xp = self._cands(starts, Xp)
+        M = len(self.members)
+        best_in = _f64(best_so_far).ravel()
+        outer = GDParams.from_seq(outer)
+        db = _f64(domain_bounds).ravel()
+        vals, pts = np.empty(ns), np.empty((ns, q, dim))
+        info = ctypes.c_int()
+        rc = lib().cmoe_ei_gradient_descent_mcmc(self._handles(), M, ctypes.byref(outer), _d(db), _d(starts), ns, q,
+                                                 _d(Xp), Xp.shape[0], int(num_mc), _d(best_in), ctypes.c_uint64(seed),
+                                                 _d(vals), _d(pts), ctypes.byref(info))
+        _check(rc, info.value)
+        return vals, pts

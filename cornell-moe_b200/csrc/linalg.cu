@@ -767,7 +767,8 @@ __global__ void __launch_bounds__(CT) trsv_chain_kernel(const double* __restrict
   if (t == 0) st_release(ready + b, 1);
 }
 
-// returns false if the chained kernel cannot be used (more blocks than SMs)
+// returns false if the chained kernel cannot be used (more blocks than SMs) or gave up waiting (its CTAs could not
+// all become resident, e.g. other streams occupy the device): x is untouched in that case and the caller falls back
 bool trsv_chained(const double* L, int n, double* x, bool trans, cudaStream_t s) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -787,11 +788,12 @@ bool trsv_chained(const double* L, int n, double* x, bool trans, cudaStream_t s)
   }
   count_launch();
   CMOE_CUDA(cudaGetLastError());
-  CMOE_CUDA(cudaMemcpyAsync(x, out.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
   int aborted = 0;
   CMOE_CUDA(cudaMemcpyAsync(&aborted, flags.p + nblk, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaStreamSynchronize(s));
+  if (aborted) return false;
+  CMOE_CUDA(cudaMemcpyAsync(x, out.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CMOE_CUDA(cudaStreamSynchronize(s));  // scratch is freed on return
-  if (aborted) throw Error(CMOE_ERR_RUNTIME, "chained triangular solve lost a dependency (internal error)");
   return true;
 }
 

@@ -525,4 +525,36 @@ int cmoe_multistart_ei_mcmc(const cmoe_gp* const* gps, int num_gp, const cmoe_gd
   });
 }
 
+int cmoe_kg_gradient_descent_mcmc(const cmoe_gp* const* gps, int num_gp, int num_fidelity, const cmoe_gd_params* outer,
+                                  const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                                  const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                                  const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                                  uint64_t seed, double* values_out, double* points_out, int* info) {
+  return guarded(info, [&] {
+    check_ensemble(gps, num_gp);
+    CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gps[0]->device);
+    validate_bounds(domain_bounds, gps[0]->spec.dim);
+    KgEnsembleEvaluator ens;
+    make_kg_ensemble(ens, gps, num_gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_starts, num_starts,
+                     q, points_being_sampled, p, num_mc, best_so_far, seed);
+    BatchEval f = std::ref(ens);
+    gradient_descent_batch(f, *outer, domain_bounds, q, gps[0]->spec.dim, starts, num_starts, values_out, points_out);
+  });
+}
+
+int cmoe_ei_gradient_descent_mcmc(const cmoe_gp* const* gps, int num_gp, const cmoe_gd_params* outer,
+                                  const double* domain_bounds, const double* starts, int num_starts, int q,
+                                  const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                                  uint64_t seed, double* values_out, double* points_out, int* info) {
+  return guarded(info, [&] {
+    check_ensemble(gps, num_gp);
+    CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gps[0]->device);
+    validate_bounds(domain_bounds, gps[0]->spec.dim);
+    BatchEval f = make_ei_ensemble(gps, num_gp, q, points_being_sampled, p, num_mc, best_so_far, seed);
+    gradient_descent_batch(f, *outer, domain_bounds, q, gps[0]->spec.dim, starts, num_starts, values_out, points_out);
+  });
+}
+
 }  // extern "C"

@@ -138,3 +138,31 @@ def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, see
         return capi.ei_gradient_descent(gp, sub, Xp, num_mc, best_so_far, outer, domain_bounds, seed=seed)
 
     return sharded_multistart(evaluate, descend, starts, -1.0, device, group)
+
+
+def multistart_kg_mcmc(ens, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
+                       num_fidelity=0, seed=0, device="cpu", group=None):
+    """multistart_knowledge_gradient_mcmc_optimization sharded over the ranks of `group`: every rank passes its own
+    `capi.GaussianProcessEnsemble` (all members on its GPU) and evaluates / descends its strided share of the starts."""
+
+    def evaluate(sub):
+        return ens.kg(sub, Xp, num_mc, best_so_far, inner, inner_bounds, discrete_pts, num_fidelity=num_fidelity,
+                      seed=seed)
+
+    def descend(sub):
+        return ens.kg_gradient_descent(sub, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds,
+                                       discrete_pts, num_fidelity=num_fidelity, seed=seed)
+
+    return sharded_multistart(evaluate, descend, starts, -np.inf, device, group)
+
+
+def multistart_ei_mcmc(ens, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0, device="cpu", group=None):
+    """multistart_expected_improvement_mcmc_optimization sharded over ranks (initial best 0.0 as in the reference)."""
+
+    def evaluate(sub):
+        return ens.ei(sub, Xp, num_mc, best_so_far, seed=seed, analytic_single=True)
+
+    def descend(sub):
+        return ens.ei_gradient_descent(sub, Xp, num_mc, best_so_far, outer, domain_bounds, seed=seed)
+
+    return sharded_multistart(evaluate, descend, starts, 0.0, device, group)

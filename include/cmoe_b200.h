@@ -231,6 +231,19 @@ int cmoe_multistart_ei_mcmc(const cmoe_gp* const* gps, int num_gp, const cmoe_gd
                             uint64_t seed, double* start_values, double* best_point, double* best_value,
                             int* found_flag, int* info);
 
+/* The restarted gradient descent of the MCMC drivers alone (RestartedGradientDescentKGMCMCOptimization,
+ * gpp_knowledge_gradient_mcmc_optimization.hpp:576-600, and its EI twin): every start is optimised, no top-20 selection.
+ * values_out[num_starts], points_out[num_starts][q][dim].  Used by the multi-GPU layer, which shards the kept starts. */
+int cmoe_kg_gradient_descent_mcmc(const cmoe_gp* const* gps, int num_gp, int num_fidelity, const cmoe_gd_params* outer,
+                                  const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                                  const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                                  const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                                  uint64_t seed, double* values_out, double* points_out, int* info);
+int cmoe_ei_gradient_descent_mcmc(const cmoe_gp* const* gps, int num_gp, const cmoe_gd_params* outer,
+                                  const double* domain_bounds, const double* starts, int num_starts, int q,
+                                  const double* points_being_sampled, int p, int num_mc, const double* best_so_far,
+                                  uint64_t seed, double* values_out, double* points_out, int* info);
+
 /* posterior_mean_optimization (gpp_python_knowledge_gradient.cpp:306-350): ComputeOptimalPosteriorMean
  * (gpp_knowledge_gradient_optimization.cpp:420-472) from ONE start on the un-fantasised GP — line-search gradient
  * descent on -mu(x) over the dim-num_fidelity free coordinates (fidelity coordinates pinned to 1.0).

@@ -106,3 +106,25 @@ def test_gp_large_fit_residual(capi):
     K = np.exp(-0.5 * d2) + prob["noise"][0] * np.eye(2000)
     np.testing.assert_allclose(L @ L.T, K, rtol=0, atol=1e-11)
     np.testing.assert_allclose(K @ kinvy, prob["y"] - mean, rtol=0, atol=1e-8)
+
+
+def test_gp_config5_fit_properties(capi):
+    """BASELINE.json configs[4] at full size (N = 5000, d = 10): look-ahead blocked Cholesky + chained triangular solves.
+    Size-independent properties on random samples: (L L^T)_ij = K_ij and (K K^-1 (y - m))_i = (y - m)_i."""
+    N, d = 5000, 10
+    prob = make_problem(N, d, seed=55, length=0.5)
+    gp = capi.GaussianProcess(0, 1.3, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    L, kinvy, mean = gp.state()
+    L = np.tril(L)
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, N, size=(3000, 2))
+    i, j = np.maximum(idx[:, 0], idx[:, 1]), np.minimum(idx[:, 0], idx[:, 1])
+    Xs = prob["X"] / prob["lengths"]
+    want = 1.3 * np.exp(-0.5 * ((Xs[i] - Xs[j]) ** 2).sum(axis=1)) + (i == j) * prob["noise"][0]
+    got = np.einsum("ij,ij->i", L[i], L[j])
+    np.testing.assert_allclose(got, want, rtol=0, atol=5e-12)
+    rows = rng.integers(0, N, size=40)
+    Krows = 1.3 * np.exp(-0.5 * ((Xs[rows][:, None, :] - Xs[None, :, :]) ** 2).sum(-1))
+    Krows[np.arange(40), rows] += prob["noise"][0]
+    np.testing.assert_allclose(Krows @ kinvy, (prob["y"] - mean)[rows], rtol=0, atol=2e-8)
+    np.testing.assert_allclose(mean, prob["y"].mean(), rtol=1e-12)
