@@ -63,5 +63,45 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
 
 
+def main_widened():
+    """Second fixture file: the rows added from SURVEY.md 8f (MCMC-averaged q-KG / q-EI, posterior-mean optimisation)."""
+    ref = orc.load_reference()
+    out = {}
+    rng = np.random.default_rng(2027)
+    for name, dim, g_idx, nf, q, p in (("mcmc_plain", 3, (), 0, 2, 1), ("mcmc_fidelity", 3, (), 1, 2, 0),
+                                       ("mcmc_deriv", 3, (0,), 0, 2, 0)):
+        M, mc, num_pts = 3, 16, 4
+        prob = make_problem(14, dim, g_idx=g_idx, seed=77 + dim + nf, noise=0.1)
+        hypers = np.concatenate([rng.uniform(0.8, 1.5, size=(M, 1)), rng.uniform(0.4, 0.9, size=(M, dim))], axis=1)
+        noises = rng.uniform(0.05, 0.15, size=(M, 1 + len(g_idx)))
+        Xq, Xp = rng.uniform(0.2, 0.9, size=(q, dim)), rng.uniform(size=(p, dim))
+        disc = rng.uniform(size=(M, num_pts, dim - nf))
+        best = rng.uniform(-0.5, 0.5, size=M)
+        t_kg = rng.standard_normal((mc // 2) * (q + p) * (1 + len(g_idx)))
+        t_ei = rng.standard_normal(mc * (q + p))
+        kg, gkg = ref.kg_mcmc(hypers, noises, prob["X"], prob["y"], prob["derivs"], Xq, Xp, mc, best, t_kg,
+                              EXAMPLE_INNER_GD, unit_bounds(dim - nf), disc, num_fidelity=nf, grad=True)
+        ei, gei = ref.ei_mcmc(hypers, noises, prob["X"], prob["y"], prob["derivs"], Xq, Xp, mc, best + 1.0, t_ei,
+                              grad=True)
+        for k, v in dict(hypers=hypers, noises=noises, X=prob["X"], y=prob["y"], g_idx=np.array(g_idx, dtype=np.int32),
+                         nf=nf, Xq=Xq, Xp=Xp, disc=disc, best=best, kg_table=t_kg, ei_table=t_ei, kg=kg, kg_grad=gkg,
+                         ei=ei, ei_grad=gei).items():
+            out[f"{name}/{k}"] = v
+    for name, kernel, g_idx, nf in (("pmopt_se", 0, (), 0), ("pmopt_matern_deriv", 1, (0, 2), 0), ("pmopt_fid", 1, (), 1)):
+        prob = make_problem(20, 3, g_idx=g_idx, seed=3)
+        gp, lm = ref.gp(kernel, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+        gd = np.array([1, 50, 3, 0, 0.7, 1.0, 0.2, 1e-8])
+        x0 = np.array([0.3, 0.6, 0.5])[: 3 - nf]
+        bp, val = gp.posterior_mean_optimization(x0, gd, unit_bounds(3 - nf), nf)
+        for k, v in dict(kernel=kernel, g_idx=np.array(g_idx, dtype=np.int32), nf=nf, X=prob["X"], y=prob["y"],
+                         lengths=prob["lengths"], noise=prob["noise"], gd=gd, x0=x0, best_point=bp, best_value=val).items():
+            out[f"{name}/{k}"] = v
+    path = os.path.join(ROOT, "tests", "golden", "reference_vectors_widened.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if "--widened-only" not in sys.argv:
+        main()
+    main_widened()

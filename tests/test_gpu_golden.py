@@ -39,3 +39,33 @@ def test_cuda_matches_golden(case):
                         table=g("kg_table"), grad=True)
         np.testing.assert_allclose(kg[0], g(f"kg_{tag}"), rtol=1e-7, atol=1e-10)
         np.testing.assert_allclose(gkg[0], g(f"kg_{tag}_grad"), rtol=1e-5, atol=1e-8)
+
+
+WIDE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_widened.npz"))
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in WIDE.files if k.startswith("mcmc")}))
+def test_cuda_mcmc_matches_golden(case):
+    from cornell_moe_b200 import capi
+    g = lambda k: WIDE[f"{case}/{k}"]
+    dim, nf = g("X").shape[1], int(g("nf"))
+    ens = capi.GaussianProcessEnsemble(g("hypers"), g("noises"), g("X"), g("y"), g("g_idx"))
+    kg, gkg = ens.kg(g("Xq"), g("Xp"), 16, g("best"), EXAMPLE_INNER_GD, unit_bounds(dim - nf), g("disc"),
+                     num_fidelity=nf, table=g("kg_table"), grad=True)
+    np.testing.assert_allclose(kg[0], g("kg"), rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(gkg[0], g("kg_grad"), rtol=1e-5, atol=1e-8)
+    ei, gei = ens.ei(g("Xq"), g("Xp"), 16, g("best") + 1.0, table=g("ei_table"), grad=True)
+    np.testing.assert_allclose(ei[0], g("ei"), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gei[0], g("ei_grad"), rtol=1e-7, atol=1e-10)
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in WIDE.files if k.startswith("pmopt")}))
+def test_cuda_posterior_mean_optimization_matches_golden(case):
+    from cornell_moe_b200 import capi
+    g = lambda k: WIDE[f"{case}/{k}"]
+    nf = int(g("nf"))
+    gp = capi.GaussianProcess(int(g("kernel")), 1.0, g("lengths"), g("X"), g("y"), g("noise"), g("g_idx"))
+    bp, val, found = capi.posterior_mean_optimization(gp, g("x0"), g("gd"), unit_bounds(3 - nf), nf)
+    assert found
+    np.testing.assert_allclose(bp, g("best_point"), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(val, float(g("best_value")), rtol=1e-9)

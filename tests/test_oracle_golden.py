@@ -82,3 +82,31 @@ def test_philox_host_stream_statistics():
     import ctypes
     lib = ctypes.CDLL(orc.oracle_path())
     assert hasattr(lib, "oracle_philox_normals")
+
+
+WIDE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_widened.npz"))
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in WIDE.files if k.startswith("mcmc")}))
+def test_oracle_mcmc_matches_golden(o, case):
+    g = lambda k: WIDE[f"{case}/{k}"]
+    dim, nf = g("X").shape[1], int(g("nf"))
+    args = (g("hypers"), g("noises"), g("X"), g("y"), g("g_idx"), g("Xq"), g("Xp"))
+    kg, gkg = o.kg_mcmc(*args, 16, g("best"), g("kg_table"), EXAMPLE_INNER_GD, unit_bounds(dim - nf), g("disc"),
+                        num_fidelity=nf, grad=True)
+    np.testing.assert_allclose(kg, g("kg"), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gkg, g("kg_grad"), rtol=1e-6, atol=1e-9)
+    ei, gei = o.ei_mcmc(*args, 16, g("best") + 1.0, g("ei_table"), grad=True)
+    np.testing.assert_allclose(ei, g("ei"), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(gei, g("ei_grad"), rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[0] for k in WIDE.files if k.startswith("pmopt")}))
+def test_oracle_posterior_mean_optimization_matches_golden(o, case):
+    g = lambda k: WIDE[f"{case}/{k}"]
+    nf = int(g("nf"))
+    gp, lm = o.gp(int(g("kernel")), 1.0, g("lengths"), g("X"), g("y"), g("noise"), g("g_idx"))
+    assert lm == 0
+    bp, val = gp.posterior_mean_optimization(g("x0"), g("gd"), unit_bounds(3 - nf), nf)
+    np.testing.assert_allclose(bp, g("best_point"), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(val, float(g("best_value")), rtol=1e-12)
