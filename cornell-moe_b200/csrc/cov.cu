@@ -66,8 +66,11 @@ __device__ __forceinline__ double exp_tab_cov(double t, const double* __restrict
 // the dot product and scaled by the exact factor -1/2, so for coincident points the three terms cancel EXACTLY and
 // k = alpha exp(0) = alpha bit-for-bit, as in the reference: duplicate points with zero noise must make the Cholesky
 // fail at the same leading minor (tests/test_gpu_gp.py::test_gp_singular_reports_leading_minor).
+#ifndef CMOE_COV_MINB
+#define CMOE_COV_MINB (RB == 4 ? 3 : 2)
+#endif
 template <int KERNEL>
-__global__ void __launch_bounds__(256, RB == 4 ? 3 : 2)
+__global__ void __launch_bounds__(256, CMOE_COV_MINB)
     cov_build_g0_kernel(const __grid_constant__ KernelSpec spec, const double* __restrict__ Xs, int N,
                         const double* __restrict__ noise, double* __restrict__ K) {
   extern __shared__ double sm[];

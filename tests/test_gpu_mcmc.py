@@ -110,19 +110,6 @@ def test_multistart_mcmc_drivers(capi):
     if v_want > -np.inf:
         np.testing.assert_allclose(bp1, want, rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(bv1, v_want, rtol=1e-12)
-    # the sharded (multi-GPU) driver run in a single process gives the C driver's answer, and the C driver is
-    # "screen, top-20 in priority-queue order, gradient descent, strict-> arg-max in slot order"
-    from cornell_moe_b200 import multigpu
-    bp_s, bv_s, found_s, sv_s = multigpu.multistart_kg_mcmc(ens, starts, None, mc, best, outer, EXAMPLE_INNER_GD,
-                                                            unit_bounds(dim), unit_bounds(dim), disc, seed=5)
-    assert bv_s == bv and found_s
-    np.testing.assert_array_equal(bp_s, bp)
-    np.testing.assert_array_equal(sv_s, sv)
-    top = multigpu.top_k_indices(sv)
-    gv, gp_ = ens.kg_gradient_descent(starts[top], None, mc, best, outer, EXAMPLE_INNER_GD, unit_bounds(dim),
-                                      unit_bounds(dim), disc, seed=5)
-    assert bv == gv[int(np.argmax(gv))]
-    np.testing.assert_array_equal(bp, gp_[int(np.argmax(gv))])
     # EI drivers: MC for q = 2 and analytic for q = 1
     ybest = np.full(M, float(prob["y"].min()))
     for qq in (1, 2):
@@ -132,10 +119,6 @@ def test_multistart_mcmc_drivers(capi):
         assert np.all(bp >= 0.0) and np.all(bp <= 1.0) and bv >= 0.0
         np.testing.assert_allclose(sv, ens.ei(st, None, 256, ybest, seed=3, analytic_single=True), rtol=1e-13,
                                    atol=1e-16)
-        bp2, bv2, _, _ = multigpu.multistart_ei_mcmc(ens, st, None, 256, ybest, [25, 4, 2, 0, 0.7, 0.2, 0.2, 1e-8],
-                                                     unit_bounds(dim), seed=3)
-        assert bv2 == bv
-        np.testing.assert_array_equal(bp2, bp)
 
 
 @pytest.mark.parametrize("kernel,g_idx,nf", [(0, (), 0), (1, (0, 2), 0), (1, (), 1), (0, (), 2)])
