@@ -10,8 +10,10 @@
 //
 // Mapping: one thread per MC sample; grid = (sample chunks, candidates).  Lanes that finish fetch the next sample of
 // the chunk from a shared counter, so a warp only idles at the very end of a chunk although the line search has
-// data-dependent trip counts.  The line search is a per-lane state machine whose only expensive transition is
-// "evaluate mu+ and its gradient at my query point" — that evaluation is warp-uniform code.
+// data-dependent trip counts.  The line search is a per-lane state machine around two warp-uniform routines:
+// "evaluate mu+ and its gradient at my query point" (POINT round) and, for the SquareExponential kernel, "evaluate all
+// backtracking trials of this step along my gradient" (LINE round, eval_line / eval_line_gen); a warp vote picks the
+// kind of round, see kg_mc_body.
 #pragma once
 
 #include "device_math.cuh"

@@ -1,5 +1,6 @@
-// Dense FP64 linear algebra on sm_100a: blocked right-looking Cholesky with the trailing-panel SYRK/GEMM on the
-// FP64 tensor pipe (mma.sync m8n8k4 DMMA — tcgen05 has no f64 kind), and blocked triangular solves.
+// Dense FP64 linear algebra on sm_100a: blocked right-looking Cholesky (register-resident panel factorisation, trailing
+// SYRK/GEMM on the FP64 tensor pipe — mma.sync m8n8k4 DMMA; tcgen05 has no f64 kind — with one-panel look-ahead), blocked
+// multi-RHS triangular solves and a single-launch flag-chained solve for one right-hand side.
 //
 // Replaces (reference, moe/optimal_learning/cpp/):
 //   ComputeCholeskyFactorL              gpp_linear_algebra.cpp:109-148  (pivot test `> 1e-16`, returns k+1 on failure)
