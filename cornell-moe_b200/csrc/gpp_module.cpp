@@ -880,6 +880,15 @@ PYBIND11_MODULE(GPP, m) {
   m.def("compute_grad_expected_improvement_mcmc", &compute_grad_expected_improvement_mcmc);
   m.def("multistart_expected_improvement_mcmc_optimization", &multistart_expected_improvement_mcmc_optimization);
   m.def("evaluate_EI_mcmc_at_point_list", &evaluate_EI_mcmc_at_point_list);
+  // names of the reference module that are outside the hot path (model selection, heuristic EI): present, so that an
+  // unmodified front end fails with the library's own exception class and a clear message rather than AttributeError
+  for (const char* name : {"compute_log_likelihood", "compute_hyperparameter_grad_log_likelihood",
+                           "multistart_hyperparameter_optimization", "restarted_hyperparameter_optimization",
+                           "evaluate_log_likelihood_at_hyperparameter_list",
+                           "heuristic_expected_improvement_optimization"}) {
+    const std::string n(name);
+    m.def(name, [n](const py::args&, const py::kwargs&) -> py::object { not_on_path(n.c_str()); });
+  }
   m.def("run_cpp_tests", []() -> int { not_on_path("run_cpp_tests"); });
   m.def("device_count", []() { return cmoe_device_count(); });
   m.def("version", []() { return std::string(cmoe_version()); });
