@@ -47,3 +47,23 @@ def test_sharded_mcmc_drivers_match_c_drivers():
         assert found == found2
         np.testing.assert_allclose(bv2, bv, rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(bp2, bp, rtol=1e-12, atol=1e-14)
+
+
+def test_kg_se_fidelity_dimension_batched_line_search():
+    """SquareExponential kernel with a fidelity coordinate (gradient pinned to 0 there) through the batched backtracking
+    path — the Matern twin of this case is tests/test_gpu_kg.py::test_kg_fidelity_dimension."""
+    from cornell_moe_b200 import capi
+    from gpu_util import checker
+    prob = make_problem(14, 3, seed=21, noise=0.1)
+    gp = capi.GaussianProcess(0, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    ref, lm = checker().gp(0, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    assert lm == 0
+    rng = np.random.default_rng(8)
+    cands = rng.uniform(size=(2, 2, 3))
+    disc = rng.uniform(size=(6, 2))
+    table = rng.standard_normal(8 * 2)
+    kg, grad = gp.kg(cands, None, 16, 0.1, EXAMPLE_INNER_GD, unit_bounds(2), disc, num_fidelity=1, table=table, grad=True)
+    for c in range(2):
+        v, g = ref.kg(cands[c], None, 16, 0.1, table, EXAMPLE_INNER_GD, unit_bounds(2), disc, num_fidelity=1, grad=True)
+        np.testing.assert_allclose(kg[c], v, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
