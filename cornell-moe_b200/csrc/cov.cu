@@ -18,22 +18,12 @@ namespace {
 
 constexpr int TR = 128;  // point rows per CTA tile
 constexpr int TCW = 64;  // point cols per CTA tile
-#ifndef CMOE_COV_ROWS
-#define CMOE_COV_ROWS 4
-#endif
-#ifndef CMOE_COV_EXP_TABLE
-#define CMOE_COV_EXP_TABLE 1
-#endif
-#ifndef CMOE_COV_UNROLL
-#define CMOE_COV_UNROLL 2
-#endif
-constexpr int kCovUnroll = CMOE_COV_UNROLL;
-constexpr int RB = CMOE_COV_ROWS;      // rows per thread (4 or 8), 4 columns per thread
+constexpr int kCovUnroll = 2;
+constexpr int RB = 4;                  // rows per thread, 4 columns per thread
 constexpr int WR = TR / (8 * RB);      // warps along the rows (a warp covers 8*RB rows x 16 cols)
 constexpr int WC = 8 / WR;             // warps along the columns
 constexpr int TC = WC * 16;            // columns per pass over the staged slabs
 
-#if CMOE_COV_EXP_TABLE
 // 2^(i/64), the table of the reduced-range exp (see exp_tab in kg_mc.cuh: 10 FP64-pipe instructions instead of 15)
 __device__ const double kCovExp2Table[64] = {
 #include "exp2_table64.inc"
@@ -54,9 +44,8 @@ __device__ __forceinline__ double exp_tab_cov(double t, const double* __restrict
   p = fma(p, r, 1.0);
   p *= tab[n & 63];
   const int k = max(n >> 6, -1000);
-  return exp_guard_out(t, __double2hiint(p) + (k << 20), __double2loint(p));
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
-#endif
 
 // g == 0 fast path: K[i + j*n] for i >= j (tile granularity), noise[0] on the diagonal.
 // Works on length-scaled coordinates Xs = X / l with the expanded distance
@@ -66,11 +55,8 @@ __device__ __forceinline__ double exp_tab_cov(double t, const double* __restrict
 // the dot product and scaled by the exact factor -1/2, so for coincident points the three terms cancel EXACTLY and
 // k = alpha exp(0) = alpha bit-for-bit, as in the reference: duplicate points with zero noise must make the Cholesky
 // fail at the same leading minor (tests/test_gpu_gp.py::test_gp_singular_reports_leading_minor).
-#ifndef CMOE_COV_MINB
-#define CMOE_COV_MINB (RB == 4 ? 3 : 2)
-#endif
 template <int KERNEL>
-__global__ void __launch_bounds__(256, CMOE_COV_MINB)
+__global__ void __launch_bounds__(256, 3)
     cov_build_g0_kernel(const __grid_constant__ KernelSpec spec, const double* __restrict__ Xs, int N,
                         const double* __restrict__ noise, double* __restrict__ K) {
   extern __shared__ double sm[];
@@ -79,10 +65,8 @@ __global__ void __launch_bounds__(256, CMOE_COV_MINB)
   double* Xc = sm + TR * dim;      // [dim][TCW]  (a warp shares its columns: broadcast reads)
   double* Hr = Xc + TCW * dim;     // [TR]   -|x_i|^2/2
   double* Hc = Hr + TR;            // [TCW]  -|x_j|^2/2
-#if CMOE_COV_EXP_TABLE
   double* tab = Hc + TCW;          // [64]
   if (threadIdx.x < 64) tab[threadIdx.x] = kCovExp2Table[threadIdx.x];
-#endif
   // linear block index -> (tile row tr, tile col tc) of the lower-triangular tile grid: tc*TCW <= tr*TR + TR - 1
   constexpr int kColsPerRow = TR / TCW;  // col tiles that fit under one row tile's diagonal extent
   int tr = static_cast<int>((sqrt(8.0 * (blockIdx.x / kColsPerRow) + 1.0) - 1.0) * 0.5);
@@ -162,11 +146,7 @@ __global__ void __launch_bounds__(256, CMOE_COV_MINB)
       for (int rr = 0; rr < RB; ++rr) {
         const double e = t[rr][cc] + (hr[rr] + hcc);  // = -r^2/2, exactly 0 for coincident points
         if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
-#if CMOE_COV_EXP_TABLE
           v[rr] = spec.alpha * exp_tab_cov(e, tab);
-#else
-          v[rr] = spec.alpha * exp_fast(e);
-#endif
         } else {
           const double r2 = fmax(0.0, -2.0 * e);
           const double arg = kSqrt5 * sqrt(r2);

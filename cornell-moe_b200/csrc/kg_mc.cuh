@@ -101,13 +101,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-#ifndef CMOE_EXP_TABLE
-#define CMOE_EXP_TABLE 1
-#endif
-#if CMOE_EXP_TABLE
 // exp(t) = 2^k * 2^(i/64) * e^r with |r| <= ln2/128: 64-entry table in shared memory + degree-5 Taylor polynomial
 // (truncation r^6/720 <= 3.5e-17 relative).  10 FP64-pipe instructions instead of 15 for exp_fast; same integer-side
-// clamp of the exponent, NO guard for |t| >= 2.3e7 (see kFastPathRadius).  Used by the shared-memory fast path of the fused q-KG kernel (+11 % throughput on the north-star shape).
+// clamp of the exponent, NO guard for |t| >= 2.3e7 (see kFastPathRadius).  Used by the shared-memory fast path of the
+// fused q-KG kernel (+11 % throughput on the north-star shape); measured max relative error 3.0e-16 over [-690, 1]
+// (profiles/exp_accuracy.py), exp(0) = 1 exactly.
 __device__ const double kExp2Table[64] = {
 #include "exp2_table64.inc"
 };
@@ -133,12 +131,9 @@ __device__ __forceinline__ double exp_tab(double t) {
   const int k = max(n >> 6, -1000);
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
-#endif
 template <bool TAB>
 __device__ __forceinline__ double exp_sel(double t) {
-#if CMOE_EXP_TABLE
   if (TAB) return exp_tab(t);
-#endif
   return exp_fast(t);
 }
 
@@ -168,38 +163,18 @@ __device__ __forceinline__ double2 ld2(const double* p) {
   }
 }
 
-// x . y and beta - B . c over the staged operands.  CMOE_SPLIT_CHAINS = 1 accumulates even and odd terms separately
-// (two half-length dependent DFMA chains + one DADD) to expose more instruction-level parallelism.
+// x . y and beta - B . c over the staged operands (one dependent DFMA chain each; splitting them into even / odd
+// half chains measured 4 % slower: more instructions, no latency win).
 template <int DIM>
 __device__ __forceinline__ double dot_dim(const double (&x)[DIM], const double (&y)[DIM], double init) {
-#if CMOE_SPLIT_CHAINS
-  double d0 = init, d1 = 0.0;
-#pragma unroll
-  for (int d = 0; d < DIM; d += 2) {
-    d0 = fma(x[d], y[d], d0);
-    d1 = fma(x[d + 1], y[d + 1], d1);
-  }
-  return d0 + d1;
-#else
   double dot = init;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) dot = fma(x[d], y[d], dot);
   return dot;
-#endif
 }
 
 template <int QP, bool SMEM>
 __device__ __forceinline__ double weight_row(const double* __restrict__ pk, double beta, const double (&c)[QP]) {
-#if CMOE_SPLIT_CHAINS
-  double a0 = beta, a1 = 0.0;
-#pragma unroll
-  for (int u = 0; u < QP; u += 2) {
-    const double2 b = ld2<SMEM>(pk + 2 + u);
-    a0 = fma(-b.x, c[u], a0);
-    a1 = fma(-b.y, c[u + 1], a1);
-  }
-  return a0 + a1;
-#else
   double a = beta;
 #pragma unroll
   for (int u = 0; u < QP; u += 2) {
@@ -208,7 +183,6 @@ __device__ __forceinline__ double weight_row(const double* __restrict__ pk, doub
     a = fma(-b.y, c[u + 1], a);
   }
   return a;
-#endif
 }
 
 // mu+(xq) - m  and  the scaled-gradient accumulators, for one query point (scaled coordinates xq).
@@ -291,16 +265,7 @@ __device__ __forceinline__ void eval_posterior(const double* __restrict__ Xt, co
 // full evaluation (dot + weights + exp) per trial.  S[k] = sum_j a_j k(x, X_j) exp(a_k p_j) for a_k = a_min 2^(KB-1-k'),
 // returned in trial order (S[0] <-> largest step); pmax_hi (high word of max_j |a_min p_j|) lets the caller reject
 // batches whose factors could leave the double range (it then falls back to one-at-a-time evaluations).
-#ifndef CMOE_LINE_BATCH
-#define CMOE_LINE_BATCH 8
-#endif
-#ifndef CMOE_PMAX_FP
-#define CMOE_PMAX_FP 0
-#endif
-#ifndef CMOE_SPLIT_CHAINS
-#define CMOE_SPLIT_CHAINS 0
-#endif
-constexpr int kLineBatch = CMOE_LINE_BATCH;
+constexpr int kLineBatch = 8;  // trial step sizes per batch (6 measured +1.5 %, but a second batch costs a whole pass)
 
 template <int DIM, int QP, bool SMEM>
 __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const double* __restrict__ Pk,
@@ -320,9 +285,6 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
   const double xga = -alpha_min * xg;
 #pragma unroll
   for (int k = 0; k < kLineBatch; ++k) S[k] = 0.0;
-#if CMOE_PMAX_FP
-  double pmax_fp = 0.0;
-#endif
   pmax_hi = 0;  // max over rows of the high word of |a_min p_j| (integer ALU; monotone in |p|, NaN/inf sort last)
 #pragma unroll 2
   for (int j = 0; j < N; ++j) {
@@ -339,11 +301,7 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
     const double dot = dot_dim<DIM>(xb, xv, 0.0);
     const double pj = dot_dim<DIM>(ga, xv, xga);
     const double a = weight_row<QP, SMEM>(pk, h.y, c);
-#if CMOE_PMAX_FP
-    pmax_fp = fmax(pmax_fp, fabs(pj));
-#else
     pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
-#endif
     const double w = a * exp_sel<SMEM>(dot + (h.x + hq));
     double G = exp_sel<SMEM>(pj);
 #pragma unroll
@@ -372,11 +330,7 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
 #pragma unroll
     for (int v = 0; v < QP; ++v)
       if (v == u) cu = c[v];
-#if CMOE_PMAX_FP
-    pmax_fp = fmax(pmax_fp, fabs(pj));
-#else
     pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
-#endif
     const double w = cu * exp_sel<SMEM>(dot + (h.x + hq));
     double G = exp_sel<SMEM>(pj);
 #pragma unroll
@@ -385,9 +339,6 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
       if (k > 0) G *= G;
     }
   }
-#if CMOE_PMAX_FP
-  pmax_hi = __double2hiint(pmax_fp) & 0x7fffffff;
-#endif
 }
 
 // Kernel pieces for the general path: kv = k(x, X_j) (value row), kb = factor of the first-derivative rows,
@@ -966,9 +917,7 @@ __global__ void __launch_bounds__(kMcThreads, CMOE_MC_MINBLOCKS) kg_mc_kernel(co
   const double* gPk = prm.Pk + static_cast<size_t>(cand) * N * (QP + 2);
   const double* gXu = prm.Xu + static_cast<size_t>(cand) * U * (DIM + 2);
   if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
-#if CMOE_EXP_TABLE
   exp_table_stage();
-#endif
   if (prm.use_smem) {
     // stage the per-candidate operands with TMA bulk copies (UBLKCP) signalled through an mbarrier
     double* sXt = reinterpret_cast<double*>(smem_raw);
@@ -1136,13 +1085,11 @@ __device__ __forceinline__ void kg_acc_body(const KgAccParams& prm, double* __re
 template <int KERNEL, int DIM, int QP>
 __global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgAccParams prm) {
   extern __shared__ __align__(16) double acc_smem[];
-#if CMOE_EXP_TABLE
   if (prm.fast_exp) {
     exp_table_stage();
     kg_acc_body<KERNEL, DIM, QP, true>(prm, acc_smem);
     return;
   }
-#endif
   kg_acc_body<KERNEL, DIM, QP, false>(prm, acc_smem);
 }
 

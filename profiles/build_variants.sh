@@ -1,4 +1,7 @@
 #!/bin/bash
+# (The variant macros of round 1 — CMOE_LINE_BATCH, CMOE_SPLIT_CHAINS, CMOE_EXP_TABLE, CMOE_EXP_GUARD, CMOE_PMAX_FP,
+# CMOE_COV_ROWS/UNROLL/MINB — were resolved to the shipped configuration after the experiments; the script stays as the
+# harness for -D experiments: add an #ifndef/#define default in the source, then build one library per flag set.)
 # Builds experiment variants of the fused q-KG kernel (only kg_mc_inst_8.cu is recompiled) into variants/libvar_<name>.so;
 # bench.py picks one up through CMOE_B200_LIB.  Usage: [FILE=cov] profiles/build_variants.sh name "-DFLAG=1 ..." [name flags]...
 # FILE = the translation unit to recompile (default kg_mc_inst_8).
