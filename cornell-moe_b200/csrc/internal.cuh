@@ -159,11 +159,13 @@ void drop_cached_plan(const cmoe_gp* gp);
 
 // ---- linalg.cu -----------------------------------------------------------------------------------------------
 // In-place blocked lower Cholesky of the n*n column-major matrix A (lda = n).  *flag (device) receives 0 or the
-// failing leading-minor index (k+1), with the reference's pivot test (> 1e-16).  Asynchronous on `s`.
+// failing leading-minor index (k+1), with the reference's pivot test (> 1e-16).  Enqueued on `s` (large systems also
+// use an internal side stream for the look-ahead update); returns after the factorisation has completed.
 void potrf_lower(double* A, int n, int* flag, cudaStream_t s);
 // X <- (L L^T)^-1 X for nrhs right-hand sides; X is n*nrhs column-major with leading dimension ldx.
 void potrs_lower(const double* L, int n, double* X, int ldx, int nrhs, cudaStream_t s);
-// X <- L^-1 X (trans = false) or L^-T X (trans = true)
+// X <- L^-1 X (trans = false) or L^-T X (trans = true).  nrhs <= 4 with n >= 1024 takes the single-launch chained
+// solver (which synchronises `s`); everything else is the blocked multi-RHS kernel, asynchronous on `s`.
 void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s);
 
 // ---- posterior.cu -------------------------------------------------------------------------------------------
