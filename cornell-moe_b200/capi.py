@@ -270,6 +270,20 @@ class GaussianProcess:
         return res[0] if len(res) == 1 else tuple(res)
 
 
+def log_marginal_likelihood(kernel, alpha, lengths, X, y, noise, derivs=None, device=0):
+    """cmoe_log_marginal_likelihood (gpp_model_selection.cpp:540-612): one device fit + two host reductions."""
+    X = _f64(X)
+    N, dim = X.shape
+    derivs = _i32(derivs)
+    val = ctypes.c_double()
+    info = ctypes.c_int()
+    rc = lib().cmoe_log_marginal_likelihood(int(kernel), ctypes.c_double(alpha), _d(_f64(lengths).ravel()), _d(X),
+                                            _d(_f64(y).ravel()), _d(_f64(noise).ravel()), _i(derivs), len(derivs), dim, N,
+                                            int(device), ctypes.byref(val), ctypes.byref(info))
+    _check(rc, info.value)
+    return val.value
+
+
 def fp64_peaks(device=0):
     """Measured FP64 peaks (TFLOP/s): (DFMA vector pipe, DMMA tensor pipe)."""
     t = np.zeros(2)

@@ -163,6 +163,53 @@ int cmoe_gp_create(int kernel, double alpha, const double* lengths, const double
   });
 }
 
+// log p(y | X, theta): one GP fit with 1e-6 added to every noise entry, then two host reductions over n numbers.
+int cmoe_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* points_sampled,
+                                 const double* points_sampled_value, const double* noise_variance,
+                                 const int* derivatives, int num_derivatives, int dim, int num_sampled, int device,
+                                 double* log_likelihood, int* info) {
+  if (log_likelihood) *log_likelihood = 0.0;
+  if (num_derivatives < 0 || noise_variance == nullptr || log_likelihood == nullptr) {
+    return guarded(info, [&] { CMOE_REQUIRE(false, CMOE_ERR_INVALID_VALUE, "invalid argument"); });
+  }
+  std::vector<double> nz(noise_variance, noise_variance + 1 + num_derivatives);
+  for (double& v : nz) v += 1.0e-6;  // gpp_model_selection.cpp:546-549
+  cmoe_gp* gp = nullptr;
+  int linfo = 0;
+  const int rc = cmoe_gp_create(kernel, alpha, lengths, points_sampled, points_sampled_value, nz.data(), derivatives,
+                                num_derivatives, dim, num_sampled, device, &gp, &linfo);
+  if (rc == CMOE_ERR_SINGULAR) {
+    // the reference ignores the failed factorisation and returns whatever the garbage factor gives (:551-553)
+    *log_likelihood = -std::numeric_limits<double>::infinity();
+    if (info) *info = linfo;
+    return CMOE_OK;
+  }
+  if (rc != CMOE_OK) {
+    if (info) *info = linfo;
+    return rc;
+  }
+  const int out = guarded(info, [&] {
+    require_device(gp->device);
+    const int n = gp->n, bs = 1 + gp->spec.g;
+    std::vector<double> diag(n), b(n);
+    // diagonal of the column-major factor: n elements, (n+1) doubles apart
+    CMOE_CUDA(cudaMemcpy2DAsync(diag.data(), sizeof(double), gp->dK.p, static_cast<size_t>(n + 1) * sizeof(double),
+                                sizeof(double), n, cudaMemcpyDeviceToHost, gp->stream));
+    gp->dKinvY.download(b.data(), n, gp->stream);
+    CMOE_CUDA(cudaStreamSynchronize(gp->stream));
+    double term1 = 0.0, term2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double yc = gp->hy[i] - ((i % bs == 0) ? gp->mean : 0.0);
+      term1 += yc * b[i];
+      term2 -= std::log(diag[i]);
+    }
+    const double kLog2Pi = 1.8378770664093453;
+    *log_likelihood = -0.5 * term1 + term2 - 0.5 * static_cast<double>(n) * kLog2Pi;
+  });
+  cmoe_gp_destroy(gp);
+  return out;
+}
+
 void cmoe_gp_destroy(cmoe_gp* gp) {
   if (!gp) return;
   cudaSetDevice(gp->device);

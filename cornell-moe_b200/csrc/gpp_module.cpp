@@ -882,7 +882,31 @@ PYBIND11_MODULE(GPP, m) {
   m.def("evaluate_EI_mcmc_at_point_list", &evaluate_EI_mcmc_at_point_list);
   // names of the reference module that are outside the hot path (model selection, heuristic EI): present, so that an
   // unmodified front end fails with the library's own exception class and a clear message rather than AttributeError
-  for (const char* name : {"compute_log_likelihood", "compute_hyperparameter_grad_log_likelihood",
+  // compute_log_likelihood(points_sampled, points_sampled_value, dim, num_sampled, objective_type, hyperparameters,
+  //                        derivatives, num_derivatives, noise_variance)   gpp_python_model_selection.cpp:43-87
+  m.def("compute_log_likelihood",
+        [](const py::list& points_sampled, const py::list& points_sampled_value, int dim, int num_sampled,
+           LogLikelihoodTypes objective_type, const py::list& hyperparameters, const py::list& derivatives,
+           int num_derivatives, const py::list& noise_variance) -> double {
+          if (objective_type != LogLikelihoodTypes::kLogMarginalLikelihood) {
+            PyErr_SetString(g_exc_base, "ERROR: invalid objective mode choice. Setting log likelihood to -DBL_MAX.");
+            throw py::error_already_set();
+          }
+          const double alpha = hyperparameters[0].cast<double>();
+          const auto lengths = to_vec(hyperparameters[1].cast<py::list>(), dim);
+          const auto X = to_vec(points_sampled, static_cast<size_t>(dim) * num_sampled);
+          const auto y = to_vec(points_sampled_value, static_cast<size_t>(num_sampled) * (1 + num_derivatives));
+          const auto noise = to_vec(noise_variance, 1 + num_derivatives);
+          const auto derivs = to_ivec(derivatives, num_derivatives);
+          double value = 0.0;
+          int info = 0;
+          // the reference's Python boundary hard-wires MaternNu2p5 here as well (:57)
+          check(cmoe_log_marginal_likelihood(CMOE_KERNEL_MATERN_NU_2P5, alpha, lengths.data(), X.data(), y.data(),
+                                             noise.data(), derivs.data(), num_derivatives, dim, num_sampled, 0, &value,
+                                             &info), info);
+          return value;
+        });
+  for (const char* name : {"compute_hyperparameter_grad_log_likelihood",
                            "multistart_hyperparameter_optimization", "restarted_hyperparameter_optimization",
                            "evaluate_log_likelihood_at_hyperparameter_list",
                            "heuristic_expected_improvement_optimization"}) {

@@ -83,6 +83,16 @@ int cmoe_device_count(void);
 int cmoe_gp_create(int kernel, double alpha, const double* lengths, const double* points_sampled,
                    const double* points_sampled_value, const double* noise_variance, const int* derivatives,
                    int num_derivatives, int dim, int num_sampled, int device, cmoe_gp** gp_out, int* info);
+/* log p(y | X, theta) = -1/2 (y-m)^T K^-1 (y-m) - sum_i log L_ii - n/2 log(2 pi) with K = K(X,X) + diag(noise by type)
+ * + 1e-6 I: LogMarginalLikelihoodEvaluator::ComputeLogLikelihood with FillLogLikelihoodState
+ * (gpp_model_selection.cpp:540-612); Python boundary compute_log_likelihood (gpp_python_model_selection.cpp:43-87) —
+ * the call the hyper-parameter MCMC of the front end makes thousands of times per refit.  One GP fit on the device
+ * (covariance build, Cholesky, K^-1 y) plus two reductions over n numbers.  A singular K yields -inf (the reference
+ * ignores the failed factorisation, :551-553).  SURVEY.md 8f rank 2, value only (no hyper-parameter gradient yet). */
+int cmoe_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* points_sampled,
+                                 const double* points_sampled_value, const double* noise_variance,
+                                 const int* derivatives, int num_derivatives, int dim, int num_sampled, int device,
+                                 double* log_likelihood, int* info);
 void cmoe_gp_destroy(cmoe_gp* gp);
 int cmoe_gp_dim(const cmoe_gp* gp);
 int cmoe_gp_num_sampled(const cmoe_gp* gp);

@@ -268,6 +268,15 @@ class CpuBackend:
             v = f(arr, M, _d(Xq), _d(Xp), q, p, int(num_mc), _d(best), _d(table), table.size, gptr)
         return (v, g) if grad else v
 
+    def log_marginal_likelihood(self, kernel, alpha, lengths, X, y, noise, derivs=None):
+        X = _f64(X)
+        N, dim = X.shape
+        derivs = _i32(derivs if derivs is not None else [])
+        f = self._fn("log_marginal_likelihood")
+        f.restype = ctypes.c_double
+        return f(int(kernel), ctypes.c_double(alpha), _d(_f64(lengths)), _d(X), _d(_f64(y).ravel()), _d(_f64(noise).ravel()),
+                 _i(derivs), derivs.size, dim, N)
+
     def max_threads(self):
         f = self._fn("max_threads")
         f.restype = ctypes.c_int

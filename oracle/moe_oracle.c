@@ -1131,3 +1131,29 @@ double oracle_ei_mcmc(const oracle_gp* const* gps, int num_gp, const double* Xq,
   free(tmp);
   return total / (double)num_gp;
 }
+
+/* ---- log marginal likelihood ------------------------------------------------------------------------------------------
+ * ref: LogMarginalLikelihoodEvaluator::FillLogLikelihoodState + ComputeLogLikelihood, gpp_model_selection.cpp:540-612:
+ * K = K(X,X) + diag(noise by type) + 1e-6 I (:546-549); y centred by the mean of the function values (:556-566);
+ *   log p = -1/2 y^T K^-1 y - sum_i log L_ii - n/2 log(2 pi).
+ * The reference ignores a failed factorisation (:551-553); here a singular K returns -HUGE_VAL. */
+double oracle_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X, const double* y,
+                                      const double* noise, const int* derivs, int g, int dim, int N) {
+  double* nz = dalloc(1 + g);
+  for (int m = 0; m <= g; ++m) nz[m] = noise[m] + 1.0e-6;
+  int lm = 0;
+  oracle_gp* gp = oracle_gp_create(kernel, alpha, lengths, X, y, nz, derivs, g, dim, N, &lm);
+  free(nz);
+  if (!gp) return -HUGE_VAL;
+  const int n = gp->n, bs = 1 + g;
+  double term1 = 0.0, term2 = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double yc = gp->y[i] - ((i % bs == 0) ? gp->mean : 0.0);
+    term1 += yc * gp->K_inv_y[i];
+    term2 -= log(gp->K_chol[(size_t)i * n + i]);
+  }
+  const double kLog2Pi = 1.8378770664093453;
+  const double out = -0.5 * term1 + term2 - 0.5 * (double)n * kLog2Pi;
+  oracle_gp_destroy(gp);
+  return out;
+}

@@ -58,6 +58,10 @@ double oracle_ei_mcmc(const oracle_gp* const* gps, int num_gp, const double* Xq,
 double oracle_posterior_mean_optimization(const oracle_gp* gp, int num_fidelity, const double* gd,
                                           const double* bounds, const double* initial_guess, double* best_point);
 
+/* log p(y | X, theta) of gpp_model_selection.cpp:540-612 (1e-6 jitter on top of the noise, centred y) */
+double oracle_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X, const double* y,
+                                      const double* noise, const int* derivs, int g, int dim, int N);
+
 void oracle_limit_update(const double* bounds, int dim, double max_relative_change, const double* current_point,
                          double* update);
 

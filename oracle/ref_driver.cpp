@@ -24,6 +24,7 @@
 #define private public
 #include "gpp_math.hpp"
 #undef private
+#include "gpp_model_selection.hpp"
 #include "gpp_covariance.hpp"
 #include "gpp_domain.hpp"
 #include "gpp_exception.hpp"
@@ -309,6 +310,17 @@ double ref_ei_mcmc(const double* hypers, const double* noises, int num_mcmc, con
     ev.ComputeGradExpectedImprovement(&st, grad);
   }
   return v;
+}
+
+// ---- log marginal likelihood (gpp_model_selection.cpp:540-612; Python boundary gpp_python_model_selection.cpp:43-87) ----
+// noise[1+g]; the state adds 1e-6 to the diagonal on top of the noise and ignores a failed factorisation (:546-553).
+double ref_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X, const double* y,
+                                   const double* noise, const int* derivs, int g, int dim, int N) {
+  auto c = MakeCovariance(kernel, dim, alpha, lengths);
+  LogMarginalLikelihoodEvaluator ev(X, y, derivs, g, dim, N);
+  std::vector<double> nz(noise, noise + 1 + g);
+  LogMarginalLikelihoodState st(ev, *c, nz);
+  return ev.ComputeLogLikelihood(st);
 }
 
 // LimitUpdate (gpp_domain.cpp:64-104) for pinning the restatement.

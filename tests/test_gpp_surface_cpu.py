@@ -70,7 +70,7 @@ def test_randomness_container():
 
 
 def test_off_path_entries_raise_the_library_exception():
-    for name in ("compute_log_likelihood", "multistart_hyperparameter_optimization",
+    for name in ("compute_hyperparameter_grad_log_likelihood", "multistart_hyperparameter_optimization",
                  "heuristic_expected_improvement_optimization", "run_cpp_tests"):
         with pytest.raises(C_GP.OptimalLearningException):
             getattr(C_GP, name)() if name == "run_cpp_tests" else getattr(C_GP, name)(1, 2, x=3)
@@ -83,6 +83,9 @@ def test_no_device_no_compute():
         C_GP.GaussianProcess([1.0, [1.0, 1.0]], [0.1, 0.2, 0.7, 0.4], [0.3, 0.9], [0.01], [], 0, 2, 2)
     with pytest.raises(C_GP.OptimalLearningException):
         C_GP.GaussianProcessMCMC([1.0, 1.0, 1.0], [0.01], [0.1, 0.2, 0.7, 0.4], [0.3, 0.9], [], 1, 0, 2, 2)
+    with pytest.raises(C_GP.OptimalLearningException):  # positional signature of gpp_python_model_selection.cpp:43-50
+        C_GP.compute_log_likelihood([0.1, 0.2, 0.7, 0.4], [0.3, 0.9], 2, 2, C_GP.LogLikelihoodTypes.log_marginal_likelihood,
+                                    [1.0, [1.0, 1.0]], [], 0, [0.01])
     # short input lists are rejected before any device work (BoundsException, like CopyPylistToVector's size check)
     with pytest.raises(C_GP.BoundsException):
         C_GP.GaussianProcess([1.0, [1.0, 1.0]], [0.1, 0.2], [0.3, 0.9], [0.01], [], 0, 2, 2)

@@ -67,3 +67,16 @@ def test_kg_se_fidelity_dimension_batched_line_search():
         v, g = ref.kg(cands[c], None, 16, 0.1, table, EXAMPLE_INNER_GD, unit_bounds(2), disc, num_fidelity=1, grad=True)
         np.testing.assert_allclose(kg[c], v, rtol=1e-7, atol=1e-10)
         np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("kernel,g_idx,N,dim", [(1, (), 20, 3), (0, (), 30, 2), (1, (0, 2), 12, 3), (0, (), 300, 4)])
+def test_log_marginal_likelihood_matches_checker(kernel, g_idx, N, dim):
+    """cmoe_log_marginal_likelihood (value only) = device fit + host reductions, against
+    LogMarginalLikelihoodEvaluator::ComputeLogLikelihood of the compiled reference (or its pinned restatement)."""
+    from cornell_moe_b200 import capi
+    from gpu_util import checker
+    prob = make_problem(N, dim, g_idx=g_idx, seed=5 + N)
+    args = (kernel, 1.3, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    got = capi.log_marginal_likelihood(*args)
+    want = checker().log_marginal_likelihood(*args)
+    np.testing.assert_allclose(got, want, rtol=1e-9)

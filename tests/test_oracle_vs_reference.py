@@ -220,3 +220,12 @@ def test_posterior_mean_optimization(libs, kernel, g_idx, nf):
     br, vr = gr.posterior_mean_optimization(x0, gd, unit_bounds(3 - nf), nf)
     np.testing.assert_allclose(bo, br, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(vo, vr, rtol=1e-12)
+
+
+@pytest.mark.parametrize("kernel,g_idx,N,dim", [(1, (), 20, 3), (0, (), 30, 2), (1, (0, 2), 12, 3), (0, (1,), 15, 2)])
+def test_log_marginal_likelihood(libs, kernel, g_idx, N, dim):
+    """gpp_model_selection.cpp:540-612 (1e-6 jitter on top of the noise, y centred by the mean of the function values)."""
+    o, r = libs
+    prob = make_problem(N, dim, g_idx=g_idx, seed=5 + N)
+    args = (kernel, 1.3, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    np.testing.assert_allclose(o.log_marginal_likelihood(*args), r.log_marginal_likelihood(*args), rtol=1e-12)
