@@ -79,4 +79,4 @@ def test_log_marginal_likelihood_matches_checker(kernel, g_idx, N, dim):
     args = (kernel, 1.3, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
     got = capi.log_marginal_likelihood(*args)
     want = checker().log_marginal_likelihood(*args)
-    np.testing.assert_allclose(got, want, rtol=1e-9)
+    np.testing.assert_allclose(got, want, rtol=1e-8)
