@@ -229,3 +229,44 @@ def test_log_marginal_likelihood(libs, kernel, g_idx, N, dim):
     prob = make_problem(N, dim, g_idx=g_idx, seed=5 + N)
     args = (kernel, 1.3, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
     np.testing.assert_allclose(o.log_marginal_likelihood(*args), r.log_marginal_likelihood(*args), rtol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_sweep(libs, seed):
+    """Random small configurations (kernel, dimension, derivative observations, q, p, fidelity dims, inner optimiser):
+    posterior with all gradients, q-EI and q-KG value + gradient of the restatement against the compiled reference."""
+    rng = np.random.default_rng(1000 + seed)
+    kernel = int(rng.integers(0, 2))
+    dim = int(rng.integers(2, 5))
+    g_idx = tuple(sorted(rng.choice(dim, size=int(rng.integers(0, min(3, dim) + 1)), replace=False).tolist()))
+    N = int(rng.integers(6, 16))
+    q, p = int(rng.integers(1, 4)), int(rng.integers(0, 3))
+    nf = int(rng.integers(0, 2)) if dim >= 3 else 0
+    prob = make_problem(N, dim, g_idx=g_idx, seed=2000 + seed, noise=float(rng.uniform(0.02, 0.2)))
+    go, gr = _gp_pair(libs, kernel, prob)
+    pts = rng.uniform(size=(q + p, dim))
+    want = ("mean", "grad_mean", "var", "chol_var", "grad_var", "grad_chol")
+    po, pr = go.posterior(pts, g_idx, want), gr.posterior(pts, g_idx, want)
+    for k in want:
+        np.testing.assert_allclose(po[k], pr[k], rtol=1e-8, atol=1e-10, err_msg=k)
+    Xq, Xp = pts[:q], pts[q:]
+    mc = 8
+    t_ei = rng.standard_normal(mc * (q + p))
+    best_ei = float(prob["y"][:: 1 + len(g_idx)].min()) + 0.3
+    vo, go_ = go.ei(Xq, Xp, mc, best_ei, t_ei, grad=True)
+    vr, gr_ = gr.ei(Xq, Xp, mc, best_ei, t_ei, grad=True)
+    np.testing.assert_allclose(vo, vr, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(go_, gr_, rtol=1e-7, atol=1e-10)
+    disc = rng.uniform(size=(int(rng.integers(1, 6)), dim - nf))
+    gd = [1, int(rng.integers(0, 8)), int(rng.integers(1, 3)), 3, float(rng.choice([0.0, 0.7])), float(rng.choice([0.5, 1.0, 2.0])),
+          float(rng.choice([0.1, 0.5])), 1e-9]
+    t_kg = rng.standard_normal((mc // 2) * (q + p) * (1 + len(g_idx)))
+    Xq_f, Xp_f = Xq.copy(), Xp.copy()
+    best_kg = float(rng.uniform(-0.5, 0.5))
+    ko, kgo, bpo = go.kg(Xq_f, Xp_f, mc, best_kg, t_kg, gd, unit_bounds(dim - nf), disc, num_fidelity=nf, grad=True,
+                         want_best_points=True)
+    kr, kgr, bpr = gr.kg(Xq_f, Xp_f, mc, best_kg, t_kg, gd, unit_bounds(dim - nf), disc, num_fidelity=nf, grad=True,
+                         want_best_points=True)
+    np.testing.assert_allclose(bpo, bpr, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(ko, kr, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(kgo, kgr, rtol=1e-5, atol=1e-8)
