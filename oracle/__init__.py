@@ -277,6 +277,16 @@ class CpuBackend:
         return f(int(kernel), ctypes.c_double(alpha), _d(_f64(lengths)), _d(X), _d(_f64(y).ravel()), _d(_f64(noise).ravel()),
                  _i(derivs), derivs.size, dim, N)
 
+    def grad_log_marginal_likelihood(self, kernel, alpha, lengths, X, y, noise, derivs=None):
+        X = _f64(X)
+        N, dim = X.shape
+        derivs = _i32(derivs if derivs is not None else [])
+        grad = np.zeros(dim + 1 + 1 + derivs.size)
+        self._fn("grad_log_marginal_likelihood")(int(kernel), ctypes.c_double(alpha), _d(_f64(lengths)), _d(X),
+                                                 _d(_f64(y).ravel()), _d(_f64(noise).ravel()), _i(derivs), derivs.size,
+                                                 dim, N, _d(grad))
+        return grad
+
     def max_threads(self):
         f = self._fn("max_threads")
         f.restype = ctypes.c_int

@@ -1157,3 +1157,107 @@ double oracle_log_marginal_likelihood(int kernel, double alpha, const double* le
   oracle_gp_destroy(gp);
   return out;
 }
+
+/* ---- gradient of the log marginal likelihood wrt the hyperparameters (alpha, l_1..l_dim, noise_0..noise_g) ---------
+ * ref: LogMarginalLikelihoodEvaluator::ComputeGradLogLikelihood, gpp_model_selection.cpp:629-677:
+ *   d/d theta_k = 1/2 a^T (dK/d theta_k) a - 1/2 tr(K^-1 dK/d theta_k),   a = K^-1 (y - m)
+ * with the per-pair blocks of SquareExponential::HyperparameterGradCovariance (gpp_covariance.cpp:245-317) and
+ * MaternNu2p5::HyperparameterGradCovariance (:461-489), assembled by BuildHyperparameterGradCovarianceMatrix
+ * (gpp_model_selection.cpp:386-444; dK/d noise_m = 1 on the diagonal entries of observation type m).
+ * Block layout: out[i_hyper + m*(dim+1) + n*(dim+1)*(1+g)], i_hyper in [0, dim].
+ * Quirk kept: the Matern routine only fills the value-value entry, so with derivative observations every other entry of
+ * its block is zero (the caller's buffer is zero-initialised and never written there), and at coincident points it
+ * returns d/d alpha = 1 (not k/alpha = 1 * ... for alpha != 1) and zero length derivatives (:469-473). */
+static void hyper_grad_block(int kernel, int dim, double alpha, const double* lsq, const double* p1, const double* p2,
+                             const int* derivs, int g, double* out) {
+  const int bs = 1 + g, hd = dim + 1;
+  memset(out, 0, (size_t)hd * bs * bs * sizeof(double));
+  const double r2 = weighted_sqdist(p1, p2, lsq, dim);
+  if (kernel != 0) {
+    if (r2 == 0.0) {
+      out[0] = 1.0;
+      return;
+    }
+    const double arg = SQRT5 * sqrt(r2);
+    const double poly = arg + 5.0 / 3.0 * r2;
+    const double e = exp(-arg);
+    out[0] = (1.0 + poly) * e;
+    for (int i = 0; i < dim; ++i) {
+      const double len = sqrt(lsq[i]);
+      const double dr2 = -2.0 * ((p1[i] - p2[i]) / len) * ((p1[i] - p2[i]) / len) / len;
+      const double dr = 0.5 * dr2 / sqrt(r2);
+      out[i + 1] = alpha * e * (5.0 / 3.0 * dr2 - poly * SQRT5 * dr);
+    }
+    return;
+  }
+  /* SquareExponential: every block entry is k * P with P in {1, u_a, -u_b, -u_a u_b + [a==b]/l_a^2}, u_a = (p2_a-p1_a)/l_a^2.
+   * d/d alpha = entry / alpha;  d/d l_i = entry * D_i^2 / l_i^3 + k dP/d l_i  with  d u_a/d l_i = -2 u_a / l_a [a==i],
+   * d (1/l_a^2)/d l_i = -2 / l_a^3 [a==i]. */
+  const double k = alpha * exp(-0.5 * r2);
+  for (int m = 0; m < bs; ++m) {
+    for (int n = 0; n < bs; ++n) {
+      const int a = m ? derivs[m - 1] : -1, b = n ? derivs[n - 1] : -1;
+      const double ua = (a >= 0) ? (p2[a] - p1[a]) / lsq[a] : 0.0;
+      const double ub = (b >= 0) ? (p2[b] - p1[b]) / lsq[b] : 0.0;
+      double P;
+      if (a < 0 && b < 0) P = 1.0;
+      else if (b < 0) P = ua;
+      else if (a < 0) P = -ub;
+      else P = -ua * ub + ((a == b) ? 1.0 / lsq[a] : 0.0);
+      double* o = out + (size_t)m * hd + (size_t)n * hd * bs;
+      o[0] = k * P / alpha;
+      for (int i = 0; i < dim; ++i) {
+        const double len = sqrt(lsq[i]);
+        const double D = p1[i] - p2[i];
+        double dP = 0.0;
+        if (a >= 0 && b < 0 && a == i) dP = -2.0 * ua / len;
+        if (a < 0 && b >= 0 && b == i) dP = 2.0 * ub / len;
+        if (a >= 0 && b >= 0) {
+          if (a == i) dP += 2.0 * ua * ub / len;
+          if (b == i) dP += 2.0 * ua * ub / len;
+          if (a == b && a == i) dP += -2.0 / (lsq[a] * len);
+        }
+        o[i + 1] = k * P * (D / len) * (D / len) / len + k * dP;
+      }
+    }
+  }
+}
+
+void oracle_grad_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X,
+                                         const double* y, const double* noise, const int* derivs, int g, int dim, int N,
+                                         double* grad /* [dim + 1 + 1 + g] */) {
+  const int nh = dim + 1 + 1 + g;
+  for (int k = 0; k < nh; ++k) grad[k] = 0.0;
+  double* nz = dalloc(1 + g);
+  for (int m = 0; m <= g; ++m) nz[m] = noise[m] + 1.0e-6;
+  int lm = 0;
+  oracle_gp* gp = oracle_gp_create(kernel, alpha, lengths, X, y, nz, derivs, g, dim, N, &lm);
+  free(nz);
+  if (!gp) return;
+  const int n = gp->n, bs = 1 + g, hd = dim + 1;
+  /* W = a a^T - K^-1 */
+  double* Kinv = dzero((size_t)n * n);
+  for (int i = 0; i < n; ++i) Kinv[(size_t)i * n + i] = 1.0;
+  oracle_potrs(gp->K_chol, n, n, Kinv);
+  double* blk = dalloc((size_t)hd * bs * bs);
+  for (int i = 0; i < N; ++i) {    /* column point */
+    for (int j = 0; j < N; ++j) {  /* row point */
+      hyper_grad_block(kernel, dim, alpha, gp->lengths_sq, gp->X + (size_t)j * dim, gp->X + (size_t)i * dim, gp->derivs,
+                       g, blk);
+      for (int m = 0; m < bs; ++m) {
+        for (int nn = 0; nn < bs; ++nn) {
+          const int row = j * bs + m, col = i * bs + nn;
+          const double W = gp->K_inv_y[row] * gp->K_inv_y[col] - Kinv[(size_t)col * n + row];
+          for (int h = 0; h < hd; ++h) grad[h] += 0.5 * W * blk[h + (size_t)m * hd + (size_t)nn * hd * bs];
+        }
+      }
+    }
+  }
+  for (int row = 0; row < n; ++row) {
+    const double W = gp->K_inv_y[row] * gp->K_inv_y[row] - Kinv[(size_t)row * n + row];
+    grad[hd + row % bs] += 0.5 * W;
+  }
+  free(blk);
+  free(Kinv);
+  oracle_gp_destroy(gp);
+}

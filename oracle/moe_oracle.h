@@ -62,6 +62,11 @@ double oracle_posterior_mean_optimization(const oracle_gp* gp, int num_fidelity,
 double oracle_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X, const double* y,
                                       const double* noise, const int* derivs, int g, int dim, int N);
 
+/* d log p / d (alpha, l_1..l_dim, noise_0..noise_g), gpp_model_selection.cpp:629-677 */
+void oracle_grad_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X,
+                                         const double* y, const double* noise, const int* derivs, int g, int dim, int N,
+                                         double* grad);
+
 void oracle_limit_update(const double* bounds, int dim, double max_relative_change, const double* current_point,
                          double* update);
 

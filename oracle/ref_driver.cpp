@@ -323,6 +323,16 @@ double ref_log_marginal_likelihood(int kernel, double alpha, const double* lengt
   return ev.ComputeLogLikelihood(st);
 }
 
+// gradient wrt (alpha, lengths[dim], noise[1+g]) (gpp_model_selection.cpp:629-677)
+void ref_grad_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* X, const double* y,
+                                      const double* noise, const int* derivs, int g, int dim, int N, double* grad) {
+  auto c = MakeCovariance(kernel, dim, alpha, lengths);
+  LogMarginalLikelihoodEvaluator ev(X, y, derivs, g, dim, N);
+  std::vector<double> nz(noise, noise + 1 + g);
+  LogMarginalLikelihoodState st(ev, *c, nz);
+  ev.ComputeGradLogLikelihood(&st, grad);
+}
+
 // LimitUpdate (gpp_domain.cpp:64-104) for pinning the restatement.
 void ref_limit_update(const double* bounds, int dim, double max_relative_change, const double* current_point,
                       double* update) {

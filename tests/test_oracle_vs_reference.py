@@ -270,3 +270,26 @@ def test_randomized_sweep(libs, seed):
     np.testing.assert_allclose(bpo, bpr, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(ko, kr, rtol=1e-8, atol=1e-11)
     np.testing.assert_allclose(kgo, kgr, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("kernel,g_idx,N,dim", [(0, (), 20, 3), (1, (), 20, 3), (0, (0, 2), 10, 3), (0, (1,), 12, 2),
+                                               (1, (0,), 10, 2)])
+def test_grad_log_marginal_likelihood(libs, kernel, g_idx, N, dim):
+    """d log p / d (alpha, lengths, noise by type), gpp_model_selection.cpp:629-677 — incl. the Matern routine's quirk of
+    filling only the value-value entry of its block.  Oracle groundwork for SURVEY.md 8f rank 2 (no device path yet)."""
+    o, r = libs
+    prob = make_problem(N, dim, g_idx=g_idx, seed=5 + N)
+    args = (kernel, 1.3, prob["lengths"] * np.linspace(1.0, 1.5, dim), prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    a, b = o.grad_log_marginal_likelihood(*args), r.grad_log_marginal_likelihood(*args)
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11 * np.abs(b).max())
+    if kernel == 0:  # and it is the derivative of the (pinned) value: central differences on alpha and the lengths
+        base = list(args)
+        for k in range(1 + dim):
+            def val(h):
+                al = 1.3 + (h if k == 0 else 0.0)
+                ls = np.array(base[2], dtype=np.float64)
+                if k > 0:
+                    ls[k - 1] += h
+                return o.log_marginal_likelihood(kernel, al, ls, *base[3:])
+            fd = (val(1e-5) - val(-1e-5)) / 2e-5
+            np.testing.assert_allclose(a[k], fd, rtol=2e-5, atol=1e-6)
