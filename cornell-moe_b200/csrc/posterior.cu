@@ -244,11 +244,6 @@ __global__ void __launch_bounds__(128) post_smith_kernel(int Q, int dim, int nd,
 #undef G_
 }
 
-__global__ void copy_cols_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t count) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < count) dst[i] = src[i];
-}
-
 }  // namespace
 
 void PosteriorBatch::configure(const cmoe_gp& gp, int nc_in, int num_in, const int* dPs_host, int gs_in, int nd_in,
