@@ -25,6 +25,33 @@ __global__ void scale_points_kernel(const __grid_constant__ KernelSpec spec, con
   if (e >= N * spec.dim) return;
   Xs[e] = X[e] * spec.inv_len[e % spec.dim];
 }
+
+// ---- incremental append (cmoe_gp_add_sampled_points) --------------------------------------------------------------
+// S22[i][j] -= sum_r T[r][i] T[r][j] for i >= j (T = L^-1 K12, n0 x mm column-major); one CTA per entry.
+__global__ void __launch_bounds__(256) append_schur_kernel(const double* __restrict__ T, int n0, int mm,
+                                                           double* __restrict__ S22) {
+  __shared__ double scratch[8];
+  int e = blockIdx.x, j = 0;  // lower-triangular entry index -> (i, j), column-major enumeration
+  while (e >= mm - j) {
+    e -= mm - j;
+    ++j;
+  }
+  const int i = j + e;
+  const double* ti = T + static_cast<size_t>(i) * n0;
+  const double* tj = T + static_cast<size_t>(j) * n0;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < n0; r += blockDim.x) acc = fma(ti[r], tj[r], acc);
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) S22[static_cast<size_t>(j) * mm + i] -= acc;
+}
+
+// K1[(n0 + i), r] = T[r, i]  (the new rows of the factor), K1 column-major with leading dimension n1
+__global__ void append_rows_kernel(const double* __restrict__ T, int n0, int mm, double* __restrict__ K1, int n1) {
+  const size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= static_cast<size_t>(n0) * mm) return;
+  const int i = static_cast<int>(e % mm), r = static_cast<int>(e / mm);
+  K1[static_cast<size_t>(r) * n1 + n0 + i] = T[static_cast<size_t>(i) * n0 + r];
+}
 }  // namespace
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
@@ -43,6 +70,7 @@ void require_device(int device) {
 
 void fit_gp(cmoe_gp* gp, bool mean_change) {
   drop_cached_plan(gp);  // the cached workspace refers to the previous training set
+  ++gp->generation;
   const KernelSpec& spec = gp->spec;
   const int N = gp->N, b = 1 + spec.g, n = N * b;
   gp->n = n;
@@ -90,6 +118,68 @@ void fit_gp(cmoe_gp* gp, bool mean_change) {
   gp->fit_usec[0] = t0.ms() * 1e3;
   gp->fit_usec[1] = t1.ms() * 1e3;
   gp->fit_usec[2] = t2.ms() * 1e3;
+}
+
+
+// O(N^2) append of m points to a fitted GP (the reference refits from scratch and leaves this as a TODO,
+// gpp_math.cpp:1699-1718):  K1 = [K K12; K12^T K22]  =>  L1 = [L 0; (L^-1 K12)^T  chol(K22 - K12^T K^-1 K12)].
+// Everything is built beside the live state and swapped in at the end, so a singular update leaves the handle intact.
+void append_points(cmoe_gp* gp, const double* new_points, const double* new_values, int m) {
+  const KernelSpec& spec = gp->spec;
+  const int dim = spec.dim, b = 1 + spec.g, N0 = gp->N, n0 = gp->n, mm = m * b, n1 = n0 + mm;
+  cudaStream_t s = gp->stream;
+  DevBuf<double> dXn(static_cast<size_t>(m) * dim), dXsn(static_cast<size_t>(m) * dim);
+  DevBuf<double> K1(static_cast<size_t>(n1) * n1), T(static_cast<size_t>(n0) * mm), S22(static_cast<size_t>(mm) * mm);
+  DevBuf<int> dDer(spec.g > 0 ? spec.g : 1), flag(1);
+  dXn.upload(new_points, static_cast<size_t>(m) * dim, s);
+  if (spec.g > 0) dDer.upload(spec.derivs, spec.g, s);
+  scale_points_kernel<<<(m * dim + 255) / 256, 256, 0, s>>>(spec, dXn.p, m, dXsn.p);
+  // old factor -> top-left block under the new leading dimension
+  CMOE_CUDA(cudaMemcpy2DAsync(K1.p, static_cast<size_t>(n1) * sizeof(double), gp->dK.p,
+                              static_cast<size_t>(n0) * sizeof(double), static_cast<size_t>(n0) * sizeof(double), n0,
+                              cudaMemcpyDeviceToDevice, s));
+  build_mix_covariance(spec, gp->dX.p, N0, dXn.p, m, dDer.p, spec.g, T.p, s);
+  trsm_lower(gp->dK.p, n0, T.p, n0, mm, false, s);  // T = L^-1 K12
+  CMOE_CUDA(cudaMemsetAsync(S22.p, 0, S22.count * sizeof(double), s));
+  build_covariance(spec, dXn.p, dXsn.p, m, gp->dnoise.p, S22.p, s);
+  append_schur_kernel<<<mm * (mm + 1) / 2, 256, 0, s>>>(T.p, n0, mm, S22.p);
+  append_rows_kernel<<<static_cast<unsigned>((static_cast<size_t>(n0) * mm + 255) / 256), 256, 0, s>>>(T.p, n0, mm, K1.p,
+                                                                                                   n1);
+  count_launch(3);
+  potrf_lower(S22.p, mm, flag.p, s);
+  int f = 0;
+  CMOE_CUDA(cudaMemcpyAsync(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaStreamSynchronize(s));
+  if (f != 0) {
+    throw Error(CMOE_ERR_SINGULAR,
+                "Covariance matrix (K) singular. Check for duplicate points_sampled (with 0 noise) and/or extreme "
+                "hyperparameter values.",
+                n0 + f);
+  }
+  CMOE_CUDA(cudaMemcpy2DAsync(K1.p + static_cast<size_t>(n0) * n1 + n0, static_cast<size_t>(n1) * sizeof(double), S22.p,
+                              static_cast<size_t>(mm) * sizeof(double), static_cast<size_t>(mm) * sizeof(double), mm,
+                              cudaMemcpyDeviceToDevice, s));
+  // commit: host copies, device arrays, mean, K^-1 (y - mean)
+  drop_cached_plan(gp);
+  ++gp->generation;
+  gp->hX.insert(gp->hX.end(), new_points, new_points + static_cast<size_t>(m) * dim);
+  gp->hy.insert(gp->hy.end(), new_values, new_values + static_cast<size_t>(mm));
+  gp->N = N0 + m;
+  gp->n = n1;
+  gp->dK = std::move(K1);
+  gp->dX.upload(gp->hX.data(), gp->hX.size(), s);
+  gp->dy.upload(gp->hy.data(), gp->hy.size(), s);
+  gp->dXs.ensure(static_cast<size_t>(gp->N) * dim);
+  gp->dKinvY.ensure(n1);
+  scale_points_kernel<<<(gp->N * dim + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, gp->N, gp->dXs.p);
+  double mu = 0.0;  // mean_ = average of the function values (gpp_math.cpp:498-504), same summation order
+  for (int i = 0; i < gp->N; ++i) mu += gp->hy[static_cast<size_t>(i) * b];
+  gp->mean = mu / gp->N;
+  center_values_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(gp->dy.p, gp->N, b, gp->mean, gp->dKinvY.p);
+  count_launch(2);
+  potrs_lower(gp->dK.p, n1, gp->dKinvY.p, n1, 1, s);
+  CMOE_CUDA(cudaGetLastError());
+  CMOE_CUDA(cudaStreamSynchronize(s));
 }
 
 }  // namespace cmoe
@@ -243,11 +333,8 @@ int cmoe_gp_add_sampled_points(cmoe_gp* gp, const double* new_points, const doub
   return guarded(info, [&] {
     CMOE_REQUIRE(num_new_points >= 0, CMOE_ERR_BOUNDS, "num_new_points must be >= 0");
     require_device(gp->device);
-    const int dim = gp->spec.dim, b = 1 + gp->spec.g;
-    gp->hX.insert(gp->hX.end(), new_points, new_points + static_cast<size_t>(num_new_points) * dim);
-    gp->hy.insert(gp->hy.end(), new_points_value, new_points_value + static_cast<size_t>(num_new_points) * b);
-    gp->N += num_new_points;
-    fit_gp(gp, true);
+    if (num_new_points == 0) return;
+    append_points(gp, new_points, new_points_value, num_new_points);
   });
 }
 

@@ -142,6 +142,7 @@ struct cmoe_gp {
   cmoe::DevBuf<double> dKinvY;    // [n]
   cmoe::DevBuf<int> dFlag;        // [1] Cholesky failure index
   double fit_usec[3] = {0, 0, 0};
+  uint64_t generation = 0;  // bumped by every (re)fit / append: explicit q-KG plans are bound to one generation
   // one cached q-KG plan (device workspace) so that repeated cmoe_kg_eval calls with the same configuration — every
   // step of an outer optimiser — do not re-allocate gigabytes of scratch; owned by kg.cu
   mutable struct cmoe_kg_plan* cached_plan = nullptr;
@@ -162,6 +163,8 @@ void drop_cached_plan(const cmoe_gp* gp);
 // failing leading-minor index (k+1), with the reference's pivot test (> 1e-16).  Enqueued on `s` (large systems also
 // use an internal side stream for the look-ahead update); returns after the factorisation has completed.
 void potrf_lower(double* A, int n, int* flag, cudaStream_t s);
+// potrf_coop.cu: one cooperative launch per 256-column panel (n >= 1024, even); false = not applicable, A untouched
+bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s);
 // X <- (L L^T)^-1 X for nrhs right-hand sides; X is n*nrhs column-major with leading dimension ldx.
 void potrs_lower(const double* L, int n, double* X, int ldx, int nrhs, cudaStream_t s);
 // X <- L^-1 X (trans = false) or L^-T X (trans = true).  nrhs <= 4 with n >= 1024 takes the single-launch chained

@@ -422,6 +422,7 @@ using namespace cmoe;  // NOLINT
 // -----------------------------------------------------------------------------------------------------------------
 struct cmoe_kg_plan {
   const cmoe_gp* gp = nullptr;
+  uint64_t gp_generation = 0;  // the fit this plan's workspace was sized for
   int nf = 0, num_pts = 0, max_cand = 0, q = 0, p = 0, U = 0, num_mc = 0, ps = 0, M = 0;
   bool want_grad = false;
   double best_so_far = 0.0;
@@ -580,6 +581,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     require_device(gp->device);
     std::unique_ptr<cmoe_kg_plan> pl(new cmoe_kg_plan());
     pl->gp = gp;
+    pl->gp_generation = gp->generation;
     pl->nf = num_fidelity;
     pl->num_pts = num_pts;
     pl->max_cand = max_candidates;
@@ -762,6 +764,8 @@ int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_ca
   return guarded(nullptr, [&] {
     CMOE_REQUIRE(num_candidates >= 1 && num_candidates <= plan->max_cand, CMOE_ERR_BOUNDS,
                  "num_candidates exceeds the plan capacity");
+    CMOE_REQUIRE(plan->gp_generation == plan->gp->generation, CMOE_ERR_INVALID_VALUE,
+                 "the GaussianProcess was refitted after this plan was created; create a new plan");
     require_device(plan->gp->device);
     plan->nc = num_candidates;
     {
@@ -787,6 +791,8 @@ int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_ca
 int cmoe_kg_plan_run(cmoe_kg_plan* plan) {
   return guarded(nullptr, [&] {
     CMOE_REQUIRE(plan->nc >= 1, CMOE_ERR_INVALID_VALUE, "no candidates uploaded");
+    CMOE_REQUIRE(plan->gp_generation == plan->gp->generation, CMOE_ERR_INVALID_VALUE,
+                 "the GaussianProcess was refitted after this plan was created; create a new plan");
     require_device(plan->gp->device);
     cudaStream_t s = plan->gp->stream;
     const int l0 = launches_issued();

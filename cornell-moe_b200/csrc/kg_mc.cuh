@@ -19,6 +19,8 @@
 #include "device_math.cuh"
 #include "internal.cuh"
 
+#include "ptx_util.cuh"
+
 namespace cmoe {
 
 // Range contract of the shared-memory fast path.  Its exp (exp_tab, no per-call guard) needs |t| < 2^31 ln2 / 64 =
@@ -71,35 +73,6 @@ struct KgAccParams {
   double* Gu;           // [nc][U][DIM]    sum_i c_iu Bpart(Xu_u, x*_i) x~*_i
   double* GkB;          // [nc][U]         sum_i c_iu Bpart(Xu_u, x*_i)
 };
-
-// ---- small PTX helpers: mbarrier + TMA bulk copy (global -> shared) ----------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 
 // exp(t) = 2^k * 2^(i/64) * e^r with |r| <= ln2/128: 64-entry table in shared memory + degree-5 Taylor polynomial
 // (truncation r^6/720 <= 3.5e-17 relative).  10 FP64-pipe instructions instead of 15 for exp_fast; same integer-side
@@ -1108,11 +1081,8 @@ const KgDispatchEntry* find_kg_entry(int kernel, int dim, int Q, bool need_gen);
 
 template <int KERNEL, int DIM, int QP>
 void launch_kg_mc(const KgMcParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(kg_mc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  // function attributes are per device: set on every launch (cheap), never cached process-wide
+  cudaFuncSetAttribute(kg_mc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   kg_mc_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, smem, s>>>(p);
 }
 template <int KERNEL, int DIM, int QP>
@@ -1122,11 +1092,7 @@ void launch_kg_mc_gen(const KgMcParams& p, dim3 grid, size_t, cudaStream_t s) {
 template <int KERNEL, int DIM, int QP>
 void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {
   const size_t smem = 2 * static_cast<size_t>(kAccTile) * (DIM + QP + 1) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(kg_acc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr = true;
-  }
+  cudaFuncSetAttribute(kg_acc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   kg_acc_kernel<KERNEL, DIM, QP><<<grid, 128, smem, s>>>(p);
 }
 template <int DIM, int QP>

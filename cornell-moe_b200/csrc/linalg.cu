@@ -14,108 +14,12 @@
 
 #include "device_math.cuh"
 #include "internal.cuh"
+#include "linalg_dev.cuh"
+#include "ptx_util.cuh"
 
 namespace cmoe {
 
 namespace {
-
-constexpr int NB = 64;        // Cholesky block size == K depth of one DMMA tile product
-constexpr int LDT = NB + 4;   // smem leading dimension: 68 = 4 (mod 16) makes the DMMA fragment loads conflict-free
-constexpr double kPivotTol = 1.0e-16;  // gpp_linear_algebra.cpp:118
-
-// --------------------------------------------------------------------------------------------------------------
-// Diagonal-block factorisation + panel solve.  The column recurrence sqrt -> scale -> update is the latency-critical
-// chain of the whole factorisation (n/64 dependent block steps), so it runs out of REGISTERS: a warp factors a 32x32
-// block with lane r holding row r and the pivot / multiplier columns travelling by shuffle — no barriers, no shared
-// memory round trips inside the recurrence.
-// --------------------------------------------------------------------------------------------------------------
-constexpr int PT = 128;  // threads of the panel kernel: one panel row per thread
-
-// The register-resident recurrences below are written as SHORT LOOPS over a rotating register window (after step k
-// the window is shifted so that slot 0 is always the pivot column) instead of fully unrolled triangles: straight-line
-// code of thousands of instructions that execute once each runs at instruction-fetch speed (measured: 18 us for a
-// 64x64 factorisation, 25 us for the panel solve), a loop body of a few hundred instructions stays in the I-cache.
-// Slots that rotate past the end of the row compute on padding and are never stored.
-
-// In-register Cholesky of a 32x32 block: on entry a[c] = A[lane][c] (c <= lane meaningful).  The finished column j of
-// L is written to LT[(col0 + j) * LTS + col0 + lane] (transposed factor) and rd[col0 + j] = 1/L_jj (FAST) or L_jj.
-// Returns 0 or the 1-based index of the first pivot that fails `> 1e-16` (gpp_linear_algebra.cpp:118,141-142); the
-// outcome is warp-uniform and only evaluated at the end (the arithmetic after a failed pivot is discarded).
-// The finished column is broadcast through a double-buffered shared column (one STS + one __syncwarp per column).
-// FAST: sqrt and divide through one reciprocal square root + Newton corrections — the same results as sqrt()/"/" to
-// the last bit in all but rare halfway cases (and exactly when the true results are representable) at a third of the
-// dependent latency; small systems (known-answer cases) keep IEEE sqrt / divide.
-constexpr int LTS = NB + 2;  // row stride of the transposed factor (even: 16-byte aligned rows)
-template <bool FAST>
-__device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __restrict__ colbuf /* [2][64], [32..63] = 0 */,
-                                           double* __restrict__ LT, double* __restrict__ rd, int col0) {
-  int fail = 0;
-#pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const double piv = __shfl_sync(0xffffffffu, a[0], j);
-    fail = (fail == 0 && !(piv > kPivotTol)) ? j + 1 : fail;
-    double l, q;
-    if (FAST) {
-      const double y = rsqrt(piv);
-      l = piv * y;
-      l = fma(0.5 * y, fma(-l, l, piv), l);
-      q = a[0] * y;
-      q = fma(fma(-q, l, a[0]), y, q);
-    } else {
-      l = sqrt(piv);
-      q = a[0] / l;
-    }
-    const double lj = (lane == j) ? l : q;
-    if (lane >= j) LT[(col0 + j) * LTS + col0 + lane] = lj;
-    if (FAST) {
-      double r = rsqrt(piv);            // ~ 1/l
-      r = fma(fma(-l, r, 1.0), r, r);   // one Newton step on 1/l: no divide on the per-column critical path
-      if (lane == j) rd[col0 + j] = r;
-    } else {
-      if (lane == j) rd[col0 + j] = l;
-    }
-    double* col = colbuf + (j & 1) * 64;
-    col[lane] = lj;
-    __syncwarp();
-    // window slot k <-> column j + k; multipliers L[j+k][j] = col[j+k] (zero beyond the block)
-#pragma unroll
-    for (int k = 1; k < 32; ++k) a[k - 1] = fma(-lj, col[j + k], a[k]);
-    a[31] = 0.0;
-  }
-  return fail;
-}
-
-// STEPS steps of  x <- x L^-T  for one row held in a rotating register window of W slots: slot i holds column
-// cbase + i on entry and column cbase + STEPS + i on exit.  The solved value of column k is handed to emit(k, value).
-// LT[k*LTS + c] = L[c][k]; cbase and UNR are multiples of 2 and LTS is even, so pairs of multipliers come as one
-// 16-byte broadcast load; rows of LT must be followed by readable padding (slots past the end of the row read it and
-// are never emitted).
-template <int W, int STEPS, int UNR, bool FAST, typename Emit>
-__device__ __forceinline__ void solve_steps_rot(double (&x)[W], const double* __restrict__ LT,
-                                                const double* __restrict__ rd, int cbase, Emit&& emit) {
-  static_assert(STEPS % UNR == 0 && UNR % 2 == 0 && W % 2 == 0, "even windows, whole bodies");
-#pragma unroll 1
-  for (int kb = 0; kb < STEPS; kb += UNR) {
-#pragma unroll
-    for (int s = 0; s < UNR; ++s) {
-      const int k = cbase + kb + s;
-      const double xk = FAST ? x[s] * rd[k] : x[s] / rd[k];
-      emit(k, xk);
-      const double* lt = LT + k * LTS + cbase + kb;  // 16-byte aligned
-      if (((s + 1) & 1) != 0) x[s + 1] = fma(-xk, lt[s + 1], x[s + 1]);
-#pragma unroll
-      for (int i = (s + 2) & ~1; i < W; i += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(lt + i);
-        x[i] = fma(-xk, v.x, x[i]);
-        x[i + 1] = fma(-xk, v.y, x[i + 1]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i + UNR < W; ++i) x[i] = x[i + UNR];
-#pragma unroll
-    for (int i = W - UNR; i < W; ++i) x[i] = 0.0;
-  }
-}
 
 // Factor the 64x64 block in shared memory S (row r, col c at S[r][c]; rows/cols beyond the matrix padded with the
 // identity): [L11 0; L21 L22] via chol32(A11), L21 = A21 L11^-T, A22 -= L21 L21^T, chol32(A22).  The factor is left
@@ -246,12 +150,6 @@ __global__ void __launch_bounds__(PT) potrf_panel_kernel(double* __restrict__ A,
 //     finish sooner than a few 128x128 ones, and this update sits on the critical path of the chain.
 // 4 warps, each owning a 32x32 sub-tile = 4x4 m8n8k4 fragments.
 // --------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
 __global__ void __launch_bounds__(128) dmma_tile_kernel(double* __restrict__ A, int lda, int n, int k0, int nb,
                                                         int col_tiles, const int* __restrict__ flag, int kdepth) {
   extern __shared__ double smem[];
@@ -648,14 +546,6 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
 // --------------------------------------------------------------------------------------------------------------
 constexpr int CT = 512;  // threads of the chained solver
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void wait_ready(const int* flag, int* abort_flag) {
   for (unsigned spins = 0; ld_acquire(flag) == 0; ++spins) {
     if (spins > (1u << 22)) {  // ~1 s: far beyond any legitimate wait
@@ -857,6 +747,7 @@ struct LookaheadCtx {
 //   and (b) everything to the right of it, on a side stream confined to a subset of the SMs so that it overlaps the
 //   next panel's latency-bound chain.  (a) of panel p waits for (b) of panel p-1 (both touch the same columns).
 void potrf_lower(double* A, int n, int* flag, cudaStream_t s) {
+  if (potrf_lower_coop(A, n, flag, s)) return;
   constexpr int W = 256;  // outer panel width (4 inner blocks of NB)
   const size_t smem = 2 * NB * LDT * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(dmma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

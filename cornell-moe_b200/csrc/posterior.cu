@@ -162,6 +162,64 @@ __global__ void __launch_bounds__(kChunk) post_gradE_kernel(const __grid_constan
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// Mean (and its gradient) of ANY number of points without forming K^-1 K*: one CTA per point,
+//   mu(x, type a) = [a == value] mean + sum_j sum_cc cov(x type a, X_j type cc) beta_(j,cc)
+// (GaussianProcess::ComputeMeanOfPoints / ComputeGradMeanOfPoints, gpp_math.cpp:600-653; the points are independent, so
+// the (q+p)(1+g) <= 96 bound of the variance kernels does not apply — this is the screening call the front end makes
+// with 1e3-1e4 points).  Threads = (output, slice of the training points); slices are combined in a fixed order.
+// --------------------------------------------------------------------------------------------------------------
+constexpr int kMeanThreads = 128;
+
+__global__ void __launch_bounds__(kMeanThreads) post_mean_only_kernel(const __grid_constant__ KernelSpec spec, int N,
+                                                                      double mean, const double* __restrict__ X,
+                                                                      const double* __restrict__ beta,
+                                                                      const double* __restrict__ P,
+                                                                      const int* __restrict__ dPs, int gs,
+                                                                      double* __restrict__ mu,
+                                                                      double* __restrict__ gmu) {
+  __shared__ double Pi[CMOE_MAX_DIM];
+  __shared__ double red[kMeanThreads];
+  const int pt = blockIdx.x, bs = 1 + gs, dim = spec.dim, b1 = 1 + spec.g;
+  const int per = gmu ? 1 + dim : 1;       // outputs per row type: value [+ dim gradient components]
+  const int nout = bs * per;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < dim; e += blockDim.x) Pi[e] = P[static_cast<size_t>(pt) * dim + e];
+  __syncthreads();
+  for (int o0 = 0; o0 < nout; o0 += kMeanThreads) {
+    const int group = min(nout - o0, kMeanThreads);  // outputs handled in this pass
+    const int nparts = kMeanThreads / group;
+    const int o = o0 + tid % group, part = tid / group;
+    double acc = 0.0;
+    if (part < nparts) {
+      const int a1 = row_type((o / per), dPs), comp = o % per;
+      for (int j = part; j < N; j += nparts) {
+        const double* xj = X + static_cast<size_t>(j) * dim;
+        const KParts kp = kernel_parts(spec, weighted_sqdist(spec, Pi, xj));
+        for (int cc = 0; cc < b1; ++cc) {
+          const int a2 = row_type(cc, spec.derivs);
+          const double v = (comp == 0) ? cov_entry(spec, kp, Pi, xj, a1, a2)
+                                       : grad_cov_entry(spec, kp, Pi, xj, a1, a2, comp - 1);
+          acc = fma(v, beta[static_cast<size_t>(j) * b1 + cc], acc);
+        }
+      }
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (part == 0 && tid < group) {
+      double t = 0.0;
+      for (int q = 0; q < nparts; ++q) t += red[q * group + tid];
+      const int row = o / per, comp = o % per;
+      if (comp == 0) {
+        mu[static_cast<size_t>(pt) * bs + row] = ((row == 0) ? mean : 0.0) + t;
+      } else {
+        gmu[(static_cast<size_t>(pt) * bs + row) * dim + comp - 1] = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
 // grad variance wrt point p (reference layout gv[delta + row*dim + col*dim*Q]); grid (nc, nd)
 // With F(delta; colp, other) = -E[delta, other, colp] + d cov(P_p type(colp), P_other type(other)) / d P_p,delta :
 //   row in p, col not in p (and the mirror): F ;  both in p: F(col,row) + F(row,col) ;  neither: 0.
@@ -331,6 +389,22 @@ extern "C" int cmoe_gp_posterior(const cmoe_gp* gp, const double* sets, int num_
     cudaStream_t s = gp->stream;
     const bool need_grad = grad_mean || grad_var || grad_chol;
     const bool need_chol = chol_var || grad_chol;
+    if (!var && !chol_var && !grad_var && !grad_chol) {
+      // mean / grad mean only: every point is independent — any number of points, no K^-1 K*
+      const size_t npts = static_cast<size_t>(num_sets) * num_pts, bs = 1 + g_s, dim = gp->spec.dim;
+      DevBuf<double> dP(npts * dim), dmu(npts * bs), dgmu(grad_mean ? npts * bs * dim : 0);
+      DevBuf<int> dd(g_s > 0 ? g_s : 1);
+      dP.upload(sets, npts * dim, s);
+      if (g_s > 0) dd.upload(derivs_s, g_s, s);
+      post_mean_only_kernel<<<static_cast<unsigned>(npts), kMeanThreads, 0, s>>>(
+          gp->spec, gp->N, gp->mean, gp->dX.p, gp->dKinvY.p, dP.p, dd.p, g_s, dmu.p, grad_mean ? dgmu.p : nullptr);
+      count_launch();
+      CMOE_CUDA(cudaGetLastError());
+      if (mean) dmu.download(mean, npts * bs, s);
+      if (grad_mean) dgmu.download(grad_mean, npts * bs * dim, s);
+      CMOE_CUDA(cudaStreamSynchronize(s));
+      return;
+    }
     PosteriorBatch pb;
     pb.configure(*gp, num_sets, num_pts, derivs_s, g_s, need_grad ? num_pts : 0, s);
     pb.P.upload(sets, static_cast<size_t>(num_sets) * num_pts * gp->spec.dim, s);

@@ -1,0 +1,577 @@
+// Blocked FP64 Cholesky for large systems: ONE cooperative launch per 256-column outer panel.
+//
+// Replaces ComputeCholeskyFactorL (reference gpp_linear_algebra.cpp:109-148; pivot test `> 1e-16`, failing leading
+// minor k+1) for n >= 1024.  The launch-per-64-columns path of linalg.cu (8 dependent launches per outer panel, ~40 us
+// per 64-column step) stays for small systems, where exact IEEE sqrt / divide keep the known-answer cases exact.
+//
+// Launch p does two things with the whole machine (grid = #SMs, 1 CTA / SM, all co-resident):
+//   * the trailing update with panel p-1 (K = 256):  C -= L_rows L_cols^T on the FP64 tensor pipe (DMMA m8n8k4), operand
+//     chunks streamed by TMA tensor copies (cp.async.bulk.tensor.2d -> SASS UTMALDG) through a 5-stage mbarrier ring,
+//     accumulators initialised from C so the epilogue is a plain store.  Tiles come from one atomic counter; the
+//     tiles that cover the columns of panel p ("(a)" tiles, 128 x 64, top rows first) are handed out before the rest
+//     ("(b)" tiles, 128 x 128) and bump a per-row-tile arrival counter when they are done;
+//   * the factorisation of panel p itself: CTA r < ceil((n - p0) / 64) owns 64 rows of the panel (a 64 x 256 slab that
+//     stays in shared memory) and starts as soon as the (a) tiles of its rows have arrived.  The four 64-column steps
+//     are chained by release/acquire flags through L2 instead of kernel boundaries: CTA kk factors the diagonal block
+//     (register Cholesky of two 32x32 halves by one warp), publishes L_kk^-1, every other CTA forms
+//     X = A_ik L_kk^-T as ONE 64x64x64 DMMA product (no per-row substitution recurrence) and applies it to its own
+//     columns; the X tiles of the rows inside the panel are published the same way.  The critical path per 64 columns
+//     is  factor + one flag hand-over + two 64^3 products.
+// When its panel work is done a CTA joins the (b) tiles, so the trailing update of panel p-1 overlaps the (latency-
+// bound) chain of panel p on the same launch — no side stream, no events.
+//
+// Determinism: every C tile receives exactly one update per panel, with a fixed K order; which CTA computes it does
+// not matter.  Failure: the factoring CTA writes the 1-based leading-minor index to *flag; every wait loop polls it.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+
+#include "device_math.cuh"
+#include "internal.cuh"
+#include "linalg_dev.cuh"
+#include "ptx_util.cuh"
+
+namespace cmoe {
+namespace {
+
+constexpr int CW = 256;                // outer panel width = K depth of the trailing update
+constexpr int CTHREADS = 512;          // 16 warps
+constexpr int TM = 128;                // rows of a trailing-update tile
+constexpr int KC = 16;                 // K chunk per pipeline stage
+constexpr int OLD = 132;               // rows of an operand box = leading dimension in shared memory (4 mod 16)
+constexpr int STAGES = 5;
+constexpr int PREFETCH = 3;            // chunks in flight ahead of the consumers
+constexpr int SLD = NB + 4;            // leading dimension of slab / staging blocks (68 = 4 mod 16)
+constexpr int BLK = SLD * NB;          // doubles per 64-column block buffer (34 816 B, a multiple of 128)
+constexpr int OPBOX = KC * OLD;        // doubles per operand box
+constexpr int NBUF = 6;                // 4 slab blocks + 2 staging buffers
+constexpr int kSyncPerPanel = 160;     // ints: [0] tile counter, [1..4] F, [5..20] X[j][kk], [32..] row-tile arrivals
+constexpr size_t kCoopSmem = static_cast<size_t>(NBUF) * BLK * sizeof(double) + 128;
+static_assert(STAGES * 2 * OPBOX <= NBUF * BLK, "operand ring must fit into the slab buffers");
+
+struct CoopParams {
+  double* A;
+  int lda, n;
+  int p0, pw;        // panel factored by this launch
+  int* flag;         // failure index (device)
+  int* sync;         // this launch's sync area
+  double* scratch;   // [4][BLK] published inverses
+  int* abort_flag;   // set when a wait gives up
+};
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// returns false if the factorisation failed / aborted while waiting
+__device__ __forceinline__ bool wait_flag(const int* f, int target, const int* fail, int* abort_flag) {
+  for (unsigned spins = 0;; ++spins) {
+    if (ld_acquire(f) >= target) return true;
+    if ((spins & 31u) == 31u && (ld_volatile(fail) != 0 || ld_volatile(abort_flag) != 0)) return false;
+    if (spins > (1u << 24)) {
+      atomicExch(abort_flag, 1);
+      return false;
+    }
+    __nanosleep(32);
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Trailing-update tile:  C(128 x TN) -= A[row0.., q0..q0+255] * A[col0.., q0..q0+255]^T
+// --------------------------------------------------------------------------------------------------------------
+template <int TN>
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring, uint64_t* full, uint64_t* empty,
+                                          uint32_t& gchunk, double* __restrict__ A, int lda, int n, int row0, int col0,
+                                          int q0) {
+  constexpr int NF = TN / 32;  // 8-column fragments per warp
+  constexpr int NCH = CW / KC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * (TN / 4);
+  const int lr = lane >> 2, lc = lane & 3;
+  const uint32_t g0 = gchunk;
+  auto issue = [&](int c) {
+    const uint32_t g = g0 + c;
+    const int st = g % STAGES;
+    mbar_wait_spin(&empty[st], ((g / STAGES) + 1) & 1);
+    mbar_expect_tx(&full[st], 2 * OPBOX * sizeof(double));
+    tma_load_2d(ring + st * 2 * OPBOX, mapOp, row0, q0 + c * KC, &full[st]);
+    tma_load_2d(ring + st * 2 * OPBOX + OPBOX, mapOp, col0, q0 + c * KC, &full[st]);
+  };
+  if (tid == 0) {
+#pragma unroll 1
+    for (int c = 0; c < PREFETCH; ++c) issue(c);
+  }
+  // accumulators start as C: D = (-A) B + C, so the epilogue is a plain store
+  double acc[4][NF][2];
+  double* Cg = A + static_cast<size_t>(col0) * lda + row0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm + i * 8 + lr;
+#pragma unroll
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = wn + j * 8 + lc * 2 + h;
+        acc[i][j][h] = (row0 + r < n && col0 + c < n) ? Cg[static_cast<size_t>(c) * lda + r] : 0.0;
+      }
+  }
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    if (tid == 0 && c + PREFETCH < NCH) issue(c + PREFETCH);
+    const uint32_t g = g0 + c;
+    const int st = g % STAGES;
+    mbar_wait_spin(&full[st], (g / STAGES) & 1);
+    const double* as = ring + st * 2 * OPBOX;
+    const double* bs = as + OPBOX;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      double a[4], b[NF];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = -as[(kk + lc) * OLD + wm + i * 8 + lr];
+#pragma unroll
+      for (int j = 0; j < NF; ++j) b[j] = bs[(kk + lc) * OLD + wn + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  gchunk = g0 + NCH;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm + i * 8 + lr;
+#pragma unroll
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = wn + j * 8 + lc * 2 + h;
+        if (row0 + r < n && col0 + c < n) Cg[static_cast<size_t>(c) * lda + r] = acc[i][j][h];
+      }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// 64 x 64 tile product out of shared memory for the panel chain: acc (+)= (+-A)(64 x K) * B(64 x K)^T, operands stored
+// [k][SLD].  16 warps x (16 x 16).  TRI: B is the transposed inverse of a lower-triangular block (B[k][c] = 0 for
+// k > c), so the K loop of a warp stops at its last column.
+// --------------------------------------------------------------------------------------------------------------
+template <bool NEG, bool TRI>
+__device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double* __restrict__ As,
+                                           const double* __restrict__ Bs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int kend = TRI ? wn + 16 : NB;
+#pragma unroll 4
+  for (int kk = 0; kk < kend; kk += 4) {
+    double a[2], b[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double v = As[(kk + lc) * SLD + wm + i * 8 + lr];
+      a[i] = NEG ? -v : v;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b[j] = Bs[(kk + lc) * SLD + wn + j * 8 + lr];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// fragment <-> block coordinates of tile64_mma
+#define CMOE_FRAG_LOOP(BODY)                                            \
+  {                                                                     \
+    const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;       \
+    const int wm_ = (warp_ & 3) * 16, wn_ = (warp_ >> 2) * 16;          \
+    const int lr_ = lane_ >> 2, lc_ = lane_ & 3;                        \
+    _Pragma("unroll") for (int i = 0; i < 2; ++i)                       \
+    _Pragma("unroll") for (int j = 0; j < 2; ++j)                       \
+    _Pragma("unroll") for (int h = 0; h < 2; ++h) {                     \
+      const int row = wm_ + i * 8 + lr_, col = wn_ + j * 8 + lc_ * 2 + h; \
+      BODY                                                              \
+    }                                                                   \
+  }
+
+// Factor the 64 x 64 diagonal block held in `blk` ([c*SLD + r], lower part meaningful) and build the packet
+// M[m*SLD + j] = (L^-1)[j][m] in `Minv`.  LT (transposed factor, [c*LTS + r]) lives in `LT`.  Returns 0 or the 1-based
+// index of the failing pivot.  All CTHREADS threads call.
+__device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* __restrict__ LT,
+                                             double* __restrict__ Minv, double* __restrict__ colbuf,
+                                             double* __restrict__ rd, int* __restrict__ sfail) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < NB * LTS + NB; e += CTHREADS) LT[e] = 0.0;
+  for (int e = tid; e < 128; e += CTHREADS) colbuf[e] = 0.0;
+  for (int e = tid; e < BLK; e += CTHREADS) Minv[e] = 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[c * SLD + lane] : 0.0;
+    const int f = chol32_warp<true>(a, lane, colbuf, LT, rd, 0);
+    if (lane == 0) *sfail = f;
+  }
+  __syncthreads();
+  if (*sfail) return *sfail;
+  if (warp == 0) {
+    // L21 = A21 L11^-T: lane r solves row 32 + r
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = blk[c * SLD + 32 + lane];
+    solve_steps_rot<32, 32, 4, true>(x, LT, rd, 0, [&](int k, double v) {
+      blk[k * SLD + 32 + lane] = v;
+      LT[k * LTS + 32 + lane] = v;
+    });
+  } else if (warp == 1) {
+    // column `lane` of L11^-1 = row `lane` of L11^-T: e_lane L11^-T
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
+    solve_steps_rot<32, 32, 4, true>(x, LT, rd, 0, [&](int k, double v) { Minv[lane * SLD + k] = v; });
+  }
+  __syncthreads();
+  {
+    // A22 -= L21 L21^T: warp w owns columns 2w, 2w+1; lane r row 32 + r
+    double acc[2];
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) acc[cc] = blk[(32 + warp * 2 + cc) * SLD + 32 + lane];
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const double xr = blk[k * SLD + 32 + lane];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) acc[cc] = fma(-xr, LT[k * LTS + 32 + warp * 2 + cc], acc[cc]);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) blk[(32 + warp * 2 + cc) * SLD + 32 + lane] = acc[cc];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double a[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[(32 + c) * SLD + 32 + lane] : 0.0;
+    const int f = chol32_warp<true>(a, lane, colbuf, LT, rd, 32);
+    if (lane == 0) *sfail = f ? 32 + f : 0;
+  } else {
+    // Y = L21 * L11^-1 (32 x 32) while warp 0 factors A22: thread -> (i = lane, t); parked in the lower-left block
+    for (int t = warp - 1; t < 32; t += CTHREADS / 32 - 1) {
+      double y = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < 32; ++m) y = fma(LT[m * LTS + 32 + lane], Minv[t * SLD + m], y);
+      Minv[t * SLD + 32 + lane] = y;
+    }
+  }
+  __syncthreads();
+  if (*sfail) return *sfail;
+  if (warp == 1) {
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
+    solve_steps_rot<32, 32, 4, true>(x, LT, rd, 32, [&](int k, double v) { Minv[(32 + lane) * SLD + k] = v; });
+  }
+  __syncthreads();
+  {
+    // Z = -L22^-1 * Y: Z[i][t] = -sum_{m <= i} Inv22[i][m] Y[m][t]; two (i, t) pairs per thread
+    double z[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = warp + 16 * u;
+      double s = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < 32; ++m) s = fma(Minv[(32 + m) * SLD + 32 + lane], Minv[t * SLD + 32 + m], s);
+      z[u] = -s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) Minv[(warp + 16 * u) * SLD + 32 + lane] = z[u];
+  }
+  __syncthreads();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Panel chain of row block r (64 rows) of the panel [p0, p0 + pw).
+// --------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopParams& P, double* buf, uint64_t* pbar,
+                                           uint32_t& pphase, double* colbuf, double* rd, int* sfail, int* sflag) {
+  const int tid = threadIdx.x;
+  const int r = blockIdx.x;
+  const int nkk = (P.pw + NB - 1) / NB;
+  const int rows0 = P.p0 + NB * r;
+  const int jmax = min(r, nkk - 1);
+  int* F = P.sync + 1;
+  int* X = P.sync + 5;
+  int* rowready = P.sync + 32;
+  auto bcast_wait = [&](const int* f, int target) -> bool {
+    if (tid == 0) *sflag = wait_flag(f, target, P.flag, P.abort_flag) ? 1 : 0;
+    __syncthreads();
+    const bool ok = *sflag != 0;
+    __syncthreads();
+    return ok;
+  };
+  if (P.p0 > 0) {
+    const int ti = r >> 1;
+    const int expect = (ti == 0) ? min(nkk, 2) : nkk;
+    if (!bcast_wait(rowready + ti, expect)) return;
+  }
+  if (tid == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(pbar, static_cast<uint32_t>((jmax + 1) * BLK * sizeof(double)));
+    for (int j = 0; j <= jmax; ++j) tma_load_2d(buf + j * BLK, mapBlk, rows0, P.p0 + NB * j, pbar);
+  }
+  mbar_wait_spin(pbar, pphase);
+  pphase ^= 1;
+  double* stageM = buf + 4 * BLK;
+  double* stageL = buf + 5 * BLK;
+  for (int kk = 0; kk < nkk; ++kk) {
+    const int k0 = P.p0 + NB * kk;
+    const int nb = min(NB, P.n - k0);
+    double* blkk = buf + kk * BLK;
+    if (r == kk) {
+      // ---- factor the diagonal block, publish L_kk^-1 ----
+      if (nb < NB) {
+        for (int c = nb + tid; c < NB; c += CTHREADS) blkk[c * SLD + c] = 1.0;  // identity padding (rows are zero-filled)
+      }
+      __syncthreads();
+      const int failed = factor_diag64(blkk, stageM, stageL, colbuf, rd, sfail);
+      if (failed) {
+        if (tid == 0) {
+          *P.flag = k0 + failed;
+          __threadfence();
+        }
+        return;
+      }
+      double* Ab = P.A + static_cast<size_t>(k0) * P.lda + k0;
+      for (int e = tid; e < NB * NB; e += CTHREADS) {
+        const int rr = e & (NB - 1), c = e >> 6;
+        if (rr >= c && rr < nb && c < nb) Ab[static_cast<size_t>(c) * P.lda + rr] = stageM[c * LTS + rr];
+      }
+      double* G = P.scratch + kk * BLK;
+      for (int e = tid; e < BLK; e += CTHREADS) G[e] = stageL[e];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        fence_proxy_async();
+        st_release(F + kk, 1);
+      }
+      return;
+    }
+    // ---- X = A_rk L_kk^-T ----
+    if (!bcast_wait(F + kk, 1)) return;
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(pbar, BLK * sizeof(double));
+      tma_bulk_g2s(stageM, P.scratch + kk * BLK, BLK * sizeof(double), pbar);
+    }
+    mbar_wait_spin(pbar, pphase);
+    pphase ^= 1;
+    {
+      double acc[2][2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      tile64_mma<false, true>(acc, blkk, stageM);
+      __syncthreads();  // every warp has read its A rows
+      double* Ag = P.A + static_cast<size_t>(k0) * P.lda + rows0;
+      CMOE_FRAG_LOOP({
+        blkk[col * SLD + row] = acc[i][j][h];
+        if (rows0 + row < P.n && col < nb) Ag[static_cast<size_t>(col) * P.lda + row] = acc[i][j][h];
+      })
+      if (r < nkk) __threadfence();
+      __syncthreads();
+      if (r < nkk && tid == 0) {
+        fence_proxy_async();
+        st_release(X + r * 4 + kk, 1);
+      }
+    }
+    // ---- apply to the columns to the right (inside the panel) ----
+    for (int jb = kk + 1; jb <= jmax; ++jb) {
+      const double* Bs = blkk;
+      if (jb != r) {
+        if (!bcast_wait(X + jb * 4 + kk, 1)) return;
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(pbar, BLK * sizeof(double));
+          tma_load_2d(stageL, mapBlk, P.p0 + NB * jb, k0, pbar);
+        }
+        mbar_wait_spin(pbar, pphase);
+        pphase ^= 1;
+        Bs = stageL;
+      }
+      double* blkj = buf + jb * BLK;
+      double acc[2][2][2];
+      CMOE_FRAG_LOOP({ acc[i][j][h] = blkj[col * SLD + row]; })
+      tile64_mma<true, false>(acc, blkk, Bs);
+      CMOE_FRAG_LOOP({ blkj[col * SLD + row] = acc[i][j][h]; })
+      __syncthreads();  // stageL is reused by the next column block; blkj complete before it becomes an operand
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CTHREADS, 1)
+    chol_step_kernel(const __grid_constant__ CUtensorMap mapOp, const __grid_constant__ CUtensorMap mapBlk,
+                     const __grid_constant__ CoopParams P) {
+  extern __shared__ __align__(128) unsigned char coop_smem_raw[];
+  double* buf = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(coop_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ __align__(8) uint64_t empty[STAGES];
+  __shared__ __align__(8) uint64_t pbar;
+  __shared__ double colbuf[128];
+  __shared__ double rd[NB];
+  __shared__ int s_tile, sfail, sflag;
+  if (ld_volatile(P.flag) != 0) return;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CTHREADS / 32);
+    }
+    mbar_init(&pbar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const int n = P.n, p0 = P.p0;
+  const int nrb = (n - p0 + NB - 1) / NB;        // panel row blocks
+  const bool is_p = static_cast<int>(blockIdx.x) < nrb;
+  bool p_done = false;
+  uint32_t gchunk = 0, pphase = 0;
+  // trailing update with the previous panel
+  int num_a = 0, total = 0, nct_a = 0, count0 = 0, nbt = 0;
+  const int q0 = p0 - CW;
+  const int tb0 = p0 + CW;  // origin of the (b) tile grid
+  if (p0 > 0) {
+    const int nrt = (n - p0 + TM - 1) / TM;
+    nct_a = (P.pw + NB - 1) / NB;
+    count0 = min(nct_a, 2);
+    num_a = count0 + (nrt - 1) * nct_a;
+    if (n > tb0) {
+      nbt = (n - tb0 + TM - 1) / TM;
+      total = num_a + nbt * (nbt + 1) / 2;
+    } else {
+      total = num_a;
+    }
+  }
+  int* counter = P.sync;
+  int* rowready = P.sync + 32;
+  for (;;) {
+    if (tid == 0) {
+      int t;
+      if (is_p && !p_done && ld_volatile(counter) >= num_a) {
+        t = -2;
+      } else {
+        t = atomicAdd(counter, 1);
+      }
+      s_tile = t;
+    }
+    __syncthreads();
+    const int t = s_tile;
+    __syncthreads();
+    if (t == -2 || (is_p && !p_done && t >= num_a)) {
+      // (a race can hand a (b) tile to a CTA whose panel work is still pending: the chain goes first)
+      panel_role(&mapBlk, P, buf, &pbar, pphase, colbuf, rd, &sfail, &sflag);
+      p_done = true;
+      __syncthreads();
+    }
+    if (t == -2) continue;
+    if (t >= total) break;
+    if (t < num_a) {
+      int ti, tj;
+      if (t < count0) {
+        ti = 0;
+        tj = t;
+      } else {
+        ti = 1 + (t - count0) / nct_a;
+        tj = (t - count0) % nct_a;
+      }
+      gemm_tile<64>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, p0 + ti * TM, p0 + tj * NB, q0);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(rowready + ti, 1);
+    } else {
+      int rem = t - num_a, tj = 0;
+      while (rem >= nbt - tj) {
+        rem -= nbt - tj;
+        ++tj;
+      }
+      const int ti = tj + rem;
+      gemm_tile<128>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, tb0 + ti * TM, tb0 + tj * TM, q0);
+    }
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+}  // namespace
+
+bool make_tensor_map_2d(CUtensorMap* map, const double* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows, uint32_t box_cols) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {rows, cols};
+  const cuuint64_t strides[1] = {ld * sizeof(double)};
+  const cuuint32_t box[2] = {box_rows, box_cols};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
+// Returns false when the cooperative path does not apply (small / odd n, more row blocks than SMs, no cooperative
+// launch): nothing has been touched in that case and the caller takes the launch-per-step path.
+bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
+  static const bool disabled = [] {
+    const char* e = std::getenv("CMOE_POTRF");
+    return e && std::string(e) == "legacy";
+  }();
+  if (disabled || n < 1024 || (n & 1) || (reinterpret_cast<uintptr_t>(A) & 15)) return false;
+  int dev = 0, sms = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop || (n + NB - 1) / NB > sms) return false;
+  CUtensorMap mapOp, mapBlk;
+  if (!make_tensor_map_2d(&mapOp, A, n, n, n, OLD, KC) || !make_tensor_map_2d(&mapBlk, A, n, n, n, SLD, NB)) return false;
+  CMOE_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kCoopSmem)));
+  const int npanels = (n + CW - 1) / CW;
+  DevBuf<int> sync(static_cast<size_t>(npanels) * kSyncPerPanel + 1);
+  DevBuf<double> scratch(static_cast<size_t>(4) * BLK);
+  CMOE_CUDA(cudaMemsetAsync(sync.p, 0, sync.count * sizeof(int), s));
+  CMOE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  int* abort_flag = sync.p + static_cast<size_t>(npanels) * kSyncPerPanel;
+  for (int p0 = 0, pi = 0; p0 < n; p0 += CW, ++pi) {
+    CoopParams P{A, n, n, p0, std::min(CW, n - p0), flag, sync.p + static_cast<size_t>(pi) * kSyncPerPanel, scratch.p,
+                 abort_flag};
+    void* args[] = {&mapOp, &mapBlk, &P};
+    CMOE_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_step_kernel), dim3(sms), dim3(CTHREADS), args,
+                                          kCoopSmem, s));
+    count_launch();
+  }
+  int aborted = 0;
+  CMOE_CUDA(cudaMemcpyAsync(&aborted, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaStreamSynchronize(s));  // scratch is freed on return
+  CMOE_REQUIRE(!aborted, CMOE_ERR_RUNTIME,
+               "cooperative Cholesky: a dependency wait timed out (device shared with another long-running kernel?)");
+  return true;
+}
+
+}  // namespace cmoe

@@ -131,7 +131,11 @@ def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_boun
 def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0, device="cpu", group=None):
     from . import capi
 
+    analytic = np.asarray(starts).shape[1] == 1 and (Xp is None or len(Xp) == 0)
+
     def evaluate(sub):
+        if analytic:  # closed-form 1-EI, as the reference and cmoe_multistart_ei screen (gpp_math.hpp:1703-1749)
+            return capi.ei_analytic(gp, np.asarray(sub).reshape(-1, np.asarray(sub).shape[-1]), best_so_far)
         return gp.ei(sub, Xp, num_mc, best_so_far, seed=seed)
 
     def descend(sub):

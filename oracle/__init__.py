@@ -352,3 +352,22 @@ def kg_grad_at_point_list(backend, gp, candidates, Xp, num_mc, best_so_far, gd, 
                                             _d(Xp), nc, q, Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far),
                                             int(num_threads), ctypes.c_uint64(seed), _d(vals), _d(grads))
     return vals, grads
+
+
+def ei_grad_at_point_list(backend, gp, candidates, Xp, num_mc, best_so_far, num_threads, seed=1):
+    """CPU baseline for q-EI: value + gradient for a list of candidates, OpenMP static over candidates
+    (reference back end: ExpectedImprovementEvaluator + one NormalRNG per thread; port: the C oracle)."""
+    cand = _f64(candidates)
+    nc, q, dim = cand.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    vals = np.empty(nc)
+    grads = np.empty((nc, q, dim))
+    if backend.prefix == "ref_":
+        backend.lib.ref_ei_grad_at_point_list(gp.h, _d(cand), _d(Xp), nc, q, Xp.shape[0], int(num_mc),
+                                              ctypes.c_double(best_so_far), int(num_threads), ctypes.c_uint(seed),
+                                              _d(vals), _d(grads))
+    else:
+        backend.lib.oracle_ei_at_point_list(gp.h, _d(cand), _d(Xp), nc, q, Xp.shape[0], int(num_mc),
+                                            ctypes.c_double(best_so_far), int(num_threads), ctypes.c_uint64(seed),
+                                            _d(vals), _d(grads))
+    return vals, grads

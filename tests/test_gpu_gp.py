@@ -64,6 +64,49 @@ def test_cholesky_failure_index(capi):
     assert e.value.info == 101
 
 
+@pytest.mark.parametrize("n", [1024, 1090, 1536, 2306])
+def test_cholesky_cooperative_path(capi, n):
+    """n >= 1024 (even) takes the one-launch-per-panel path (potrf_coop.cu): flag-chained panel steps, TMA-fed DMMA
+    trailing update.  Compared with the reference's ComputeCholeskyFactorL on the same matrix."""
+    rng = np.random.default_rng(977 + n)
+    G = rng.standard_normal((n, n // 2))
+    A = G @ G.T + 0.5 * n * np.eye(n)
+    L = np.tril(capi.cholesky(A))
+    rc, Lref = checker().cholesky(A)
+    assert rc == 0
+    tril_close(L, Lref, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(L @ L.T, A, rtol=1e-12, atol=1e-11 * n)
+    # odd sizes keep the launch-per-step path; both must agree with the reference
+    Lo = np.tril(capi.cholesky(A[: n - 1, : n - 1]))
+    tril_close(Lo, Lref[: n - 1, : n - 1], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("bad", [0, 70, 300, 1279, 1535])
+def test_cholesky_cooperative_failure_index(capi, bad):
+    n = 1536
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((n, 64))
+    A = G @ G.T + n * np.eye(n)
+    A[bad, :] = 0.0
+    A[:, bad] = 0.0
+    with pytest.raises(capi.SingularMatrixError) as e:
+        capi.cholesky(A)
+    assert e.value.info == bad + 1
+
+
+def test_gp_fit_n2000_matches_reference_factor(capi):
+    """Large fit against the reference's own factor (not only residual properties): N = 2000, d = 10."""
+    prob = make_problem(2000, 10, seed=77, length=0.5)
+    gp = capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    ref, lm = checker().gp(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    assert lm == 0
+    K, kinvy, mean = gp.state()
+    Kr, kr, mr = ref.state()
+    assert mean == mr
+    tril_close(K, Kr, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(kinvy, kr, rtol=1e-6, atol=1e-6)
+
+
 def test_philox_stream_matches_host(capi):
     dev = capi.philox_normals(0xC0FFEE, 5, 300, 7)
     host = orc.philox_normals(0xC0FFEE, 5, 300, 7)
