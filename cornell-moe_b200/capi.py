@@ -366,9 +366,26 @@ def _gd_args(gp, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_fi
             _f64(discrete_pts).reshape(-1, gp.dim - num_fidelity) if discrete_pts is not None else None)
 
 
+class MultistartOpts(ctypes.Structure):
+    _fields_ = [("normals_table", ctypes.POINTER(ctypes.c_double)), ("table_len", ctypes.c_size_t),
+                ("devices", ctypes.POINTER(ctypes.c_int)), ("num_devices", ctypes.c_int)]
+
+
+def _multistart_opts(table, devices):
+    """(opts struct or None, keep-alive tuple) for cmoe_multistart_{kg,ei}_ex."""
+    if table is None and not devices:
+        return None, ()
+    t = _f64(table).ravel() if table is not None else None
+    dv = _i32(devices) if devices else None
+    o = MultistartOpts(_d(t) if t is not None else None, t.size if t is not None else 0,
+                       _i(dv) if dv is not None else None, dv.size if dv is not None else 0)
+    return o, (t, dv)
+
+
 def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
-                  num_fidelity=0, seed=0):
-    """cmoe_multistart_kg: returns (best_point [q, dim], best_value, found_flag, start_values)."""
+                  num_fidelity=0, seed=0, table=None, devices=None):
+    """cmoe_multistart_kg(_ex): returns (best_point [q, dim], best_value, found_flag, start_values).
+    table: normals replayed by every evaluation (NormalRNGSimulator semantics); devices: GPUs to shard the starts over."""
     starts = _f64(starts)
     ns, q, dim = starts.shape
     Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
@@ -378,15 +395,18 @@ def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_boun
     bv = ctypes.c_double()
     found = ctypes.c_int()
     info = ctypes.c_int()
-    rc = lib().cmoe_multistart_kg(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db), _d(ib),
-                                  _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0], int(num_mc),
-                                  ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals), _d(best),
-                                  ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+    opts, keep = _multistart_opts(table, devices)
+    rc = lib().cmoe_multistart_kg_ex(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db), _d(ib),
+                                     _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0], int(num_mc),
+                                     ctypes.c_double(best_so_far), ctypes.c_uint64(seed),
+                                     ctypes.byref(opts) if opts is not None else None, _d(vals), _d(best),
+                                     ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+    del keep
     _check(rc, info.value)
     return best, bv.value, bool(found.value), vals
 
 
-def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0):
+def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0, table=None, devices=None):
     starts = _f64(starts)
     ns, q, dim = starts.shape
     Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
@@ -397,9 +417,12 @@ def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, see
     bv = ctypes.c_double()
     found = ctypes.c_int()
     info = ctypes.c_int()
-    rc = lib().cmoe_multistart_ei(gp.h, ctypes.byref(outer), _d(db), _d(starts), ns, q, _d(Xp), Xp.shape[0],
-                                  int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals), _d(best),
-                                  ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+    opts, keep = _multistart_opts(table, devices)
+    rc = lib().cmoe_multistart_ei_ex(gp.h, ctypes.byref(outer), _d(db), _d(starts), ns, q, _d(Xp), Xp.shape[0],
+                                     int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed),
+                                     ctypes.byref(opts) if opts is not None else None, _d(vals), _d(best),
+                                     ctypes.byref(bv), ctypes.byref(found), ctypes.byref(info))
+    del keep
     _check(rc, info.value)
     return best, bv.value, bool(found.value), vals
 

@@ -9,8 +9,12 @@
 // through shared memory once and every thread produces a 4x4 register block (4 consecutive rows of 4 columns), so a
 // lane's stores are 32 contiguous bytes and a warp store covers 8 lanes x 32 B = 256 contiguous bytes per column.  Only lower-triangular tiles are visited: the algorithmic traffic
 // is 4*n*(n+1) bytes written + 8*N*dim read.
+#include <algorithm>
+
 #include "device_math.cuh"
 #include "internal.cuh"
+#include "linalg_dev.cuh"
+#include "ptx_util.cuh"
 
 namespace cmoe {
 
@@ -169,6 +173,137 @@ __global__ void __launch_bounds__(256, 3)
   }  // passes
 }
 
+// --------------------------------------------------------------------------------------------------------------
+// g == 0, even N: persistent TMA version.  Per 128 x 64 tile of the lower-triangular tile grid:
+//   * the two point slabs (rows of the length-scaled Xs, contiguous in global memory) arrive by TMA bulk copies
+//     (cp.async.bulk -> UBLKCP) on an mbarrier — no transposing per-element staging, no bank-conflicted LDGSTS;
+//   * the scaled dot products x_i . x_j run on the FP64 tensor pipe (DMMA m8n8k4, K = dim padded to a multiple of 4):
+//     it has the FP64 units' throughput but 1/8 of the issue slots and no per-FMA operand traffic;
+//   * -|x|^2/2 comes from the SAME instruction sequence applied to the 8 x 8 diagonal blocks of each slab, so
+//     t_ij + (h_i + h_j) cancels exactly for coincident points and k = alpha bit-for-bit (see cov_build_g0_kernel);
+//   * exp in the accumulator-fragment layout, results staged as a dense [64][128] tile in shared memory and written by
+//     ONE TMA tensor store per tile (cp.async.bulk.tensor.2d.global.shared -> UTMASTG); the store drains while the other
+//     resident CTA of the SM computes (2 CTAs / SM), and rows / columns beyond N are clipped by the tensor map.
+// Contract: Xs readable for ceil(N/128)*128 rows (the slabs are copied whole; rows >= N only feed clipped outputs).
+// --------------------------------------------------------------------------------------------------------------
+constexpr int kTmaThreads = 256;
+
+template <int KERNEL>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+    cov_build_tma_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ KernelSpec spec,
+                         const double* __restrict__ Xs, int N, const double* __restrict__ noise, int ntiles) {
+  extern __shared__ __align__(128) unsigned char cov_smem_raw[];
+  double* stage = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(cov_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  const int dim = spec.dim;
+  double* slabR = stage + TCW * TR;      // [TR][dim]  rows of Xs as they lie in global memory
+  double* slabC = slabR + TR * dim;      // [TCW][dim]
+  double* Hr = slabC + TCW * dim;        // [TR]   -|x_i|^2/2
+  double* Hc = Hr + TR;                  // [TCW]
+  double* tab = Hc + TCW;                // [64]
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  if (tid < 64) tab[tid] = kCovExp2Table[tid];
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int ksteps = (dim + 3) >> 2;
+  const double nz = noise[0];
+  uint32_t phase = 0;
+  constexpr int kColsPerRow = TR / TCW;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int tr = static_cast<int>((sqrt(8.0 * (tile / kColsPerRow) + 1.0) - 1.0) * 0.5);
+    while (tr * (tr + 1) / 2 * kColsPerRow > tile) --tr;
+    while ((tr + 1) * (tr + 2) / 2 * kColsPerRow <= tile) ++tr;
+    const int tc = tile - tr * (tr + 1) / 2 * kColsPerRow;
+    const int row0 = tr * TR, col0 = tc * TCW;
+    if (col0 >= N) continue;
+    if (tid == 0) {
+      tma_store_wait_read<0>();  // the previous tile's store has finished reading the staging buffer
+      mbar_expect_tx(&bar, static_cast<uint32_t>((TR + TCW) * dim * sizeof(double)));
+      tma_bulk_g2s(slabR, Xs + static_cast<size_t>(row0) * dim, static_cast<uint32_t>(TR * dim * sizeof(double)), &bar);
+      tma_bulk_g2s(slabC, Xs + static_cast<size_t>(col0) * dim, static_cast<uint32_t>(TCW * dim * sizeof(double)), &bar);
+    }
+    __syncthreads();  // staging buffer free, previous tile's readers of slabs / H done
+    while (!mbar_try_wait(&bar, phase)) {
+    }
+    phase ^= 1;
+    // half norms from 8 x 8 diagonal blocks, same DMMA chain as the tile product
+    for (int blk = warp; blk < (TR + TCW) / 8; blk += kTmaThreads / 32) {
+      const double* src = (blk < TR / 8) ? slabR + blk * 8 * dim : slabC + (blk - TR / 8) * 8 * dim;
+      double c0 = 0.0, c1 = 0.0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int kk = ks * 4 + lc;
+        const double a = (kk < dim) ? src[lr * dim + kk] : 0.0;
+        dmma_m8n8k4(c0, c1, a, a);
+      }
+      if ((lr >> 1) == lc) {
+        const double d = (lr & 1) ? c1 : c0;
+        ((blk < TR / 8) ? Hr + blk * 8 : Hc + (blk - TR / 8) * 8)[lr] = -0.5 * d;
+      }
+    }
+    __syncthreads();
+    // a warp sub-tile entirely above the diagonal is skipped (its staging area keeps stale values; the strictly
+    // upper triangle of K is unspecified, as in the reference)
+    if (col0 + wn <= row0 + wm + 31) {
+      double acc[4][4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int kk = ks * 4 + lc;
+        const bool ok = kk < dim;
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = ok ? slabR[(wm + i * 8 + lr) * dim + kk] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = ok ? slabC[(wn + j * 8 + lr) * dim + kk] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      double hrv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hrv[i] = Hr[wm + i * 8 + lr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = wn + j * 8 + lc * 2 + h;
+          const double hcv = Hc[col];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = wm + i * 8 + lr;
+            const double e = acc[i][j][h] + (hrv[i] + hcv);  // = -r^2/2, exactly 0 for coincident points
+            double v;
+            if (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
+              v = spec.alpha * exp_tab_cov(e, tab);
+            } else {
+              const double r2 = fmax(0.0, -2.0 * e);
+              const double arg = kSqrt5 * sqrt(r2);
+              v = spec.alpha * exp_fast(-arg) * (1.0 + arg + 5.0 / 3.0 * r2);
+            }
+            if (row0 + row == col0 + col) v = spec.alpha + nz;  // exact diagonal: k(x, x) = alpha
+            stage[col * TR + row] = v;
+          }
+        }
+      }
+    }
+    fence_proxy_async();  // generic-proxy writes of the staging tile -> visible to the TMA store
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_2d(&mapK, stage, row0, col0);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) tma_store_wait<0>();
+}
+
 // generic path (derivative observations): one thread per point pair, writes the (1+g)x(1+g) block
 __global__ void __launch_bounds__(256) cov_build_generic_kernel(const __grid_constant__ KernelSpec spec,
                                                                 const double* __restrict__ X, int N,
@@ -233,6 +368,33 @@ __global__ void philox_table_kernel(uint64_t seed, uint64_t first_draw, int num_
 
 void build_covariance(const KernelSpec& spec, const double* X, const double* Xs, int N, const double* noise,
                       double* K, cudaStream_t s) {
+  if (spec.g == 0 && N >= 256 && (N & 1) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(Xs) & 15) == 0) {
+    CUtensorMap mapK;
+    if (make_tensor_map_2d(&mapK, K, N, N, N, TR, TCW)) {
+      const int trows = (N + TR - 1) / TR;
+      const int ntiles = trows * (trows + 1) / 2 * (TR / TCW);
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const size_t smem = (static_cast<size_t>(TCW) * TR + static_cast<size_t>(TR + TCW) * (spec.dim + 1) + 64) *
+                              sizeof(double) + 128;
+      const int grid = std::min(ntiles, 2 * sms);
+      if (spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL) {
+        CMOE_CUDA(cudaFuncSetAttribute(cov_build_tma_kernel<CMOE_KERNEL_SQUARE_EXPONENTIAL>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cov_build_tma_kernel<CMOE_KERNEL_SQUARE_EXPONENTIAL><<<grid, kTmaThreads, smem, s>>>(mapK, spec, Xs, N, noise,
+                                                                                            ntiles);
+      } else {
+        CMOE_CUDA(cudaFuncSetAttribute(cov_build_tma_kernel<CMOE_KERNEL_MATERN_NU_2P5>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cov_build_tma_kernel<CMOE_KERNEL_MATERN_NU_2P5><<<grid, kTmaThreads, smem, s>>>(mapK, spec, Xs, N, noise, ntiles);
+      }
+      count_launch();
+      CMOE_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   if (spec.g == 0) {
     const int trows = (N + TR - 1) / TR;
     dim3 grid(trows * (trows + 1) / 2 * (TR / TCW));

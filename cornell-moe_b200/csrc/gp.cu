@@ -52,6 +52,14 @@ __global__ void append_rows_kernel(const double* __restrict__ T, int n0, int mm,
   const int i = static_cast<int>(e % mm), r = static_cast<int>(e / mm);
   K1[static_cast<size_t>(r) * n1 + n0 + i] = T[static_cast<size_t>(i) * n0 + r];
 }
+
+// The TMA covariance build copies whole 128-row slabs of the scaled points: keep the allocation padded (and defined)
+// up to the next multiple of 128 rows.
+void ensure_scaled_points(DevBuf<double>& buf, int N, int dim, cudaStream_t s) {
+  const size_t rows = (static_cast<size_t>(N) + 127) / 128 * 128;
+  if (buf.count < rows * dim) buf.alloc(rows * dim);
+  CMOE_CUDA(cudaMemsetAsync(buf.p + static_cast<size_t>(N) * dim, 0, (rows - N) * dim * sizeof(double), s));
+}
 }  // namespace
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
@@ -80,7 +88,7 @@ void fit_gp(cmoe_gp* gp, bool mean_change) {
   gp->dnoise.upload(gp->hnoise.data(), gp->hnoise.size(), s);
   gp->dK.ensure(static_cast<size_t>(n) * n);
   gp->dKinvY.ensure(n);
-  gp->dXs.ensure(static_cast<size_t>(N) * spec.dim);
+  ensure_scaled_points(gp->dXs, N, spec.dim, s);
   if (gp->dFlag.count == 0) gp->dFlag.alloc(1);
 
   scale_points_kernel<<<(N * spec.dim + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, N, gp->dXs.p);
@@ -128,7 +136,8 @@ void append_points(cmoe_gp* gp, const double* new_points, const double* new_valu
   const KernelSpec& spec = gp->spec;
   const int dim = spec.dim, b = 1 + spec.g, N0 = gp->N, n0 = gp->n, mm = m * b, n1 = n0 + mm;
   cudaStream_t s = gp->stream;
-  DevBuf<double> dXn(static_cast<size_t>(m) * dim), dXsn(static_cast<size_t>(m) * dim);
+  DevBuf<double> dXn(static_cast<size_t>(m) * dim), dXsn;
+  ensure_scaled_points(dXsn, m, dim, s);
   DevBuf<double> K1(static_cast<size_t>(n1) * n1), T(static_cast<size_t>(n0) * mm), S22(static_cast<size_t>(mm) * mm);
   DevBuf<int> dDer(spec.g > 0 ? spec.g : 1), flag(1);
   dXn.upload(new_points, static_cast<size_t>(m) * dim, s);
@@ -169,7 +178,7 @@ void append_points(cmoe_gp* gp, const double* new_points, const double* new_valu
   gp->dK = std::move(K1);
   gp->dX.upload(gp->hX.data(), gp->hX.size(), s);
   gp->dy.upload(gp->hy.data(), gp->hy.size(), s);
-  gp->dXs.ensure(static_cast<size_t>(gp->N) * dim);
+  ensure_scaled_points(gp->dXs, gp->N, dim, s);
   gp->dKinvY.ensure(n1);
   scale_points_kernel<<<(gp->N * dim + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, gp->N, gp->dXs.p);
   double mu = 0.0;  // mean_ = average of the function values (gpp_math.cpp:498-504), same summation order
@@ -182,9 +191,44 @@ void append_points(cmoe_gp* gp, const double* new_points, const double* new_valu
   CMOE_CUDA(cudaStreamSynchronize(s));
 }
 
+
+cmoe_gp* clone_gp_to_device(const cmoe_gp* src, int device) {
+  require_device(device);
+  std::unique_ptr<cmoe_gp> gp(new cmoe_gp());
+  gp->device = device;
+  gp->spec = src->spec;
+  gp->N = src->N;
+  gp->n = src->n;
+  gp->mean = src->mean;
+  gp->hX = src->hX;
+  gp->hy = src->hy;
+  gp->hnoise = src->hnoise;
+  gp->hlengths = src->hlengths;
+  gp->generation = src->generation;
+  CMOE_CUDA(cudaStreamCreateWithFlags(&gp->stream, cudaStreamNonBlocking));
+  cudaStream_t s = gp->stream;
+  auto peer = [&](DevBuf<double>& dst, const DevBuf<double>& from, size_t count) {
+    dst.ensure(std::max(count, from.count));
+    if (count)
+      CMOE_CUDA(cudaMemcpyPeerAsync(dst.p, device, from.p, src->device, std::min(count, from.count) * sizeof(double), s));
+  };
+  const size_t n = static_cast<size_t>(src->n);
+  peer(gp->dX, src->dX, src->hX.size());
+  peer(gp->dXs, src->dXs, src->dXs.count);
+  peer(gp->dy, src->dy, src->hy.size());
+  peer(gp->dnoise, src->dnoise, src->hnoise.size());
+  peer(gp->dK, src->dK, n * n);
+  peer(gp->dKinvY, src->dKinvY, n);
+  gp->dFlag.alloc(1);
+  CMOE_CUDA(cudaStreamSynchronize(s));
+  return gp.release();
+}
+
 }  // namespace cmoe
 
 cmoe_gp::~cmoe_gp() {
+  for (cmoe_gp* r : replicas) cmoe_gp_destroy(r);
+  replicas.clear();
   cmoe::drop_cached_plan(this);
   if (stream) {
     cudaSetDevice(device);
@@ -247,6 +291,7 @@ int cmoe_gp_create(int kernel, double alpha, const double* lengths, const double
     gp->hy.assign(points_sampled_value,
                   points_sampled_value + static_cast<size_t>(num_sampled) * (1 + num_derivatives));
     gp->hnoise.assign(noise_variance, noise_variance + 1 + num_derivatives);
+    gp->hlengths.assign(lengths, lengths + dim);
     CMOE_CUDA(cudaStreamCreateWithFlags(&gp->stream, cudaStreamNonBlocking));
     fit_gp(gp.get(), true);
     *gp_out = gp.release();

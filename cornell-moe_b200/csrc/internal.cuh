@@ -132,7 +132,7 @@ struct cmoe_gp {
   int N = 0;  // points
   int n = 0;  // rows = N * (1 + g)
   double mean = 0.0;
-  std::vector<double> hX, hy, hnoise;
+  std::vector<double> hX, hy, hnoise, hlengths;
   cudaStream_t stream = nullptr;
   cmoe::DevBuf<double> dX;        // [N][dim]
   cmoe::DevBuf<double> dXs;       // [N][dim] scaled by 1/l (for the MC kernels)
@@ -146,6 +146,9 @@ struct cmoe_gp {
   // one cached q-KG plan (device workspace) so that repeated cmoe_kg_eval calls with the same configuration — every
   // step of an outer optimiser — do not re-allocate gigabytes of scratch; owned by kg.cu
   mutable struct cmoe_kg_plan* cached_plan = nullptr;
+  // replicas of this GP on other devices (multi-GPU multistart inside one call); rebuilt when the generation changes
+  mutable std::vector<cmoe_gp*> replicas;
+  mutable uint64_t replicas_generation = 0;
   ~cmoe_gp();
 };
 
@@ -155,6 +158,8 @@ constexpr int kTrsmNB = 32;
 
 // ---- gp.cu ----
 void fit_gp(cmoe_gp* gp, bool mean_change);
+// bit-identical copy of a fitted GP on another device (peer copies of the factor; no refit)
+cmoe_gp* clone_gp_to_device(const cmoe_gp* gp, int device);
 // ---- kg.cu ----
 void drop_cached_plan(const cmoe_gp* gp);
 
@@ -170,6 +175,8 @@ void potrs_lower(const double* L, int n, double* X, int ldx, int nrhs, cudaStrea
 // X <- L^-1 X (trans = false) or L^-T X (trans = true).  nrhs <= 4 with n >= 1024 takes the single-launch chained
 // solver (which synchronises `s`); everything else is the blocked multi-RHS kernel, asynchronous on `s`.
 void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s);
+// trsv_coop.cu: one cooperative launch, owner + helper CTAs per 128-unknown block row; false = not applicable / gave up
+bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s);
 
 // ---- posterior.cu -------------------------------------------------------------------------------------------
 constexpr int kMaxQ = 96;  // largest (q+p)*(1+num_derivatives) handled by the per-set kernels

@@ -837,6 +837,7 @@ void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans
   if (nrhs <= 4 && n >= 1024) {
     for (int r = 0; r < nrhs; ++r) {
       double* xr = X + static_cast<size_t>(r) * ldx;
+      if (trsv_coop(L, n, xr, trans, s)) continue;
       if (!trsv_chained(L, n, xr, trans, s)) trsv_blocked(L, n, xr, trans, s);
     }
     return;

@@ -15,7 +15,9 @@
 #include <functional>
 #include <limits>
 #include <memory>
+#include <exception>
 #include <queue>
+#include <thread>
 
 #include "internal.cuh"
 
@@ -226,7 +228,7 @@ void analytic_ei(const cmoe_gp* gp, const double* pts, int nc, double best_so_fa
 }
 
 BatchEval make_ei_eval(const cmoe_gp* gp, int q, const double* Xp, int p, int num_mc, double best_so_far,
-                       uint64_t seed) {
+                       uint64_t seed, const double* dtable = nullptr) {
   if (q == 1 && p == 0) {
     // special analytic case (gpp_math.hpp:1703-1749)
     return [=](const double* pts, int nc, double* values, double* grads) {
@@ -234,8 +236,90 @@ BatchEval make_ei_eval(const cmoe_gp* gp, int q, const double* Xp, int p, int nu
     };
   }
   return [=](const double* pts, int nc, double* values, double* grads) {
-    ei_eval_batch(*gp, pts, nc, q, Xp, p, num_mc, best_so_far, seed, nullptr, values, grads);
+    require_device(gp->device);  // may run on a worker thread of the multi-device driver
+    ei_eval_batch(*gp, pts, nc, q, Xp, p, num_mc, best_so_far, seed, dtable, values, grads);
   };
+}
+
+// ---- the parallel axis inside the call: starts strided over several GPUs ---------------------------------------------
+// (reference: OpenMP threads over starts, gpp_optimization.hpp:1472-1546).  One worker per device, each with its own
+// bit-identical replica of the GP, its own plans and streams; one host thread per device and evaluation.
+const cmoe_gp* replica_on(const cmoe_gp* gp, int device) {
+  if (device == gp->device) return gp;
+  if (gp->replicas_generation != gp->generation) {
+    for (cmoe_gp* r : gp->replicas) cmoe_gp_destroy(r);
+    gp->replicas.clear();
+    gp->replicas_generation = gp->generation;
+  }
+  for (cmoe_gp* r : gp->replicas)
+    if (r->device == device) return r;
+  gp->replicas.push_back(clone_gp_to_device(gp, device));
+  return gp->replicas.back();
+}
+
+struct DeviceWorker {
+  const cmoe_gp* gp = nullptr;
+  KgEvaluator kg;
+  DevBuf<double> table;  // q-EI table on this device
+  BatchEval eval;
+  std::vector<double> pts, vals, grads;
+  std::vector<int> idx;
+};
+
+struct ShardedEval {
+  std::vector<std::unique_ptr<DeviceWorker>> workers;
+  size_t ps = 0;
+  void operator()(const double* pts, int nc, double* values, double* grads) {
+    const int G = static_cast<int>(workers.size());
+    if (G == 1) {
+      workers[0]->eval(pts, nc, values, grads);
+      return;
+    }
+    std::vector<std::exception_ptr> errs(G);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < G; ++d) {
+      DeviceWorker& w = *workers[d];
+      w.idx.clear();
+      for (int c = d; c < nc; c += G) w.idx.push_back(c);
+      if (w.idx.empty()) continue;
+      threads.emplace_back([&, d] {
+        DeviceWorker& ww = *workers[d];
+        try {
+          const int m = static_cast<int>(ww.idx.size());
+          ww.pts.resize(m * ps);
+          ww.vals.resize(m);
+          if (grads) ww.grads.resize(m * ps);
+          for (int k = 0; k < m; ++k) std::copy(pts + ww.idx[k] * ps, pts + (ww.idx[k] + 1) * ps, ww.pts.begin() + k * ps);
+          ww.eval(ww.pts.data(), m, ww.vals.data(), grads ? ww.grads.data() : nullptr);
+        } catch (...) {
+          errs[d] = std::current_exception();
+        }
+      });
+    }
+    for (auto& t : threads) t.join();
+    for (int d = 0; d < G; ++d)
+      if (errs[d]) std::rethrow_exception(errs[d]);
+    for (int d = 0; d < G; ++d) {
+      DeviceWorker& w = *workers[d];
+      for (size_t k = 0; k < w.idx.size(); ++k) {
+        values[w.idx[k]] = w.vals[k];
+        if (grads) std::copy(w.grads.begin() + k * ps, w.grads.begin() + (k + 1) * ps, grads + w.idx[k] * ps);
+      }
+    }
+  }
+};
+
+std::vector<int> device_list(const cmoe_gp* gp, const cmoe_multistart_opts* opts) {
+  std::vector<int> devs;
+  if (opts && opts->devices && opts->num_devices > 0) {
+    const int count = cmoe_device_count();
+    for (int i = 0; i < opts->num_devices; ++i) {
+      CMOE_REQUIRE(opts->devices[i] >= 0 && opts->devices[i] < count, CMOE_ERR_BOUNDS, "device ordinal out of range");
+      if (std::find(devs.begin(), devs.end(), opts->devices[i]) == devs.end()) devs.push_back(opts->devices[i]);
+    }
+  }
+  if (devs.empty()) devs.push_back(gp->device);
+  return devs;
 }
 
 // ---- ensembles of GPs ("MCMC-averaged" acquisition: one GP per hyper-parameter sample) -----------------------------
@@ -362,21 +446,79 @@ void validate_bounds(const double* b, int dim) {
 
 extern "C" {
 
+int cmoe_multistart_kg_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
+                          const double* domain_bounds, const double* inner_bounds, const double* discrete_pts,
+                          int num_pts, const double* starts, int num_starts, int q, const double* points_being_sampled,
+                          int p, int num_mc, double best_so_far, uint64_t seed, const cmoe_multistart_opts* opts,
+                          double* start_values, double* best_point, double* best_value, int* found_flag, int* info) {
+  return guarded(info, [&] {
+    CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
+    require_device(gp->device);
+    validate_bounds(domain_bounds, gp->spec.dim);
+    const std::vector<int> devs = device_list(gp, opts);
+    const int G = static_cast<int>(devs.size());
+    ShardedEval sh;
+    sh.ps = static_cast<size_t>(q) * gp->spec.dim;
+    for (int d = 0; d < G; ++d) {
+      sh.workers.emplace_back(new DeviceWorker());
+      DeviceWorker& w = *sh.workers.back();
+      w.gp = replica_on(gp, devs[d]);
+      make_kg_evaluator(w.kg, w.gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, (num_starts + G - 1) / G,
+                        (std::min(kTopK, num_starts) + G - 1) / G, q, points_being_sampled, p, num_mc, best_so_far, seed);
+      if (opts && opts->normals_table) {
+        KgEvaluator::check(cmoe_kg_plan_set_table(w.kg.vplan, opts->normals_table, static_cast<int>(opts->table_len)));
+        KgEvaluator::check(cmoe_kg_plan_set_table(w.kg.gplan, opts->normals_table, static_cast<int>(opts->table_len)));
+      }
+      w.eval = std::ref(w.kg);
+    }
+    BatchEval f = std::ref(sh);
+    multistart_common(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts,
+                      -std::numeric_limits<double>::infinity(), start_values, best_point, best_value, found_flag);
+    require_device(gp->device);
+  });
+}
+
 int cmoe_multistart_kg(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
                        const double* domain_bounds, const double* inner_bounds, const double* discrete_pts, int num_pts,
                        const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
                        int num_mc, double best_so_far, uint64_t seed, double* start_values, double* best_point,
                        double* best_value, int* found_flag, int* info) {
+  return cmoe_multistart_kg_ex(gp, num_fidelity, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_pts,
+                               starts, num_starts, q, points_being_sampled, p, num_mc, best_so_far, seed, nullptr,
+                               start_values, best_point, best_value, found_flag, info);
+}
+
+int cmoe_multistart_ei_ex(const cmoe_gp* gp, const cmoe_gd_params* outer, const double* domain_bounds,
+                          const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
+                          int num_mc, double best_so_far, uint64_t seed, const cmoe_multistart_opts* opts,
+                          double* start_values, double* best_point, double* best_value, int* found_flag, int* info) {
   return guarded(info, [&] {
     CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
     require_device(gp->device);
     validate_bounds(domain_bounds, gp->spec.dim);
-    KgEvaluator ev;
-    make_kg_evaluator(ev, gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_starts,
-                      std::min(kTopK, num_starts), q, points_being_sampled, p, num_mc, best_so_far, seed);
-    BatchEval f = std::ref(ev);
-    multistart_common(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts,
-                      -std::numeric_limits<double>::infinity(), start_values, best_point, best_value, found_flag);
+    const std::vector<int> devs = device_list(gp, opts);
+    ShardedEval sh;
+    sh.ps = static_cast<size_t>(q) * gp->spec.dim;
+    const bool analytic = (q == 1 && p == 0);
+    for (int dev : devs) {
+      sh.workers.emplace_back(new DeviceWorker());
+      DeviceWorker& w = *sh.workers.back();
+      w.gp = replica_on(gp, dev);
+      const double* dtable = nullptr;
+      if (!analytic && opts && opts->normals_table) {
+        CMOE_REQUIRE(opts->table_len >= static_cast<size_t>(num_mc) * (q + p), CMOE_ERR_INVALID_VALUE,
+                     "All random numbers stored in the RNG have been used up!");
+        require_device(dev);
+        w.table.upload(opts->normals_table, opts->table_len, w.gp->stream);
+        CMOE_CUDA(cudaStreamSynchronize(w.gp->stream));
+        dtable = w.table.p;
+      }
+      w.eval = make_ei_eval(w.gp, q, points_being_sampled, p, num_mc, best_so_far, seed, dtable);
+    }
+    BatchEval f = std::ref(sh);
+    multistart_common(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts, -1.0, start_values, best_point,
+                      best_value, found_flag);
+    require_device(gp->device);
   });
 }
 
@@ -384,14 +526,8 @@ int cmoe_multistart_ei(const cmoe_gp* gp, const cmoe_gd_params* outer, const dou
                        const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
                        int num_mc, double best_so_far, uint64_t seed, double* start_values, double* best_point,
                        double* best_value, int* found_flag, int* info) {
-  return guarded(info, [&] {
-    CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
-    require_device(gp->device);
-    validate_bounds(domain_bounds, gp->spec.dim);
-    BatchEval f = make_ei_eval(gp, q, points_being_sampled, p, num_mc, best_so_far, seed);
-    multistart_common(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts, -1.0, start_values, best_point,
-                      best_value, found_flag);
-  });
+  return cmoe_multistart_ei_ex(gp, outer, domain_bounds, starts, num_starts, q, points_being_sampled, p, num_mc,
+                               best_so_far, seed, nullptr, start_values, best_point, best_value, found_flag, info);
 }
 
 int cmoe_kg_gradient_descent(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,

@@ -25,6 +25,7 @@
 #ifndef CMOE_B200_H_
 #define CMOE_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -184,6 +185,33 @@ int cmoe_multistart_ei(const cmoe_gp* gp, const cmoe_gd_params* outer, const dou
                        const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
                        int num_mc, double best_so_far, uint64_t seed, double* start_values, double* best_point,
                        double* best_value, int* found_flag, int* info);
+
+/* Extended forms of the two drivers above (opts may be NULL = plain call):
+ *   normals_table / table_len — standard normals replayed for every evaluation exactly like the reference's
+ *     NormalRNG after ResetToMostRecentSeed (every q-KG / q-EI evaluation of a driver call rewinds its generator,
+ *     gpp_knowledge_gradient_optimization.cpp:81,164, gpp_math.cpp:2011,2076): ((num_mc+1)/2)*(q+p)*(1+g) values for
+ *     q-KG, num_mc*(q+p) for q-EI.  With the table drawn from a NormalRNG of the same seed the device path and
+ *     ComputeKGOptimalPointsToSampleViaMultistartGradientDescent consume identical draws.
+ *   devices / num_devices — the reference's parallel axis (OpenMP threads over starts, gpp_optimization.hpp:1472-1546)
+ *     inside the call: the GP is replicated on every listed GPU (one host thread and stream set per device), starts
+ *     are strided over the devices for the screening pass and for the gradient descent of the kept 20, values are
+ *     gathered on the host.  Every start is evaluated by the same kernels with the same seed wherever it runs, so the
+ *     result is bit-identical to the single-device call. */
+typedef struct cmoe_multistart_opts {
+  const double* normals_table;
+  size_t table_len;
+  const int* devices;
+  int num_devices;
+} cmoe_multistart_opts;
+int cmoe_multistart_kg_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
+                          const double* domain_bounds, const double* inner_bounds, const double* discrete_pts,
+                          int num_pts, const double* starts, int num_starts, int q, const double* points_being_sampled,
+                          int p, int num_mc, double best_so_far, uint64_t seed, const cmoe_multistart_opts* opts,
+                          double* start_values, double* best_point, double* best_value, int* found_flag, int* info);
+int cmoe_multistart_ei_ex(const cmoe_gp* gp, const cmoe_gd_params* outer, const double* domain_bounds,
+                          const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
+                          int num_mc, double best_so_far, uint64_t seed, const cmoe_multistart_opts* opts,
+                          double* start_values, double* best_point, double* best_value, int* found_flag, int* info);
 
 /* Restarted gradient descent from given starts only (the second half of the multistart drivers); used by the
  * multi-GPU host layer after the global top-20 has been agreed on.  values_out[num_starts], points_out[num_starts][q*dim]. */

@@ -371,3 +371,42 @@ def ei_grad_at_point_list(backend, gp, candidates, Xp, num_mc, best_so_far, num_
                                             ctypes.c_double(best_so_far), int(num_threads), ctypes.c_uint64(seed),
                                             _d(vals), _d(grads))
     return vals, grads
+
+
+def normal_draws(seed, count):
+    """First `count` draws of the reference's NormalRNG(seed) — the table every evaluation of a multistart driver call
+    replays (each evaluation rewinds the generator).  Reference back end only."""
+    lib = load_reference().lib
+    out = np.empty(count)
+    lib.ref_normal_draws(ctypes.c_uint(seed), int(count), _d(out))
+    return out
+
+
+def ref_multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
+                      seed, num_fidelity=0):
+    """The reference's ComputeKGOptimalPointsToSampleViaMultistartGradientDescent, unmodified, one thread.
+    Returns (best_point [q, dim], found_flag)."""
+    lib = load_reference().lib
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    disc = _f64(discrete_pts).reshape(-1, dim - num_fidelity)
+    best = np.empty((q, dim))
+    lib.ref_multistart_kg.restype = ctypes.c_int
+    found = lib.ref_multistart_kg(gp.h, int(num_fidelity), _d(_f64(outer)), _d(_f64(inner)),
+                                  _d(_f64(domain_bounds).ravel()), _d(_f64(inner_bounds).ravel()), _d(disc),
+                                  disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0], int(num_mc),
+                                  ctypes.c_double(best_so_far), ctypes.c_uint(seed), _d(best))
+    return best, bool(found)
+
+
+def ref_multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed):
+    """The reference's ComputeOptimalPointsToSampleViaMultistartGradientDescent, unmodified, one thread."""
+    lib = load_reference().lib
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    best = np.empty((q, dim))
+    lib.ref_multistart_ei(gp.h, _d(_f64(outer)), _d(_f64(domain_bounds).ravel()), _d(starts), ns, q, _d(Xp),
+                          Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint(seed), _d(best))
+    return best

@@ -340,6 +340,49 @@ void ref_limit_update(const double* bounds, int dim, double max_relative_change,
   dom.LimitUpdate(max_relative_change, current_point, update);
 }
 
+// ---- the multistart drivers themselves, UNMODIFIED, single-threaded --------------------------------------------------
+// Every q-KG / q-EI evaluation rewinds its NormalRNG (ResetToMostRecentSeed, gpp_knowledge_gradient_optimization.cpp:81,
+// 164; gpp_math.cpp:2011, 2076), so a whole driver call consumes the same first draws of NormalRNG(seed) over and over:
+// ref_normal_draws() returns that table, and feeding it to the device path as `normals_table` makes both sides use
+// identical normals without touching the reference.
+void ref_normal_draws(unsigned seed, int count, double* out) {
+  NormalRNG rng(seed);
+  for (int i = 0; i < count; ++i) out[i] = rng();
+}
+
+// ComputeKGOptimalPointsToSampleViaMultistartGradientDescent (gpp_knowledge_gradient_optimization.hpp:859-935)
+int ref_multistart_kg(void* h, int num_fidelity, const double* gd_outer, const double* gd_inner, const double* bounds,
+                      const double* inner_bounds, const double* discrete_pts, int num_pts, const double* starts,
+                      int num_starts, int q, const double* Xp, int p, int num_mc, double best_so_far, unsigned seed,
+                      double* best_point) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  TensorProductDomain dom = MakeDomain(bounds, gp->dim());
+  TensorProductDomain inner_dom = MakeDomain(inner_bounds, gp->dim() - num_fidelity);
+  GradientDescentParameters outer = MakeGD(gd_outer), inner = MakeGD(gd_inner);
+  NormalRNG rng(seed);
+  ThreadSchedule sched(1, omp_sched_static);
+  bool found = false;
+  ComputeKGOptimalPointsToSampleViaMultistartGradientDescent(*gp, num_fidelity, outer, inner, dom, inner_dom, sched,
+                                                             starts, Xp, discrete_pts, num_starts, q, p, num_pts,
+                                                             best_so_far, num_mc, &rng, &found, best_point);
+  return found ? 1 : 0;
+}
+
+// ComputeOptimalPointsToSampleViaMultistartGradientDescent (gpp_math.hpp:1683-1802); the reference never sets its
+// found_flag there, so only the point is returned
+void ref_multistart_ei(void* h, const double* gd_outer, const double* bounds, const double* starts, int num_starts,
+                       int q, const double* Xp, int p, int num_mc, double best_so_far, unsigned seed,
+                       double* best_point) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  TensorProductDomain dom = MakeDomain(bounds, gp->dim());
+  GradientDescentParameters outer = MakeGD(gd_outer);
+  NormalRNG rng(seed);
+  ThreadSchedule sched(1, omp_sched_static);
+  bool found = false;
+  ComputeOptimalPointsToSampleViaMultistartGradientDescent(*gp, outer, dom, sched, starts, Xp, num_starts, q, p,
+                                                           best_so_far, num_mc, &rng, &found, best_point);
+}
+
 int ref_max_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

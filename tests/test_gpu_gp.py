@@ -76,6 +76,10 @@ def test_cholesky_cooperative_path(capi, n):
     assert rc == 0
     tril_close(L, Lref, rtol=1e-10, atol=1e-11)
     np.testing.assert_allclose(L @ L.T, A, rtol=1e-12, atol=1e-11 * n)
+    # one right-hand side on a large factor: the cooperative owner/helper triangular solve (trsv_coop.cu)
+    b = rng.standard_normal(n)
+    x = capi.potrs(L, b)
+    np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-9, atol=1e-12)
     # odd sizes keep the launch-per-step path; both must agree with the reference
     Lo = np.tril(capi.cholesky(A[: n - 1, : n - 1]))
     tril_close(Lo, Lref[: n - 1, : n - 1], rtol=1e-10, atol=1e-11)
@@ -136,6 +140,30 @@ def test_gp_singular_reports_leading_minor(capi):
     with pytest.raises(capi.SingularMatrixError) as e:
         capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
     assert e.value.info == 2
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_gp_singular_on_tma_cov_path(capi, kernel):
+    """N >= 256 (even) builds K with the TMA / DMMA kernel: coincident points must still give k = alpha bit-for-bit, so
+    a duplicate with zero noise fails the factorisation at the reference's leading minor."""
+    prob = make_problem(300, 5, seed=21)
+    prob["X"][217] = prob["X"][40]
+    prob["noise"][:] = 0.0
+    _, lm = checker().gp(kernel, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    assert lm == 218
+    with pytest.raises(capi.SingularMatrixError) as e:
+        capi.GaussianProcess(kernel, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    assert e.value.info == lm
+
+
+def test_gp_cov_build_tma_matches_checker(capi):
+    # K itself (not only its factor): a huge noise term keeps the factor's first column ~ K[:, 0] / sqrt(K00)
+    for N, dim in [(256, 3), (386, 10), (1000, 7)]:
+        prob = make_problem(N, dim, seed=N)
+        gp = capi.GaussianProcess(0, 1.7, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+        ref, lm = checker().gp(0, 1.7, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+        assert lm == 0
+        tril_close(gp.state()[0], ref.state()[0], rtol=1e-9, atol=1e-11)
 
 
 def test_gp_large_fit_residual(capi):

@@ -293,3 +293,36 @@ def test_grad_log_marginal_likelihood(libs, kernel, g_idx, N, dim):
                 return o.log_marginal_likelihood(kernel, al, ls, *base[3:])
             fd = (val(1e-5) - val(-1e-5)) / 2e-5
             np.testing.assert_allclose(a[k], fd, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="compiled reference not built")
+def test_normal_rng_table_replay():
+    """The device path is compared with the reference's UNMODIFIED multistart drivers by handing it the normals those
+    drivers consume.  Basis: every evaluation rewinds its NormalRNG, so an evaluation driven by NormalRNG(seed) equals —
+    bit for bit — one driven by NormalRNGSimulator over the first draws of NormalRNG(seed); and the drivers run."""
+    from synth import EXAMPLE_INNER_GD, make_problem, unit_bounds
+    ref = orc.load_reference()
+    prob = make_problem(40, 3, seed=3)
+    gp, lm = ref.gp(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    assert lm == 0
+    rng = np.random.default_rng(0)
+    q, mc, seed = 2, 32, 1234
+    cands = rng.uniform(size=(3, q, 3))
+    disc = rng.uniform(size=(6, 3))
+    best = float(gp.mean_additional(disc).min())
+    vals, grads = orc.kg_grad_at_point_list(ref, gp, cands, None, mc, best, EXAMPLE_INNER_GD, unit_bounds(3), disc, 1,
+                                            seed=seed)
+    table = orc.normal_draws(seed, (mc // 2) * q)
+    for c in range(3):
+        v, g = gp.kg(cands[c], None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(3), disc, grad=True)
+        assert v == vals[c]
+        np.testing.assert_array_equal(g, grads[c])
+    starts = rng.uniform(size=(25, q, 3))
+    outer = [1, 4, 1, 0, 0.7, 0.5, 0.3, 1e-7]
+    bp, found = orc.ref_multistart_kg(gp, starts, None, mc, best, outer, EXAMPLE_INNER_GD, unit_bounds(3),
+                                      unit_bounds(3), disc, seed)
+    assert found and np.all((bp >= 0.0) & (bp <= 1.0))
+    # the driver's winner is at least as good as the best start it screened
+    v_best = gp.kg(bp, None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(3), disc)
+    v_starts = [gp.kg(s, None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(3), disc) for s in starts]
+    assert v_best >= max(v_starts) - 1e-12
