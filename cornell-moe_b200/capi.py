@@ -284,6 +284,20 @@ def log_marginal_likelihood(kernel, alpha, lengths, X, y, noise, derivs=None, de
     return val.value
 
 
+def grad_log_marginal_likelihood(kernel, alpha, lengths, X, y, noise, derivs=None, device=0):
+    """cmoe_grad_log_marginal_likelihood: d log p / d (alpha, lengths..., noise by observation type)."""
+    X = _f64(X)
+    N, dim = X.shape
+    derivs = _i32(derivs if derivs is not None else [])
+    grad = np.zeros(dim + 2 + derivs.size)
+    info = ctypes.c_int(0)
+    rc = lib().cmoe_grad_log_marginal_likelihood(int(kernel), ctypes.c_double(alpha), _d(_f64(lengths).ravel()), _d(X),
+                                                 _d(_f64(y).ravel()), _d(_f64(noise).ravel()), _i(derivs), derivs.size,
+                                                 dim, N, int(device), _d(grad), ctypes.byref(info))
+    _check(rc, info.value)
+    return grad
+
+
 def fp64_peaks(device=0):
     """Measured FP64 peaks (TFLOP/s): (DFMA vector pipe, DMMA tensor pipe)."""
     t = np.zeros(2)

@@ -352,6 +352,7 @@ void cmoe_gp_destroy(cmoe_gp* gp) {
 }
 
 int cmoe_gp_dim(const cmoe_gp* gp) { return gp->spec.dim; }
+int cmoe_gp_device(const cmoe_gp* gp) { return gp->device; }
 int cmoe_gp_num_sampled(const cmoe_gp* gp) { return gp->N; }
 int cmoe_gp_num_derivatives(const cmoe_gp* gp) { return gp->spec.g; }
 

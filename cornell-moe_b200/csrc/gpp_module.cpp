@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
 #include <random>
 #include <string>
@@ -285,6 +286,20 @@ std::vector<double> lhc_starts(const std::vector<double>& bounds, int dim, int q
   return out;
 }
 
+// The reference's parallel axis is `max_num_threads` OpenMP threads over the multistart starts; here that knob selects
+// how many GPUs share the starts inside ONE call: min(max_num_threads, visible devices, $CMOE_MAX_DEVICES), beginning
+// with the GP's own device.  One device (the default when CMOE_MAX_DEVICES is unset) keeps the single-GPU path.
+std::vector<int> devices_for(int home_device, int max_num_threads) {
+  int cap = 1;
+  if (const char* e = std::getenv("CMOE_MAX_DEVICES")) cap = std::max(1, std::atoi(e));
+  const int count = cmoe_device_count();
+  const int n = std::max(1, std::min(std::min(max_num_threads, cap), count));
+  std::vector<int> devs{home_device};
+  for (int d = 0; d < count && static_cast<int>(devs.size()) < n; ++d)
+    if (d != home_device) devs.push_back(d);
+  return devs;
+}
+
 py::list multistart_expected_improvement_optimization(const py::object& optimizer_parameters, const GaussianProcess& gp,
                                                       const py::list& domain_bounds, const py::list& being, int q, int p,
                                                       double best_so_far, int max_int_steps, int max_num_threads,
@@ -321,8 +336,11 @@ py::list multistart_expected_improvement_optimization(const py::object& optimize
   } else if (opt_type == OptimizerTypes::kGradientDescent) {
     const cmoe_gd_params gd = gd_of(optimizer_parameters);
     const auto starts = lhc_starts(bounds, dim, q, gd.num_multistarts, rnd.uniform_engine);
-    check(cmoe_multistart_ei(gp.h, &gd, bounds.data(), starts.data(), gd.num_multistarts, q, Xp.data(), p, max_int_steps,
-                             best_so_far, rnd.seed0(), nullptr, best.data(), &best_value, &found, &info), info);
+    const std::vector<int> devs = devices_for(cmoe_gp_device(gp.h), max_num_threads);
+    const cmoe_multistart_opts opts{nullptr, 0, devs.data(), static_cast<int>(devs.size())};
+    check(cmoe_multistart_ei_ex(gp.h, &gd, bounds.data(), starts.data(), gd.num_multistarts, q, Xp.data(), p,
+                                max_int_steps, best_so_far, rnd.seed0(), &opts, nullptr, best.data(), &best_value, &found,
+                                &info), info);
     status["gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
   } else {
     PyErr_SetString(g_exc_base, "ERROR: invalid optimizer choice. Setting all coordinates to 0.0.");
@@ -470,9 +488,11 @@ py::list multistart_knowledge_gradient_optimization(const py::object& optimizer_
   } else if (opt_type == OptimizerTypes::kGradientDescent) {
     const cmoe_gd_params gd = gd_of(optimizer_parameters);
     const auto starts = lhc_starts(bounds, dim, q, gd.num_multistarts, rnd.uniform_engine);
-    check(cmoe_multistart_kg(gp.h, num_fidelity, &gd, &inner, bounds.data(), inner_bounds.data(), D.data(), num_pts,
-                             starts.data(), gd.num_multistarts, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(),
-                             nullptr, best.data(), &best_value, &found, &info), info);
+    const std::vector<int> devs = devices_for(cmoe_gp_device(gp.h), max_num_threads);
+    const cmoe_multistart_opts opts{nullptr, 0, devs.data(), static_cast<int>(devs.size())};
+    check(cmoe_multistart_kg_ex(gp.h, num_fidelity, &gd, &inner, bounds.data(), inner_bounds.data(), D.data(), num_pts,
+                                starts.data(), gd.num_multistarts, q, Xp.data(), p, max_int_steps, best_so_far,
+                                rnd.seed0(), &opts, nullptr, best.data(), &best_value, &found, &info), info);
     status["gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
   } else {
     PyErr_SetString(g_exc_base, "ERROR: invalid optimizer choice. Setting all coordinates to 0.0.");
@@ -925,8 +945,29 @@ PYBIND11_MODULE(GPP, m) {
                                              &info), info);
           return value;
         });
-  for (const char* name : {"compute_hyperparameter_grad_log_likelihood",
-                           "multistart_hyperparameter_optimization", "restarted_hyperparameter_optimization",
+  // compute_hyperparameter_grad_log_likelihood(... same arguments ...)   gpp_python_model_selection.cpp:89-140
+  m.def("compute_hyperparameter_grad_log_likelihood",
+        [](const py::list& points_sampled, const py::list& points_sampled_value, int dim, int num_sampled,
+           LogLikelihoodTypes objective_type, const py::list& hyperparameters, const py::list& derivatives,
+           int num_derivatives, const py::list& noise_variance) -> py::list {
+          if (objective_type != LogLikelihoodTypes::kLogMarginalLikelihood) {
+            PyErr_SetString(g_exc_base, "ERROR: invalid objective mode choice. Setting all gradients to DBL_MAX.");
+            throw py::error_already_set();
+          }
+          const double alpha = hyperparameters[0].cast<double>();
+          const auto lengths = to_vec(hyperparameters[1].cast<py::list>(), dim);
+          const auto X = to_vec(points_sampled, static_cast<size_t>(dim) * num_sampled);
+          const auto y = to_vec(points_sampled_value, static_cast<size_t>(num_sampled) * (1 + num_derivatives));
+          const auto noise = to_vec(noise_variance, 1 + num_derivatives);
+          const auto derivs = to_ivec(derivatives, num_derivatives);
+          std::vector<double> grad(static_cast<size_t>(dim) + 2 + num_derivatives);
+          int info = 0;
+          check(cmoe_grad_log_marginal_likelihood(CMOE_KERNEL_MATERN_NU_2P5, alpha, lengths.data(), X.data(), y.data(),
+                                                  noise.data(), derivs.data(), num_derivatives, dim, num_sampled, 0,
+                                                  grad.data(), &info), info);
+          return to_list(grad);
+        });
+  for (const char* name : {"multistart_hyperparameter_optimization", "restarted_hyperparameter_optimization",
                            "evaluate_log_likelihood_at_hyperparameter_list",
                            "heuristic_expected_improvement_optimization"}) {
     const std::string n(name);

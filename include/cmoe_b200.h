@@ -94,8 +94,18 @@ int cmoe_log_marginal_likelihood(int kernel, double alpha, const double* lengths
                                  const double* points_sampled_value, const double* noise_variance,
                                  const int* derivatives, int num_derivatives, int dim, int num_sampled, int device,
                                  double* log_likelihood, int* info);
+/* d log p / d (alpha, l_1..l_dim, noise_0..noise_g): LogMarginalLikelihoodEvaluator::ComputeGradLogLikelihood
+ * (gpp_model_selection.cpp:629-690) with HyperparameterGradCovariance (gpp_covariance.cpp:245-317, 461-489); Python
+ * boundary compute_hyperparameter_grad_log_likelihood (gpp_python_model_selection.cpp:89-140).  grad[dim + 2 + g].
+ * One device fit, K^-1 by the blocked solves, one fused 1/2 tr[(a a^T - K^-1) dK/d theta] contraction kernel.  Keeps the
+ * reference's Matern quirk (only the value-value entry of a derivative block contributes).  Singular K: zeros. */
+int cmoe_grad_log_marginal_likelihood(int kernel, double alpha, const double* lengths, const double* points_sampled,
+                                      const double* points_sampled_value, const double* noise_variance,
+                                      const int* derivatives, int num_derivatives, int dim, int num_sampled, int device,
+                                      double* grad, int* info);
 void cmoe_gp_destroy(cmoe_gp* gp);
 int cmoe_gp_dim(const cmoe_gp* gp);
+int cmoe_gp_device(const cmoe_gp* gp);
 int cmoe_gp_num_sampled(const cmoe_gp* gp);
 int cmoe_gp_num_derivatives(const cmoe_gp* gp);
 /* Copies out K_chol_ (n*n, lower triangle valid), K_inv_y_ (n) and mean_ (gpp_math.hpp:838-867); any may be NULL. */

@@ -181,3 +181,17 @@ def test_posterior_mean_screening_batch(capi):
     lst = GPP.compute_posterior_mean_of_points(g, 0, list(pts[:300].ravel()), 300)
     np.testing.assert_allclose(-np.array(lst), mu[:300], rtol=1e-12)
     assert abs(GPP.compute_posterior_mean(g, 0, list(pts[5])) - lst[5]) < 1e-12
+
+
+@needs_ref
+@pytest.mark.parametrize("kernel,g_idx,N,dim", [(0, (), 60, 3), (1, (), 60, 3), (0, (0, 2), 25, 3), (1, (0,), 20, 2),
+                                               (0, (), 400, 6), (1, (), 700, 5)])
+def test_grad_log_marginal_likelihood_matches_reference(capi, kernel, g_idx, N, dim):
+    """§8f rank 2: hyper-parameter gradient of log p(y | X, theta) on the device vs
+    LogMarginalLikelihoodEvaluator::ComputeGradLogLikelihood (incl. the Matern routine's value-entry-only quirk)."""
+    prob = make_problem(N, dim, g_idx=g_idx, seed=5 + N)
+    args = (kernel, 1.3, prob["lengths"] * np.linspace(1.0, 1.5, dim), prob["X"], prob["y"], prob["noise"],
+            prob["derivs"])
+    got = capi.grad_log_marginal_likelihood(*args)
+    want = orc.load_reference().grad_log_marginal_likelihood(*args)
+    np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9 * np.abs(want).max())
