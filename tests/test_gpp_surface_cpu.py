@@ -70,7 +70,7 @@ def test_randomness_container():
 
 
 def test_off_path_entries_raise_the_library_exception():
-    for name in ("compute_hyperparameter_grad_log_likelihood", "multistart_hyperparameter_optimization",
+    for name in ("restarted_hyperparameter_optimization", "multistart_hyperparameter_optimization",
                  "heuristic_expected_improvement_optimization", "run_cpp_tests"):
         with pytest.raises(C_GP.OptimalLearningException):
             getattr(C_GP, name)() if name == "run_cpp_tests" else getattr(C_GP, name)(1, 2, x=3)
