@@ -382,17 +382,30 @@ def _gd_args(gp, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_fi
 
 class MultistartOpts(ctypes.Structure):
     _fields_ = [("normals_table", ctypes.POINTER(ctypes.c_double)), ("table_len", ctypes.c_size_t),
-                ("devices", ctypes.POINTER(ctypes.c_int)), ("num_devices", ctypes.c_int)]
+                ("devices", ctypes.POINTER(ctypes.c_int)), ("num_devices", ctypes.c_int),
+                ("domain_type", ctypes.c_int)]
 
 
-def _multistart_opts(table, devices):
+TENSOR_PRODUCT, SIMPLEX = 0, 1
+
+
+def limit_update(domain_type, bounds, mrc, x, upd):
+    """cmoe_limit_update: one LimitUpdate of the outer optimiser's domain (host arithmetic)."""
+    x = _f64(x).ravel()
+    upd = _f64(upd).ravel().copy()
+    _check(lib().cmoe_limit_update(int(domain_type), _d(_f64(bounds).ravel()), x.size, ctypes.c_double(mrc), _d(x),
+                                   _d(upd)))
+    return upd
+
+
+def _multistart_opts(table, devices, domain_type=0):
     """(opts struct or None, keep-alive tuple) for cmoe_multistart_{kg,ei}_ex."""
-    if table is None and not devices:
+    if table is None and not devices and not domain_type:
         return None, ()
     t = _f64(table).ravel() if table is not None else None
     dv = _i32(devices) if devices else None
     o = MultistartOpts(_d(t) if t is not None else None, t.size if t is not None else 0,
-                       _i(dv) if dv is not None else None, dv.size if dv is not None else 0)
+                       _i(dv) if dv is not None else None, dv.size if dv is not None else 0, int(domain_type))
     return o, (t, dv)
 
 
@@ -420,7 +433,8 @@ def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_boun
     return best, bv.value, bool(found.value), vals
 
 
-def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0, table=None, devices=None):
+def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed=0, table=None, devices=None,
+                  domain_type=0):
     starts = _f64(starts)
     ns, q, dim = starts.shape
     Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
@@ -431,7 +445,7 @@ def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, see
     bv = ctypes.c_double()
     found = ctypes.c_int()
     info = ctypes.c_int()
-    opts, keep = _multistart_opts(table, devices)
+    opts, keep = _multistart_opts(table, devices, domain_type)
     rc = lib().cmoe_multistart_ei_ex(gp.h, ctypes.byref(outer), _d(db), _d(starts), ns, q, _d(Xp), Xp.shape[0],
                                      int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed),
                                      ctypes.byref(opts) if opts is not None else None, _d(vals), _d(best),

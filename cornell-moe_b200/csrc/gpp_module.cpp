@@ -286,6 +286,26 @@ std::vector<double> lhc_starts(const std::vector<double>& bounds, int dim, int q
   return out;
 }
 
+// Starts inside the unit simplex intersected with the box, by rejection from the (clipped) box as
+// SimplexIntersectTensorProductDomain::GeneratePointInDomain does (gpp_domain.cpp:153-163): every one of the q points of a
+// start is drawn until it lies in the simplex (at most 10000 attempts each, then the last draw is kept).
+std::vector<double> simplex_starts(const std::vector<double>& bounds, int dim, int q, int num, std::mt19937& eng) {
+  std::vector<double> out(static_cast<size_t>(num) * q * dim);
+  for (size_t pt = 0; pt < static_cast<size_t>(num) * q; ++pt) {
+    double* x = out.data() + pt * dim;
+    for (int attempt = 0; attempt < 10000; ++attempt) {
+      double sum = 0.0;
+      for (int d = 0; d < dim; ++d) {
+        const double lo = std::max(bounds[2 * d], 0.0), hi = std::min(bounds[2 * d + 1], 1.0);
+        x[d] = std::uniform_real_distribution<double>(lo, hi)(eng);
+        sum += x[d];
+      }
+      if (sum <= 1.0) break;
+    }
+  }
+  return out;
+}
+
 // The reference's parallel axis is `max_num_threads` OpenMP threads over the multistart starts; here that knob selects
 // how many GPUs share the starts inside ONE call: min(max_num_threads, visible devices, $CMOE_MAX_DEVICES), beginning
 // with the GP's own device.  One device (the default when CMOE_MAX_DEVICES is unset) keeps the single-GPU path.
@@ -311,16 +331,16 @@ py::list multistart_expected_improvement_optimization(const py::object& optimize
   const auto Xp = to_vec(being, static_cast<size_t>(p) * dim);
   const auto domain_type = optimizer_parameters.attr("domain_type").cast<DomainTypes>();
   const auto opt_type = optimizer_parameters.attr("optimizer_type").cast<OptimizerTypes>();
-  if (domain_type != DomainTypes::kTensorProduct) {
-    PyErr_SetString(g_exc_base, "only the tensor_product domain is implemented on the B200 path");
-    throw py::error_already_set();
-  }
+  const bool simplex = domain_type == DomainTypes::kSimplex;
+  auto make_starts = [&](int n) {
+    return simplex ? simplex_starts(bounds, dim, q, n, rnd.uniform_engine) : lhc_starts(bounds, dim, q, n, rnd.uniform_engine);
+  };
   std::vector<double> best(static_cast<size_t>(q) * dim, 0.0);
   double best_value = 0.0;
   int found = 0, info = 0;
   if (opt_type == OptimizerTypes::kNull) {
     const int n = optimizer_parameters.attr("num_random_samples").cast<int>();
-    const auto starts = lhc_starts(bounds, dim, q, n, rnd.uniform_engine);
+    const auto starts = make_starts(n);
     std::vector<double> vals(n);
     check(cmoe_ei_eval(gp.h, starts.data(), n, q, Xp.data(), p, max_int_steps, best_so_far, rnd.seed0(), nullptr,
                        vals.data(), nullptr, &info), info);
@@ -332,16 +352,17 @@ py::list multistart_expected_improvement_optimization(const py::object& optimize
         found = 1;
         std::copy(starts.begin() + static_cast<size_t>(i) * q * dim, starts.begin() + static_cast<size_t>(i + 1) * q * dim, best.begin());
       }
-    status["lhc_tensor_product_domain_found_update"] = static_cast<bool>(found);
+    status[simplex ? "lhc_simplex_domain_found_update" : "lhc_tensor_product_domain_found_update"] = static_cast<bool>(found);
   } else if (opt_type == OptimizerTypes::kGradientDescent) {
     const cmoe_gd_params gd = gd_of(optimizer_parameters);
-    const auto starts = lhc_starts(bounds, dim, q, gd.num_multistarts, rnd.uniform_engine);
+    const auto starts = make_starts(gd.num_multistarts);
     const std::vector<int> devs = devices_for(cmoe_gp_device(gp.h), max_num_threads);
-    const cmoe_multistart_opts opts{nullptr, 0, devs.data(), static_cast<int>(devs.size())};
+    const cmoe_multistart_opts opts{nullptr, 0, devs.data(), static_cast<int>(devs.size()),
+                                    simplex ? CMOE_DOMAIN_SIMPLEX : CMOE_DOMAIN_TENSOR_PRODUCT};
     check(cmoe_multistart_ei_ex(gp.h, &gd, bounds.data(), starts.data(), gd.num_multistarts, q, Xp.data(), p,
                                 max_int_steps, best_so_far, rnd.seed0(), &opts, nullptr, best.data(), &best_value, &found,
                                 &info), info);
-    status["gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
+    status[simplex ? "gradient_descent_simplex_domain_found_update" : "gradient_descent_tensor_product_domain_found_update"] = static_cast<bool>(found);
   } else {
     PyErr_SetString(g_exc_base, "ERROR: invalid optimizer choice. Setting all coordinates to 0.0.");
     throw py::error_already_set();

@@ -44,11 +44,49 @@ double limit_step_host(double step, double x, double lo, double hi, double mrc) 
   return step;
 }
 
+// SimplexIntersectTensorProductDomain::LimitUpdate (gpp_domain.cpp:234-289) for one point: box limited to [0,1]^dim
+// (constructor, :107-139), tensor-product limit first, then half the distance to the diagonal face if the limited step
+// would leave the simplex.
+void limit_update_simplex_host(const double* bounds, int dim, double mrc, const double* x, double* upd) {
+  if (mrc == 1.0) mrc -= 4.0 * std::numeric_limits<double>::epsilon();  // kRelativeChangeEpsilonTweak
+  for (int d = 0; d < dim; ++d) {
+    const double lo = std::fmax(bounds[2 * d], 0.0), hi = std::fmin(bounds[2 * d + 1], 1.0);
+    upd[d] = limit_step_host(upd[d], x[d], lo, hi, mrc);
+  }
+  double norm = 0.0;
+  for (int d = 0; d < dim; ++d) norm += upd[d] * upd[d];
+  norm = std::sqrt(norm);
+  if (norm == 0.0) norm = std::numeric_limits<double>::min();
+  bool inside = true;
+  double sum = 0.0;
+  for (int d = 0; d < dim; ++d) {
+    const double t = x[d] + upd[d];
+    if (t < 0.0) inside = false;
+    sum += t;
+  }
+  inside = inside && (sum - 4.0 * std::numeric_limits<double>::epsilon()) <= 1.0;  // CheckPointInUnitSimplex
+  if (!inside) {
+    // plane -1/sqrt(dim) + sum_i x_i / sqrt(dim) = 0; distance along the unit direction (gpp_geometry.hpp:252-272)
+    const double nrm = 1.0 / std::sqrt(static_cast<double>(dim));
+    double xn = 0.0, vn = 0.0;
+    for (int d = 0; d < dim; ++d) {
+      xn += x[d] * nrm;
+      vn += (upd[d] / norm) * nrm;
+    }
+    const double numerator = nrm - xn;
+    double dist = (vn == 0.0) ? ((numerator == 0.0) ? 0.0 : std::numeric_limits<double>::infinity()) : numerator / vn;
+    if (dist < 0.0) dist = 0.0;
+    const double step = 0.5 * dist;  // kInvalidStepScaleFactor
+    for (int d = 0; d < dim; ++d) upd[d] = step * (upd[d] / norm);
+  }
+}
+
 using BatchEval = std::function<void(const double* pts, int nc, double* values, double* grads)>;
 
 // Restarted gradient descent on `ns` starts at once.  eval(pts, nc, values, grads): grads may be NULL.
 void gradient_descent_batch(const BatchEval& eval, const cmoe_gd_params& gd, const double* domain_bounds, int q,
-                            int dim, const double* starts, int ns, double* values_out, double* points_out) {
+                            int dim, const double* starts, int ns, double* values_out, double* points_out,
+                            int domain_type = CMOE_DOMAIN_TENSOR_PRODUCT) {
   const int ps = q * dim;
   std::vector<double> x(starts, starts + static_cast<size_t>(ns) * ps);
   if (gd.max_num_restarts > 0) {
@@ -80,12 +118,25 @@ void gradient_descent_batch(const BatchEval& eval, const cmoe_gd_params& gd, con
           double* xs = x.data() + static_cast<size_t>(cur[k]) * ps;
           const double* g = grads.data() + static_cast<size_t>(k) * ps;
           double ns2 = 0.0;
-          for (int j = 0; j < ps; ++j) {
-            const int d = j % dim;
-            const double step = limit_step_host(alpha * g[j], xs[j], domain_bounds[2 * d], domain_bounds[2 * d + 1],
-                                                gd.max_relative_change);
-            xs[j] += step;
-            ns2 += step * step;
+          if (domain_type == CMOE_DOMAIN_SIMPLEX) {
+            // RepeatedDomain::LimitUpdate: each of the q points against the simplex domain (gpp_domain.hpp:536-540)
+            double upd[CMOE_MAX_DIM];
+            for (int pt = 0; pt < q; ++pt) {
+              for (int d = 0; d < dim; ++d) upd[d] = alpha * g[pt * dim + d];
+              limit_update_simplex_host(domain_bounds, dim, gd.max_relative_change, xs + pt * dim, upd);
+              for (int d = 0; d < dim; ++d) {
+                xs[pt * dim + d] += upd[d];
+                ns2 += upd[d] * upd[d];
+              }
+            }
+          } else {
+            for (int j = 0; j < ps; ++j) {
+              const int d = j % dim;
+              const double step = limit_step_host(alpha * g[j], xs[j], domain_bounds[2 * d], domain_bounds[2 * d + 1],
+                                                  gd.max_relative_change);
+              xs[j] += step;
+              ns2 += step * step;
+            }
           }
           if (std::sqrt(ns2) < step_tol) run_done[cur[k]] = 1;
         }
@@ -126,7 +177,8 @@ std::vector<int> top_k_indices(const double* values, int n) {
 
 void multistart_common(const BatchEval& eval, const cmoe_gd_params& outer, const double* domain_bounds, int q, int dim,
                        const double* starts, int num_starts, double init_best, double* start_values,
-                       double* best_point, double* best_value, int* found_flag) {
+                       double* best_point, double* best_value, int* found_flag,
+                       int domain_type = CMOE_DOMAIN_TENSOR_PRODUCT) {
   const int ps = q * dim;
   std::vector<double> vals(num_starts);
   eval(starts, num_starts, vals.data(), nullptr);
@@ -137,7 +189,7 @@ void multistart_common(const BatchEval& eval, const cmoe_gd_params& outer, const
   for (int i = 0; i < k; ++i)
     std::copy(starts + static_cast<size_t>(top[i]) * ps, starts + static_cast<size_t>(top[i] + 1) * ps,
               tk.begin() + static_cast<size_t>(i) * ps);
-  gradient_descent_batch(eval, outer, domain_bounds, q, dim, tk.data(), k, fin_v.data(), fin_p.data());
+  gradient_descent_batch(eval, outer, domain_bounds, q, dim, tk.data(), k, fin_v.data(), fin_p.data(), domain_type);
   // OptimizationIOContainer: best point initialised to the first start, strict `<` update
   double best = init_best;
   int found = 0;
@@ -446,6 +498,21 @@ void validate_bounds(const double* b, int dim) {
 
 extern "C" {
 
+int cmoe_limit_update(int domain_type, const double* domain_bounds, int dim, double max_relative_change,
+                      const double* current_point, double* update) {
+  return guarded(nullptr, [&] {
+    CMOE_REQUIRE(dim >= 1 && dim <= CMOE_MAX_DIM, CMOE_ERR_BOUNDS, "dim must be in [1, CMOE_MAX_DIM]");
+    if (domain_type == CMOE_DOMAIN_SIMPLEX) {
+      limit_update_simplex_host(domain_bounds, dim, max_relative_change, current_point, update);
+    } else {
+      CMOE_REQUIRE(domain_type == CMOE_DOMAIN_TENSOR_PRODUCT, CMOE_ERR_INVALID_VALUE, "unknown domain type");
+      for (int d = 0; d < dim; ++d)
+        update[d] = limit_step_host(update[d], current_point[d], domain_bounds[2 * d], domain_bounds[2 * d + 1],
+                                    max_relative_change);
+    }
+  });
+}
+
 int cmoe_multistart_kg_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
                           const double* domain_bounds, const double* inner_bounds, const double* discrete_pts,
                           int num_pts, const double* starts, int num_starts, int q, const double* points_being_sampled,
@@ -455,6 +522,9 @@ int cmoe_multistart_kg_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_par
     CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
     require_device(gp->device);
     validate_bounds(domain_bounds, gp->spec.dim);
+    CMOE_REQUIRE(!opts || opts->domain_type == CMOE_DOMAIN_TENSOR_PRODUCT, CMOE_ERR_INVALID_VALUE,
+                 "q-KG: only the tensor_product domain is implemented (the per-sample inner optimiser of the fused "
+                 "kernel has no simplex LimitUpdate)");
     const std::vector<int> devs = device_list(gp, opts);
     const int G = static_cast<int>(devs.size());
     ShardedEval sh;
@@ -516,8 +586,11 @@ int cmoe_multistart_ei_ex(const cmoe_gp* gp, const cmoe_gd_params* outer, const 
       w.eval = make_ei_eval(w.gp, q, points_being_sampled, p, num_mc, best_so_far, seed, dtable);
     }
     BatchEval f = std::ref(sh);
+    const int domain_type = opts ? opts->domain_type : CMOE_DOMAIN_TENSOR_PRODUCT;
+    CMOE_REQUIRE(domain_type == CMOE_DOMAIN_TENSOR_PRODUCT || domain_type == CMOE_DOMAIN_SIMPLEX, CMOE_ERR_INVALID_VALUE,
+                 "unknown domain type");
     multistart_common(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts, -1.0, start_values, best_point,
-                      best_value, found_flag);
+                      best_value, found_flag, domain_type);
     require_device(gp->device);
   });
 }

@@ -212,7 +212,18 @@ typedef struct cmoe_multistart_opts {
   size_t table_len;
   const int* devices;
   int num_devices;
+  int domain_type; /* CMOE_DOMAIN_TENSOR_PRODUCT (0) or CMOE_DOMAIN_SIMPLEX (1): the outer optimiser's domain */
 } cmoe_multistart_opts;
+/* DomainTypes, gpp_python_common.cpp:201-240.  CMOE_DOMAIN_SIMPLEX = unit simplex intersected with the box
+ * (SimplexIntersectTensorProductDomain, gpp_domain.cpp:107-289): implemented for the q-EI drivers; q-KG needs the same
+ * domain for its per-sample inner optimiser, which the fused kernel only has for the tensor product — it reports
+ * CMOE_ERR_INVALID_VALUE. */
+#define CMOE_DOMAIN_TENSOR_PRODUCT 0
+#define CMOE_DOMAIN_SIMPLEX 1
+/* One LimitUpdate of the outer optimiser's domain (host arithmetic, no device needed): update[dim] is limited in place.
+ * TensorProductDomain::LimitUpdate gpp_domain.cpp:64-104 / SimplexIntersectTensorProductDomain::LimitUpdate :234-289. */
+int cmoe_limit_update(int domain_type, const double* domain_bounds, int dim, double max_relative_change,
+                      const double* current_point, double* update);
 int cmoe_multistart_kg_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer, const cmoe_gd_params* inner,
                           const double* domain_bounds, const double* inner_bounds, const double* discrete_pts,
                           int num_pts, const double* starts, int num_starts, int q, const double* points_being_sampled,

@@ -410,3 +410,23 @@ def ref_multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds,
     lib.ref_multistart_ei(gp.h, _d(_f64(outer)), _d(_f64(domain_bounds).ravel()), _d(starts), ns, q, _d(Xp),
                           Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint(seed), _d(best))
     return best
+
+
+def ref_limit_update_simplex(bounds, mrc, x, upd):
+    """SimplexIntersectTensorProductDomain::LimitUpdate of the compiled reference; returns the limited update."""
+    lib = load_reference().lib
+    x = _f64(x).ravel()
+    upd = _f64(upd).ravel().copy()
+    lib.ref_limit_update_simplex(_d(_f64(bounds).ravel()), x.size, ctypes.c_double(mrc), _d(x), _d(upd))
+    return upd
+
+
+def ref_multistart_ei_simplex(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, seed):
+    lib = load_reference().lib
+    starts = _f64(starts)
+    ns, q, dim = starts.shape
+    Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
+    best = np.empty((q, dim))
+    lib.ref_multistart_ei_simplex(gp.h, _d(_f64(outer)), _d(_f64(domain_bounds).ravel()), _d(starts), ns, q, _d(Xp),
+                                  Xp.shape[0], int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint(seed), _d(best))
+    return best

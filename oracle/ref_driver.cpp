@@ -340,6 +340,31 @@ void ref_limit_update(const double* bounds, int dim, double max_relative_change,
   dom.LimitUpdate(max_relative_change, current_point, update);
 }
 
+// SimplexIntersectTensorProductDomain::LimitUpdate (gpp_domain.cpp:234-289)
+void ref_limit_update_simplex(const double* bounds, int dim, double max_relative_change, const double* current_point,
+                              double* update) {
+  std::vector<ClosedInterval> iv(dim);
+  for (int i = 0; i < dim; ++i) iv[i] = ClosedInterval(bounds[2 * i], bounds[2 * i + 1]);
+  SimplexIntersectTensorProductDomain dom(iv.data(), dim);
+  dom.LimitUpdate(max_relative_change, current_point, update);
+}
+
+// the q-EI multistart driver over the simplex-intersect-box domain
+void ref_multistart_ei_simplex(void* h, const double* gd_outer, const double* bounds, const double* starts,
+                               int num_starts, int q, const double* Xp, int p, int num_mc, double best_so_far,
+                               unsigned seed, double* best_point) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  std::vector<ClosedInterval> iv(gp->dim());
+  for (int i = 0; i < gp->dim(); ++i) iv[i] = ClosedInterval(bounds[2 * i], bounds[2 * i + 1]);
+  SimplexIntersectTensorProductDomain dom(iv.data(), gp->dim());
+  GradientDescentParameters outer = MakeGD(gd_outer);
+  NormalRNG rng(seed);
+  ThreadSchedule sched(1, omp_sched_static);
+  bool found = false;
+  ComputeOptimalPointsToSampleViaMultistartGradientDescent(*gp, outer, dom, sched, starts, Xp, num_starts, q, p,
+                                                           best_so_far, num_mc, &rng, &found, best_point);
+}
+
 // ---- the multistart drivers themselves, UNMODIFIED, single-threaded --------------------------------------------------
 // Every q-KG / q-EI evaluation rewinds its NormalRNG (ResetToMostRecentSeed, gpp_knowledge_gradient_optimization.cpp:81,
 // 164; gpp_math.cpp:2011, 2076), so a whole driver call consumes the same first draws of NormalRNG(seed) over and over:

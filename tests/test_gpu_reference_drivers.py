@@ -195,3 +195,26 @@ def test_grad_log_marginal_likelihood_matches_reference(capi, kernel, g_idx, N, 
     got = capi.grad_log_marginal_likelihood(*args)
     want = orc.load_reference().grad_log_marginal_likelihood(*args)
     np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9 * np.abs(want).max())
+
+
+@needs_ref
+def test_multistart_ei_simplex_domain_matches_reference_driver(capi):
+    """§8f rank 4: the q-EI multistart driver over SimplexIntersectTensorProductDomain (gpp_domain.cpp:107-289) vs the
+    reference's own driver instantiated with that domain."""
+    prob = make_problem(25, 3, seed=8, noise=0.05)
+    prob["X"] *= 0.33  # training data inside the simplex
+    gp = capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    ref, lm = orc.load_reference().gp(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    assert lm == 0
+    rng = np.random.default_rng(19)
+    q, mc, seed = 2, 256, 7
+    starts = rng.dirichlet(np.ones(4), size=(30, q))[:, :, :3] * 0.9
+    best = float(prob["y"].min()) + 0.2
+    outer = [30, 10, 2, 0, 0.7, 0.8, 1.0, 1e-7]  # max_relative_change = 1.0 exercises the epsilon tweak
+    bounds = np.tile([0.0, 1.0], 3)
+    table = orc.normal_draws(seed, mc * q)
+    bp_ref = orc.ref_multistart_ei_simplex(ref, starts, None, mc, best, outer, bounds, seed)
+    bp, bv, found, sv = capi.multistart_ei(gp, starts, None, mc, best, outer, bounds, seed=1, table=table,
+                                           domain_type=capi.SIMPLEX)
+    assert np.all(bp >= 0.0) and np.all(bp.sum(axis=1) <= 1.0 + 1e-12)
+    np.testing.assert_allclose(bp, bp_ref, rtol=1e-4, atol=1e-5)

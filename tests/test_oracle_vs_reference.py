@@ -326,3 +326,29 @@ def test_normal_rng_table_replay():
     v_best = gp.kg(bp, None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(3), disc)
     v_starts = [gp.kg(s, None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(3), disc) for s in starts]
     assert v_best >= max(v_starts) - 1e-12
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="compiled reference not built")
+def test_simplex_limit_update_host_logic():
+    """SimplexIntersectTensorProductDomain::LimitUpdate (gpp_domain.cpp:234-289) as the multistart drivers' host code
+    restates it (cmoe_limit_update needs no device): random points in the simplex, random steps, all three regimes
+    (inside, clipped by the box, clipped by the diagonal face), max_relative_change = 1 included."""
+    from cornell_moe_b200 import capi
+    rng = np.random.default_rng(12)
+    hit_face = 0
+    for trial in range(400):
+        dim = int(rng.integers(2, 7))
+        x = rng.dirichlet(np.ones(dim + 1))[:dim] * rng.uniform(0.6, 1.0)
+        lo = np.minimum(x, rng.uniform(0.0, 0.2, dim)) * rng.integers(0, 2, dim)
+        hi = np.maximum(x, rng.uniform(0.5, 1.3, dim))
+        bounds = np.stack([lo, hi], axis=1).ravel()
+        upd = (rng.standard_normal(dim) + rng.choice([0.0, 1.0])) * rng.choice([0.01, 0.3, 2.0])
+        mrc = float(rng.choice([0.3, 0.8, 1.0]))
+        want = orc.ref_limit_update_simplex(bounds, mrc, x, upd)
+        got = capi.limit_update(capi.SIMPLEX, bounds, mrc, x, upd)
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-300)
+        box = capi.limit_update(capi.TENSOR_PRODUCT, bounds, mrc, x, upd)
+        ref_box = orc.load_reference().limit_update(bounds, mrc, x, upd.copy())
+        np.testing.assert_allclose(box, ref_box if ref_box is not None else box, rtol=1e-14, atol=0)
+        hit_face += (x + box).sum() > 1.0 + 1e-9  # the box-limited step would leave the simplex: the face clip fires
+    assert hit_face > 20
