@@ -1104,9 +1104,12 @@ size_t kg_smem_bytes(int N, int U) {
   { K, D, Q, &launch_kg_mc<K, D, Q>, nullptr, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
 #define CMOE_KG_ENTRY_GEN(K, D, Q) \
   { K, D, Q, &launch_kg_mc<K, D, Q>, &launch_kg_mc_gen<K, D, Q>, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
+// union-row counts: 2, 4, 8, 16, 24, 32 (24 serves config 4: q = 4 with 4 derivative observations -> 20 rows; the
+// 32-wide instantiation spilled ~1.5 KB per thread there)
 #define CMOE_KG_ENTRIES_FOR_DIM(D)                                                                              \
   CMOE_KG_ENTRY(0, D, 2), CMOE_KG_ENTRY(0, D, 4), CMOE_KG_ENTRY_GEN(0, D, 8), CMOE_KG_ENTRY_GEN(0, D, 16),       \
-      CMOE_KG_ENTRY_GEN(0, D, 32), CMOE_KG_ENTRY(1, D, 2), CMOE_KG_ENTRY(1, D, 4), CMOE_KG_ENTRY_GEN(1, D, 8),  \
-      CMOE_KG_ENTRY_GEN(1, D, 16), CMOE_KG_ENTRY_GEN(1, D, 32)
+      CMOE_KG_ENTRY_GEN(0, D, 24), CMOE_KG_ENTRY_GEN(0, D, 32), CMOE_KG_ENTRY(1, D, 2), CMOE_KG_ENTRY(1, D, 4),  \
+      CMOE_KG_ENTRY_GEN(1, D, 8), CMOE_KG_ENTRY_GEN(1, D, 16), CMOE_KG_ENTRY_GEN(1, D, 24),                    \
+      CMOE_KG_ENTRY_GEN(1, D, 32)
 
 }  // namespace cmoe
