@@ -172,6 +172,25 @@ def test_dkg_config4_shape_spot_check(capi):
         np.testing.assert_allclose(grad[c], g, rtol=1e-4, atol=1e-7)
 
 
+def test_dkg_config4_full_size(capi):
+    """BASELINE.json configs[3] at FULL training size: d = 4, N = 300 with all 4 partial derivatives observed (system
+    n = 1500), q = 4 (20 union rows -> the 24-row instantiation); two candidates, 64 samples, same normals as the
+    reference (table replay)."""
+    prob = make_problem(300, 4, g_idx=(0, 1, 2, 3), seed=44, noise=1e-2)
+    gp, ref = _pair(capi, 0, prob)
+    rng = np.random.default_rng(5)
+    q, mc = 4, 64
+    cands = rng.uniform(size=(2, q, 4))
+    disc = rng.uniform(size=(10, 4))
+    best = float(ref.mean_additional(disc).min())
+    table = orc.philox_normals(0xC0FFEE, 0, mc // 2, q * 5)
+    kg, grad = gp.kg(cands, None, mc, best, EXAMPLE_INNER_GD, unit_bounds(4), disc, seed=0xC0FFEE, grad=True)
+    for c in range(2):
+        v, g = ref.kg(cands[c], None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(4), disc, grad=True)
+        np.testing.assert_allclose(kg[c], v, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(grad[c], g, rtol=1e-4, atol=1e-7)
+
+
 @pytest.mark.parametrize("dim,q", [(2, 2), (5, 3), (6, 4), (10, 2), (13, 1)])
 def test_kg_other_dimensions(capi, dim, q):
     """Every compiled padded-dimension variant (2, 4, 6, 8, 12, 16, 32) against the checker."""
