@@ -220,6 +220,10 @@ void build_mix_covariance(const KernelSpec& spec, const double* X, int N, const 
 void philox_normals_device(uint64_t seed, uint64_t first_draw, int num_draws, int per_draw, double* out,
                            cudaStream_t s);
 
+// CMOE_LEGACY_LINALG=1 routes the large-N fit through the round-1 kernels (launch-per-step Cholesky, chained trsv,
+// LDGSTS covariance build): an A/B switch for profiling, and a fall-back should a device mis-handle cooperative launches
+bool legacy_linalg();
+
 int launches_issued();        // global counter of kernel launches made by this library (host side)
 void count_launch(int n = 1);
 

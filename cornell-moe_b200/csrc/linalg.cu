@@ -10,6 +10,7 @@
 //
 // Layout: column-major, only the lower triangle of the factor is defined (as in the reference).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_math.cuh"
@@ -714,6 +715,13 @@ void trsv_blocked(const double* L, int n, double* x, bool trans, cudaStream_t s)
 }  // namespace
 
 int launches_issued() { return g_launches; }
+bool legacy_linalg() {
+  static const bool on = [] {
+    const char* e = std::getenv("CMOE_LEGACY_LINALG");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 void count_launch(int n) { g_launches += n; }
 
 // Side stream + events for the look-ahead schedule, created once per host thread and device.
@@ -837,7 +845,7 @@ void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans
   if (nrhs <= 4 && n >= 1024) {
     for (int r = 0; r < nrhs; ++r) {
       double* xr = X + static_cast<size_t>(r) * ldx;
-      if (trsv_coop(L, n, xr, trans, s)) continue;
+      if (!legacy_linalg() && trsv_coop(L, n, xr, trans, s)) continue;
       if (!trsv_chained(L, n, xr, trans, s)) trsv_blocked(L, n, xr, trans, s);
     }
     return;

@@ -74,6 +74,63 @@ __device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __
   return fail;
 }
 
+// Same factorisation, two columns per round: the 2 x 2 pivot block [l11 0; l21 l22] is formed from three shuffles, both
+// multiplier columns travel through ONE shared-memory round trip and the window is updated by a rank-2 step.  The
+// arithmetic (operation order and roundings) is exactly that of two successive rounds of chol32_warp<true>; only the
+// synchronisation per column is halved — the column recurrence is the latency-critical chain of the factorisation.
+// colbuf: [2][2][64] with [32..63] of every column zero.
+__device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, double* __restrict__ colbuf,
+                                                double* __restrict__ LT, double* __restrict__ rd, int col0) {
+  int fail = 0;
+#pragma unroll 1
+  for (int j = 0; j < 32; j += 2) {
+    const double p11 = __shfl_sync(0xffffffffu, a[0], j);
+    const double p21 = __shfl_sync(0xffffffffu, a[0], j + 1);
+    const double p22 = __shfl_sync(0xffffffffu, a[1], j + 1);
+    fail = (fail == 0 && !(p11 > kPivotTol)) ? j + 1 : fail;
+    // column j
+    const double y1 = rsqrt(p11);
+    double l11 = p11 * y1;
+    l11 = fma(0.5 * y1, fma(-l11, l11, p11), l11);
+    double q1 = a[0] * y1;
+    q1 = fma(fma(-q1, l11, a[0]), y1, q1);
+    double l21 = p21 * y1;  // what lane j+1 computes as its q1 (same operations on the same operands)
+    l21 = fma(fma(-l21, l11, p21), y1, l21);
+    // column j+1 after the update by column j
+    const double d2 = fma(-l21, l21, p22);
+    fail = (fail == 0 && !(d2 > kPivotTol)) ? j + 2 : fail;
+    const double y2 = rsqrt(d2);
+    double l22 = d2 * y2;
+    l22 = fma(0.5 * y2, fma(-l22, l22, d2), l22);
+    const double a1 = fma(-q1, l21, a[1]);
+    double q2 = a1 * y2;
+    q2 = fma(fma(-q2, l22, a1), y2, q2);
+    const double lj1 = (lane == j) ? l11 : q1;
+    const double lj2 = (lane == j + 1) ? l22 : q2;
+    if (lane >= j) LT[(col0 + j) * LTS + col0 + lane] = lj1;
+    if (lane >= j + 1) LT[(col0 + j + 1) * LTS + col0 + lane] = lj2;
+    if (lane == j) {
+      double r = rsqrt(p11);
+      rd[col0 + j] = fma(fma(-l11, r, 1.0), r, r);
+    }
+    if (lane == j + 1) {
+      double r = rsqrt(d2);
+      rd[col0 + j + 1] = fma(fma(-l22, r, 1.0), r, r);
+    }
+    double* c1 = colbuf + ((j >> 1) & 1) * 128;
+    double* c2 = c1 + 64;
+    c1[lane] = lj1;
+    c2[lane] = lj2;
+    __syncwarp();
+    // window slot k <-> column j + k
+#pragma unroll
+    for (int k = 2; k < 32; ++k) a[k - 2] = fma(-lj2, c2[j + k], fma(-lj1, c1[j + k], a[k]));
+    a[30] = 0.0;
+    a[31] = 0.0;
+  }
+  return fail;
+}
+
 // STEPS steps of  x <- x L^-T  for one row held in a rotating register window of W slots: slot i holds column
 // cbase + i on entry and column cbase + STEPS + i on exit.  The solved value of column k is handed to emit(k, value).
 // LT[k*LTS + c] = L[c][k]; cbase and UNR are multiples of 2 and LTS is even, so pairs of multipliers come as one

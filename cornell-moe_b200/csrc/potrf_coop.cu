@@ -207,14 +207,14 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
                                              double* __restrict__ rd, int* __restrict__ sfail) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * LTS + NB; e += CTHREADS) LT[e] = 0.0;
-  for (int e = tid; e < 128; e += CTHREADS) colbuf[e] = 0.0;
+  for (int e = tid; e < 256; e += CTHREADS) colbuf[e] = 0.0;
   for (int e = tid; e < BLK; e += CTHREADS) Minv[e] = 0.0;
   __syncthreads();
   if (warp == 0) {
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[c * SLD + lane] : 0.0;
-    const int f = chol32_warp<true>(a, lane, colbuf, LT, rd, 0);
+    const int f = chol32_warp_pair(a, lane, colbuf, LT, rd, 0);
     if (lane == 0) *sfail = f;
   }
   __syncthreads();
@@ -255,7 +255,7 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[(32 + c) * SLD + 32 + lane] : 0.0;
-    const int f = chol32_warp<true>(a, lane, colbuf, LT, rd, 32);
+    const int f = chol32_warp_pair(a, lane, colbuf, LT, rd, 32);
     if (lane == 0) *sfail = f ? 32 + f : 0;
   } else {
     // Y = L21 * L11^-1 (32 x 32) while warp 0 factors A22: thread -> (i = lane, t); parked in the lower-left block
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ __align__(8) uint64_t empty[STAGES];
   __shared__ __align__(8) uint64_t pbar;
-  __shared__ double colbuf[128];
+  __shared__ double colbuf[256];
   __shared__ double rd[NB];
   __shared__ int s_tile, sfail, sflag;
   if (ld_volatile(P.flag) != 0) return;
@@ -538,11 +538,7 @@ bool make_tensor_map_2d(CUtensorMap* map, const double* base, uint64_t rows, uin
 // Returns false when the cooperative path does not apply (small / odd n, more row blocks than SMs, no cooperative
 // launch): nothing has been touched in that case and the caller takes the launch-per-step path.
 bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
-  static const bool disabled = [] {
-    const char* e = std::getenv("CMOE_POTRF");
-    return e && std::string(e) == "legacy";
-  }();
-  if (disabled || n < 1024 || (n & 1) || (reinterpret_cast<uintptr_t>(A) & 15)) return false;
+  if (legacy_linalg() || n < 1024 || (n & 1) || (reinterpret_cast<uintptr_t>(A) & 15)) return false;
   int dev = 0, sms = 0, coop = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
