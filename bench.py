@@ -263,6 +263,20 @@ def fit_extra(capi, device, fp64_dmma, with_cpu):
                          "achieved": 2 * 4.0 * Nl * (Nl + 1) / fit[2] * 1e-3, "peak": hbm, "unit": "GB/s",
                          "frac": 2 * 4.0 * Nl * (Nl + 1) / fit[2] * 1e-3 / hbm},
         "gp_fit_N5000_usec_cov_chol_solve": fit}
+    # the round-1 kernels on the same box (CMOE_LEGACY_LINALG=1 is read once per process, hence the subprocess)
+    try:
+        env = dict(os.environ, CMOE_LEGACY_LINALG="1")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "chol_probe.py"), "5000"], env=env,
+                           capture_output=True, text=True, timeout=240)
+        for line in r.stdout.splitlines():
+            if "warm:" in line:
+                tok = line.split()
+                out["legacy_round1_kernels"] = {"cov_build_usec": float(tok[tok.index("cov") + 2]),
+                                                "cholesky_usec": float(tok[tok.index("chol") + 2])}
+            if "second fit" in line:
+                out.setdefault("legacy_round1_kernels", {})["fit_line"] = line.strip()
+    except Exception as e:
+        out["legacy_round1_kernels"] = {"error": str(e)}
     if with_cpu:
         try:
             backend = cpu_backend()

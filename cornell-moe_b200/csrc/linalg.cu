@@ -27,8 +27,8 @@ namespace {
 // in LT (transposed) with rd[k] = 1/L_kk (FAST) or L_kk.  Called by all PT threads; returns 0 or the failing 1-based
 // pivot index.
 template <bool FAST>
-__device__ __forceinline__ int factor_block64(double (*S)[NB + 1], double* __restrict__ LT, double* __restrict__ rd,
-                                              double* __restrict__ colbuf, int* __restrict__ sfail) {
+__device__ __forceinline__ int factor_block64(double (*S)[NB + 1], double* LT, double* rd,
+                                              double* colbuf, volatile int* sfail) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp == 0) {
     double a[32];

@@ -36,8 +36,8 @@ constexpr int PT = 128;  // threads of the panel kernel: one panel row per threa
 // dependent latency; small systems (known-answer cases) keep IEEE sqrt / divide.
 constexpr int LTS = NB + 2;  // row stride of the transposed factor (even: 16-byte aligned rows)
 template <bool FAST>
-__device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __restrict__ colbuf /* [2][64], [32..63] = 0 */,
-                                           double* __restrict__ LT, double* __restrict__ rd, int col0) {
+__device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* colbuf /* [2][64], [32..63] = 0 */,
+                                           double* LT, double* rd, int col0) {
   int fail = 0;
 #pragma unroll 1
   for (int j = 0; j < 32; ++j) {
@@ -79,8 +79,8 @@ __device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* __
 // arithmetic (operation order and roundings) is exactly that of two successive rounds of chol32_warp<true>; only the
 // synchronisation per column is halved — the column recurrence is the latency-critical chain of the factorisation.
 // colbuf: [2][2][64] with [32..63] of every column zero.
-__device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, double* __restrict__ colbuf,
-                                                double* __restrict__ LT, double* __restrict__ rd, int col0) {
+__device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, double* colbuf,
+                                                double* LT, double* rd, int col0) {
   int fail = 0;
 #pragma unroll 1
   for (int j = 0; j < 32; j += 2) {
@@ -88,6 +88,7 @@ __device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, doubl
     const double p21 = __shfl_sync(0xffffffffu, a[0], j + 1);
     const double p22 = __shfl_sync(0xffffffffu, a[1], j + 1);
     fail = (fail == 0 && !(p11 > kPivotTol)) ? j + 1 : fail;
+    if (fail) break;  // warp-uniform: nothing after a failed pivot is used; do not feed 0 / NaN to rsqrt
     // column j
     const double y1 = rsqrt(p11);
     double l11 = p11 * y1;
@@ -99,6 +100,7 @@ __device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, doubl
     // column j+1 after the update by column j
     const double d2 = fma(-l21, l21, p22);
     fail = (fail == 0 && !(d2 > kPivotTol)) ? j + 2 : fail;
+    if (fail) break;
     const double y2 = rsqrt(d2);
     double l22 = d2 * y2;
     l22 = fma(0.5 * y2, fma(-l22, l22, d2), l22);
@@ -109,14 +111,8 @@ __device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, doubl
     const double lj2 = (lane == j + 1) ? l22 : q2;
     if (lane >= j) LT[(col0 + j) * LTS + col0 + lane] = lj1;
     if (lane >= j + 1) LT[(col0 + j + 1) * LTS + col0 + lane] = lj2;
-    if (lane == j) {
-      double r = rsqrt(p11);
-      rd[col0 + j] = fma(fma(-l11, r, 1.0), r, r);
-    }
-    if (lane == j + 1) {
-      double r = rsqrt(d2);
-      rd[col0 + j + 1] = fma(fma(-l22, r, 1.0), r, r);
-    }
+    if (lane == j) rd[col0 + j] = fma(fma(-l11, y1, 1.0), y1, y1);          // one Newton step on 1/l from y ~ 1/l
+    if (lane == j + 1) rd[col0 + j + 1] = fma(fma(-l22, y2, 1.0), y2, y2);
     double* c1 = colbuf + ((j >> 1) & 1) * 128;
     double* c2 = c1 + 64;
     c1[lane] = lj1;
@@ -137,8 +133,8 @@ __device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, doubl
 // 16-byte broadcast load; rows of LT must be followed by readable padding (slots past the end of the row read it and
 // are never emitted).
 template <int W, int STEPS, int UNR, bool FAST, typename Emit>
-__device__ __forceinline__ void solve_steps_rot(double (&x)[W], const double* __restrict__ LT,
-                                                const double* __restrict__ rd, int cbase, Emit&& emit) {
+__device__ __forceinline__ void solve_steps_rot(double (&x)[W], const double* LT,
+                                                const double* rd, int cbase, Emit&& emit) {
   static_assert(STEPS % UNR == 0 && UNR % 2 == 0 && W % 2 == 0, "even windows, whole bodies");
 #pragma unroll 1
   for (int kb = 0; kb < STEPS; kb += UNR) {

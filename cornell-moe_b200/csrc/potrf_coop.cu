@@ -25,7 +25,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 
 #include "device_math.cuh"
 #include "internal.cuh"
@@ -47,6 +49,7 @@ constexpr int BLK = SLD * NB;          // doubles per 64-column block buffer (34
 constexpr int OPBOX = KC * OLD;        // doubles per operand box
 constexpr int NBUF = 6;                // 4 slab blocks + 2 staging buffers
 constexpr int kSyncPerPanel = 160;     // ints: [0] tile counter, [1..4] F, [5..20] X[j][kk], [32..] row-tile arrivals
+constexpr int kTraceSlots = 64;
 constexpr size_t kCoopSmem = static_cast<size_t>(NBUF) * BLK * sizeof(double) + 128;
 static_assert(STAGES * 2 * OPBOX <= NBUF * BLK, "operand ring must fit into the slab buffers");
 
@@ -58,6 +61,7 @@ struct CoopParams {
   int* sync;         // this launch's sync area
   double* scratch;   // [4][BLK] published inverses
   int* abort_flag;   // set when a wait gives up
+  unsigned long long* trace;  // optional [gridDim][kTraceSlots] time stamps (CMOE_CHOL_TRACE), else NULL
 };
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -72,6 +76,15 @@ __device__ __forceinline__ bool wait_flag(const int* f, int target, const int* f
       return false;
     }
     __nanosleep(32);
+  }
+}
+
+__device__ __forceinline__ void trace_mark(const CoopParams& P, int slot) {
+  if (P.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + slot] = t;
+    P.trace[static_cast<size_t>(blockIdx.x) * kTraceSlots + kTraceSlots - 1] = slot;  // last checkpoint reached
   }
 }
 
@@ -162,8 +175,8 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring
 // k > c), so the K loop of a warp stops at its last column.
 // --------------------------------------------------------------------------------------------------------------
 template <bool NEG, bool TRI>
-__device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double* __restrict__ As,
-                                           const double* __restrict__ Bs) {
+__device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double* As,
+                                           const double* Bs) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
   const int lr = lane >> 2, lc = lane & 3;
@@ -199,12 +212,16 @@ __device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double*
     }                                                                   \
   }
 
+// NOTE: none of the shared-memory pointers below may be __restrict__: they carry data BETWEEN threads across barriers
+// (a restrict-qualified `sfail` let the compiler keep the first half's value in a register across __syncthreads(); the
+// warp that wrote the failure then returned alone and the CTA dead-locked on its next barrier).
 // Factor the 64 x 64 diagonal block held in `blk` ([c*SLD + r], lower part meaningful) and build the packet
 // M[m*SLD + j] = (L^-1)[j][m] in `Minv`.  LT (transposed factor, [c*LTS + r]) lives in `LT`.  Returns 0 or the 1-based
 // index of the failing pivot.  All CTHREADS threads call.
-__device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* __restrict__ LT,
-                                             double* __restrict__ Minv, double* __restrict__ colbuf,
-                                             double* __restrict__ rd, int* __restrict__ sfail) {
+__device__ __forceinline__ int factor_diag64(double* blk, double* LT,
+                                             double* Minv, double* colbuf,
+                                             double* rd, volatile int* sfail, const CoopParams& P,
+                                             int tbase) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * LTS + NB; e += CTHREADS) LT[e] = 0.0;
   for (int e = tid; e < 256; e += CTHREADS) colbuf[e] = 0.0;
@@ -218,6 +235,7 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
     if (lane == 0) *sfail = f;
   }
   __syncthreads();
+  trace_mark(P, tbase + 1);
   if (*sfail) return *sfail;
   if (warp == 0) {
     // L21 = A21 L11^-T: lane r solves row 32 + r
@@ -236,6 +254,7 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
     solve_steps_rot<32, 32, 4, true>(x, LT, rd, 0, [&](int k, double v) { Minv[lane * SLD + k] = v; });
   }
   __syncthreads();
+  trace_mark(P, tbase + 2);
   {
     // A22 -= L21 L21^T: warp w owns columns 2w, 2w+1; lane r row 32 + r
     double acc[2];
@@ -267,6 +286,7 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
     }
   }
   __syncthreads();
+  trace_mark(P, tbase + 3);
   if (*sfail) return *sfail;
   if (warp == 1) {
     double x[32];
@@ -291,6 +311,7 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
     for (int u = 0; u < 2; ++u) Minv[(warp + 16 * u) * SLD + 32 + lane] = z[u];
   }
   __syncthreads();
+  trace_mark(P, tbase + 4);
   return 0;
 }
 
@@ -298,7 +319,7 @@ __device__ __forceinline__ int factor_diag64(double* __restrict__ blk, double* _
 // Panel chain of row block r (64 rows) of the panel [p0, p0 + pw).
 // --------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopParams& P, double* buf, uint64_t* pbar,
-                                           uint32_t& pphase, double* colbuf, double* rd, int* sfail, int* sflag) {
+                                           uint32_t& pphase, double* colbuf, double* rd, volatile int* sfail, volatile int* sflag) {
   const int tid = threadIdx.x;
   const int r = blockIdx.x;
   const int nkk = (P.pw + NB - 1) / NB;
@@ -314,6 +335,7 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
     __syncthreads();
     return ok;
   };
+  trace_mark(P, 1);
   if (P.p0 > 0) {
     const int ti = r >> 1;
     const int expect = (ti == 0) ? min(nkk, 2) : nkk;
@@ -324,8 +346,10 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
     mbar_expect_tx(pbar, static_cast<uint32_t>((jmax + 1) * BLK * sizeof(double)));
     for (int j = 0; j <= jmax; ++j) tma_load_2d(buf + j * BLK, mapBlk, rows0, P.p0 + NB * j, pbar);
   }
+  trace_mark(P, 2);
   mbar_wait_spin(pbar, pphase);
   pphase ^= 1;
+  trace_mark(P, 3);
   double* stageM = buf + 4 * BLK;
   double* stageL = buf + 5 * BLK;
   for (int kk = 0; kk < nkk; ++kk) {
@@ -338,7 +362,8 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         for (int c = nb + tid; c < NB; c += CTHREADS) blkk[c * SLD + c] = 1.0;  // identity padding (rows are zero-filled)
       }
       __syncthreads();
-      const int failed = factor_diag64(blkk, stageM, stageL, colbuf, rd, sfail);
+      trace_mark(P, 32 + kk * 6 + 0);
+      const int failed = factor_diag64(blkk, stageM, stageL, colbuf, rd, sfail, P, 32 + kk * 6);
       if (failed) {
         if (tid == 0) {
           *P.flag = k0 + failed;
@@ -359,10 +384,13 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         fence_proxy_async();
         st_release(F + kk, 1);
       }
+      trace_mark(P, 32 + kk * 6 + 5);
       return;
     }
     // ---- X = A_rk L_kk^-T ----
+    trace_mark(P, 8 + kk * 6 + 0);
     if (!bcast_wait(F + kk, 1)) return;
+    trace_mark(P, 8 + kk * 6 + 1);
     if (tid == 0) {
       fence_proxy_async();
       mbar_expect_tx(pbar, BLK * sizeof(double));
@@ -370,6 +398,7 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
     }
     mbar_wait_spin(pbar, pphase);
     pphase ^= 1;
+    trace_mark(P, 8 + kk * 6 + 2);
     {
       double acc[2][2][2];
 #pragma unroll
@@ -389,6 +418,7 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         fence_proxy_async();
         st_release(X + r * 4 + kk, 1);
       }
+      trace_mark(P, 8 + kk * 6 + 3);
     }
     // ---- apply to the columns to the right (inside the panel) ----
     for (int jb = kk + 1; jb <= jmax; ++jb) {
@@ -410,8 +440,10 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
       tile64_mma<true, false>(acc, blkk, Bs);
       CMOE_FRAG_LOOP({ blkj[col * SLD + row] = acc[i][j][h]; })
       __syncthreads();  // stageL is reused by the next column block; blkj complete before it becomes an operand
+      trace_mark(P, 8 + kk * 6 + 4);
     }
   }
+  trace_mark(P, 60);
 }
 
 __global__ void __launch_bounds__(CTHREADS, 1)
@@ -425,6 +457,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   __shared__ double colbuf[256];
   __shared__ double rd[NB];
   __shared__ int s_tile, sfail, sflag;
+  trace_mark(P, 0);
   if (ld_volatile(P.flag) != 0) return;
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -480,6 +513,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
     }
     if (t == -2) continue;
     if (t >= total) break;
+    trace_mark(P, t < num_a ? 4 : 61);
     if (t < num_a) {
       int ti, tj;
       if (t < count0) {
@@ -493,6 +527,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
       __threadfence();
       __syncthreads();
       if (tid == 0) atomicAdd(rowready + ti, 1);
+      trace_mark(P, 5);
     } else {
       int rem = t - num_a, tj = 0;
       while (rem >= nbt - tj) {
@@ -502,7 +537,9 @@ __global__ void __launch_bounds__(CTHREADS, 1)
       const int ti = tj + rem;
       gemm_tile<128>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, tb0 + ti * TM, tb0 + tj * TM, q0);
     }
+    trace_mark(P, 6);
   }
+  trace_mark(P, 62);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
@@ -554,13 +591,49 @@ bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
   CMOE_CUDA(cudaMemsetAsync(sync.p, 0, sync.count * sizeof(int), s));
   CMOE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
   int* abort_flag = sync.p + static_cast<size_t>(npanels) * kSyncPerPanel;
+  // CMOE_CHOL_TRACE=<file>: %globaltimer stamps of thread 0 of every CTA at the role / step boundaries of every panel
+  const char* trace_path = std::getenv("CMOE_CHOL_TRACE");
+  DevBuf<unsigned long long> trace;
+  const size_t per_panel = static_cast<size_t>(sms) * kTraceSlots;
+  if (trace_path) {
+    trace.alloc(per_panel * npanels);
+    CMOE_CUDA(cudaMemsetAsync(trace.p, 0, trace.count * sizeof(unsigned long long), s));
+  }
   for (int p0 = 0, pi = 0; p0 < n; p0 += CW, ++pi) {
     CoopParams P{A, n, n, p0, std::min(CW, n - p0), flag, sync.p + static_cast<size_t>(pi) * kSyncPerPanel, scratch.p,
-                 abort_flag};
+                 abort_flag, trace_path ? trace.p + per_panel * pi : nullptr};
     void* args[] = {&mapOp, &mapBlk, &P};
     CMOE_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_step_kernel), dim3(sms), dim3(CTHREADS), args,
                                           kCoopSmem, s));
     count_launch();
+  }
+  if (trace_path) {
+    // watchdog: if the launches have not drained after 20 s, dump where every CTA is and keep waiting
+    cudaStream_t side;
+    CMOE_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    std::vector<unsigned long long> ht(trace.count);
+    bool done = false;
+    for (int it = 0; it < 2000 && !(done = cudaStreamQuery(s) == cudaSuccess); ++it) {
+      struct timespec ts = {0, 10 * 1000 * 1000};
+      nanosleep(&ts, nullptr);
+    }
+    CMOE_CUDA(cudaMemcpyAsync(ht.data(), trace.p, trace.count * sizeof(unsigned long long), cudaMemcpyDeviceToHost, side));
+    CMOE_CUDA(cudaStreamSynchronize(side));
+    cudaStreamDestroy(side);
+    if (FILE* f = std::fopen(trace_path, "w")) {
+      std::fprintf(f, "# n=%d done=%d; per panel and CTA: last checkpoint, then stamps (ns, relative to the CTA's slot 0)\n", n,
+                   done ? 1 : 0);
+      for (int pi = 0; pi < npanels; ++pi)
+        for (int c = 0; c < sms; ++c) {
+          const unsigned long long* t = ht.data() + per_panel * pi + static_cast<size_t>(c) * kTraceSlots;
+          if (t[0] == 0) continue;
+          std::fprintf(f, "p%d c%d last=%llu :", pi, c, t[kTraceSlots - 1]);
+          for (int k = 1; k < kTraceSlots - 1; ++k)
+            if (t[k]) std::fprintf(f, " %d:%lld[%llx]", k, static_cast<long long>(t[k] - t[0]), t[k]);
+          std::fprintf(f, "\n");
+        }
+      std::fclose(f);
+    }
   }
   int aborted = 0;
   CMOE_CUDA(cudaMemcpyAsync(&aborted, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -38,7 +38,7 @@ __device__ __forceinline__ bool wait_ge(const int* f, int target, int* abort_fla
 
 // In-place inversion of the lower-triangular 128 x 128 block M ([c*VB + r], r >= c meaningful, upper part ignored and
 // left untouched).  Rows / columns >= nb are treated as identity.  All CT threads call.
-__device__ __forceinline__ void invert_lower128(double* __restrict__ M) {
+__device__ __forceinline__ void invert_lower128(double* M) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // level 0: the four 32 x 32 diagonal blocks, warp w < 4, lane t = column t of the inverse
   if (warp < 4) {
@@ -155,7 +155,7 @@ __device__ __forceinline__ void load_tile(double (&v)[32], const double* __restr
 
 // adds the product into acc (per-thread partials; reduce with reduce_acc)
 template <bool TRANS>
-__device__ __forceinline__ void apply_tile(const double (&v)[32], const double* __restrict__ xs, double (&acc)[8]) {
+__device__ __forceinline__ void apply_tile(const double (&v)[32], const double* xs, double (&acc)[8]) {
   const int t = threadIdx.x;
   if (!TRANS) {
     const int q = t >> 7;
@@ -172,8 +172,8 @@ __device__ __forceinline__ void apply_tile(const double (&v)[32], const double* 
 
 // combine the per-thread partials into out[0..127] (shared memory, valid after the trailing barrier)
 template <bool TRANS>
-__device__ __forceinline__ void reduce_acc(const double (&acc)[8], double* __restrict__ part /* [4][VB] */,
-                                           double* __restrict__ out) {
+__device__ __forceinline__ void reduce_acc(const double (&acc)[8], double* part /* [4][VB] */,
+                                           double* out) {
   const int t = threadIdx.x;
   if (!TRANS) {
     const int r = t & (VB - 1), q = t >> 7;
