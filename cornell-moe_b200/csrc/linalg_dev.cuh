@@ -74,13 +74,34 @@ __device__ __forceinline__ int chol32_warp(double (&a)[32], int lane, double* co
   return fail;
 }
 
+// sqrt(p) and 1/sqrt(p) for a normal p > 0: hardware seed (MUFU.RSQ64H) + two coupled Goldschmidt steps: one MUFU and
+// five dependent FP64 operations (measured on B200: dependent DFMA 11 cycles, seed 13) instead of the library rsqrt
+// (66 cycles) plus a Newton correction (33) on the pivot chain.  Results within ~1 ulp.
+__device__ __forceinline__ void sqrt_rsqrt(double p, double& l, double& y) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(p));
+  double g = p * y0, h = 0.5 * y0;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  l = fma(g, r, g);
+  y = 2.0 * fma(h, r, h);
+}
+
 // Same factorisation, two columns per round: the 2 x 2 pivot block [l11 0; l21 l22] is formed from three shuffles, both
-// multiplier columns travel through ONE shared-memory round trip and the window is updated by a rank-2 step.  The
-// arithmetic (operation order and roundings) is exactly that of two successive rounds of chol32_warp<true>; only the
-// synchronisation per column is halved — the column recurrence is the latency-critical chain of the factorisation.
+// multiplier columns travel through ONE shared-memory round trip and the window is updated by a rank-2 step.
+// LEAN = false: the arithmetic (operation order and roundings) is exactly that of two successive rounds of
+// chol32_warp<true>.  LEAN = true (the cooperative large-n path): pivots through sqrt_rsqrt, multipliers as a * (1/l)
+// without the correction step — the column recurrence is the latency-critical chain of the whole factorisation
+// (measured per column, one warp alone on the SM: 324 cycles single-column, 270 paired, see microbench_chain.cu).
 // colbuf: [2][2][64] with [32..63] of every column zero.
+// prog (optional, shared memory): columns finished so far, for follower warps that trail the factorisation.  The
+// column data (LT, rd) and the counter are shared-memory stores of the same warp, issued in program order behind a
+// __syncwarp(); no fence is placed on the pivot chain (measured: a block fence by one lane costs ~70 cycles there).
+template <bool LEAN = false>
 __device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, double* colbuf,
-                                                double* LT, double* rd, int col0) {
+                                                double* LT, double* rd, int col0, volatile int* prog = nullptr) {
   int fail = 0;
 #pragma unroll 1
   for (int j = 0; j < 32; j += 2) {
@@ -89,41 +110,127 @@ __device__ __forceinline__ int chol32_warp_pair(double (&a)[32], int lane, doubl
     const double p22 = __shfl_sync(0xffffffffu, a[1], j + 1);
     fail = (fail == 0 && !(p11 > kPivotTol)) ? j + 1 : fail;
     if (fail) break;  // warp-uniform: nothing after a failed pivot is used; do not feed 0 / NaN to rsqrt
-    // column j
-    const double y1 = rsqrt(p11);
-    double l11 = p11 * y1;
-    l11 = fma(0.5 * y1, fma(-l11, l11, p11), l11);
-    double q1 = a[0] * y1;
-    q1 = fma(fma(-q1, l11, a[0]), y1, q1);
-    double l21 = p21 * y1;  // what lane j+1 computes as its q1 (same operations on the same operands)
-    l21 = fma(fma(-l21, l11, p21), y1, l21);
+    double y1, l11, q1, l21;
+    if (LEAN) {
+      sqrt_rsqrt(p11, l11, y1);
+      q1 = a[0] * y1;
+      l21 = p21 * y1;
+    } else {
+      y1 = rsqrt(p11);
+      l11 = p11 * y1;
+      l11 = fma(0.5 * y1, fma(-l11, l11, p11), l11);
+      q1 = a[0] * y1;
+      q1 = fma(fma(-q1, l11, a[0]), y1, q1);
+      l21 = p21 * y1;  // what lane j+1 computes as its q1 (same operations on the same operands)
+      l21 = fma(fma(-l21, l11, p21), y1, l21);
+    }
     // column j+1 after the update by column j
     const double d2 = fma(-l21, l21, p22);
     fail = (fail == 0 && !(d2 > kPivotTol)) ? j + 2 : fail;
     if (fail) break;
-    const double y2 = rsqrt(d2);
-    double l22 = d2 * y2;
-    l22 = fma(0.5 * y2, fma(-l22, l22, d2), l22);
     const double a1 = fma(-q1, l21, a[1]);
-    double q2 = a1 * y2;
-    q2 = fma(fma(-q2, l22, a1), y2, q2);
+    double y2, l22, q2;
+    if (LEAN) {
+      sqrt_rsqrt(d2, l22, y2);
+      q2 = a1 * y2;
+    } else {
+      y2 = rsqrt(d2);
+      l22 = d2 * y2;
+      l22 = fma(0.5 * y2, fma(-l22, l22, d2), l22);
+      q2 = a1 * y2;
+      q2 = fma(fma(-q2, l22, a1), y2, q2);
+    }
     const double lj1 = (lane == j) ? l11 : q1;
     const double lj2 = (lane == j + 1) ? l22 : q2;
     if (lane >= j) LT[(col0 + j) * LTS + col0 + lane] = lj1;
     if (lane >= j + 1) LT[(col0 + j + 1) * LTS + col0 + lane] = lj2;
-    if (lane == j) rd[col0 + j] = fma(fma(-l11, y1, 1.0), y1, y1);          // one Newton step on 1/l from y ~ 1/l
-    if (lane == j + 1) rd[col0 + j + 1] = fma(fma(-l22, y2, 1.0), y2, y2);
+    if (LEAN) {
+      if (lane == j) rd[col0 + j] = y1;
+      if (lane == j + 1) rd[col0 + j + 1] = y2;
+    } else {
+      if (lane == j) rd[col0 + j] = fma(fma(-l11, y1, 1.0), y1, y1);  // one Newton step on 1/l from y ~ 1/l
+      if (lane == j + 1) rd[col0 + j + 1] = fma(fma(-l22, y2, 1.0), y2, y2);
+    }
     double* c1 = colbuf + ((j >> 1) & 1) * 128;
     double* c2 = c1 + 64;
     c1[lane] = lj1;
     c2[lane] = lj2;
     __syncwarp();
+    if (prog && lane == 0) *prog = j + 2;
     // window slot k <-> column j + k
 #pragma unroll
     for (int k = 2; k < 32; ++k) a[k - 2] = fma(-lj2, c2[j + k], fma(-lj1, c1[j + k], a[k]));
     a[30] = 0.0;
     a[31] = 0.0;
   }
+  if (prog && fail && lane == 0) *prog = 1 << 20;  // release the followers (their results are discarded)
+  return fail;
+}
+
+// Software-pipelined form of the paired factorisation (lean pivots).  Measured: in chol32_warp_pair half of a round is
+// the ISSUE time of the 60 window FMAs + 60 shared-memory loads that sit, in program order, between one round's pivots
+// and the next round's shuffles (an in-order warp cannot start the next dependent chain before they have issued).
+// Here only the two window slots the next pivots need are updated right away; the rest of round j's rank-2 update is
+// carried as "pending" (multipliers in registers, columns in the other parity buffer) and executed inside round j+1,
+// in one branch-free basic block together with that round's dependent pivot chain, so the scheduler fills the chain's
+// latency gaps with it.  A failed pivot is recorded, not branched on (the raw RSQ64H seed has no slow path).
+__device__ __forceinline__ int chol32_warp_pipe(double (&a)[32], int lane, double* colbuf, double* LT, double* rd,
+                                                int col0, volatile int* prog = nullptr) {
+  int fail = 0;
+  double plj1 = 0.0, plj2 = 0.0;            // pending multipliers of the previous round (zero: nothing pending)
+  const double* pc1 = colbuf + 128;         // previous round's column buffers (start: zeros)
+  const double* pc2 = colbuf + 192;
+  double p11 = __shfl_sync(0xffffffffu, a[0], 0);
+  double p21 = __shfl_sync(0xffffffffu, a[0], 1);
+  double p22 = __shfl_sync(0xffffffffu, a[1], 1);
+#pragma unroll 1
+  for (int j = 0; j < 32; j += 2) {
+    // ---- pivot chain of columns j, j+1 (dependent) ----
+    fail = (fail == 0 && !(p11 > kPivotTol)) ? j + 1 : fail;
+    double y1, l11, y2, l22;
+    sqrt_rsqrt(p11, l11, y1);
+    const double q1 = a[0] * y1;
+    const double l21 = p21 * y1;
+    const double d2 = fma(-l21, l21, p22);
+    fail = (fail == 0 && !(d2 > kPivotTol)) ? j + 2 : fail;
+    sqrt_rsqrt(d2, l22, y2);
+    const double a1 = fma(-q1, l21, a[1]);
+    const double q2 = a1 * y2;
+    const double lj1 = (lane == j) ? l11 : q1;
+    const double lj2 = (lane == j + 1) ? l22 : q2;
+    // ---- pending rank-2 update of the previous round on slots 2..31 (independent of the chain above) ----
+#pragma unroll
+    for (int k = 2; k < 32; ++k) a[k] = fma(-plj2, pc2[j + k], fma(-plj1, pc1[j + k], a[k]));
+    // ---- publish the two columns ----
+    if (lane >= j) LT[(col0 + j) * LTS + col0 + lane] = lj1;
+    if (lane >= j + 1) LT[(col0 + j + 1) * LTS + col0 + lane] = lj2;
+    if (lane == j) rd[col0 + j] = y1;
+    if (lane == j + 1) rd[col0 + j + 1] = y2;
+    double* c1 = colbuf + ((j >> 1) & 1) * 128;
+    double* c2 = c1 + 64;
+    c1[lane] = lj1;
+    c2[lane] = lj2;
+    __syncwarp();
+    if (prog && lane == 0) *prog = j + 2;
+    // ---- the two slots the next pivots need, then their shuffles ----
+    const double n0 = fma(-lj2, c2[j + 2], fma(-lj1, c1[j + 2], a[2]));
+    const double n1 = fma(-lj2, c2[j + 3], fma(-lj1, c1[j + 3], a[3]));
+    p11 = __shfl_sync(0xffffffffu, n0, (j + 2) & 31);
+    p21 = __shfl_sync(0xffffffffu, n0, (j + 3) & 31);
+    p22 = __shfl_sync(0xffffffffu, n1, (j + 3) & 31);
+    // window: slot k <-> column j + 2 + k; slots 2.. still lack this round's update (done in the next round)
+    a[0] = n0;
+    a[1] = n1;
+#pragma unroll
+    for (int k = 4; k < 32; ++k) a[k - 2] = a[k];
+    a[30] = 0.0;
+    a[31] = 0.0;
+    plj1 = lj1;
+    plj2 = lj2;
+    pc1 = c1;
+    pc2 = c2;
+  }
+  if (prog && fail && lane == 0) *prog = 1 << 20;
   return fail;
 }
 

@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(kHgTx * kHgTy)
                                double* __restrict__ partial) {
   __shared__ double scratch[kHgTx * kHgTy / 32];
   const int dim = spec.dim, g = spec.g, bs = 1 + g, hd = dim + 1, n = N * bs;
-  const int j = blockIdx.x * kHgTx + threadIdx.x;  // row point (fast)
-  const int i = blockIdx.y * kHgTy + threadIdx.y;  // column point
+  // 1-D block (block_sum's warp bookkeeping assumes it): thread -> (row point fast, column point slow)
+  const int j = blockIdx.x * kHgTx + (threadIdx.x % kHgTx);  // row point (fast)
+  const int i = blockIdx.y * kHgTy + (threadIdx.x / kHgTx);  // column point
   double acc[CMOE_MAX_DIM + 1];
   for (int h = 0; h < hd; ++h) acc[h] = 0.0;
   if (i < N && j < N) {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kHgTx * kHgTy)
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   for (int h = 0; h < hd; ++h) {
     const double s = block_sum(acc[h], scratch);
-    if (threadIdx.x == 0 && threadIdx.y == 0) partial[static_cast<size_t>(cta) * hd + h] = 0.5 * s;
+    if (threadIdx.x == 0) partial[static_cast<size_t>(cta) * hd + h] = 0.5 * s;
     __syncthreads();
   }
 }
@@ -155,7 +156,7 @@ extern "C" int cmoe_grad_log_marginal_likelihood(int kernel, double alpha, const
     const dim3 grid((N + kHgTx - 1) / kHgTx, (N + kHgTy - 1) / kHgTy);
     const size_t nctas = static_cast<size_t>(grid.x) * grid.y;
     DevBuf<double> partial(nctas * hd);
-    hyper_grad_contract_kernel<<<grid, dim3(kHgTx, kHgTy), 0, s>>>(gp->spec, gp->dX.p, N, gp->dKinvY.p, Kinv.p, partial.p);
+    hyper_grad_contract_kernel<<<grid, kHgTx * kHgTy, 0, s>>>(gp->spec, gp->dX.p, N, gp->dKinvY.p, Kinv.p, partial.p);
     hyper_grad_diag_kernel<<<(n + 255) / 256, 256, 0, s>>>(gp->dKinvY.p, Kinv.p, n, diagW.p);
     count_launch(2);
     CMOE_CUDA(cudaGetLastError());

@@ -175,27 +175,50 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring
 // k > c), so the K loop of a warp stops at its last column.
 // --------------------------------------------------------------------------------------------------------------
 template <bool NEG, bool TRI>
-__device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double* As,
-                                           const double* Bs) {
+__device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double* As, const double* Bs,
+                                           bool lower_only = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
   const int lr = lane >> 2, lc = lane & 3;
   const int kend = TRI ? wn + 16 : NB;
-#pragma unroll 4
-  for (int kk = 0; kk < kend; kk += 4) {
-    double a[2], b[2];
+  if (lower_only && wn > wm) return;  // symmetric update of a diagonal block: only the lower triangle is ever read
+  // two independent accumulator sets (even / odd k-steps): the product is a chain of dependent DMMAs per accumulator
+  // and this routine sits on the panel's critical path — half the chain, summed at the end
+  double acc2[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc2[i][j][0] = acc2[i][j][1] = 0.0;
+#pragma unroll 2
+  for (int kk = 0; kk < kend; kk += 8) {
+    double a[2], b[2], a2[2], b2[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const double v = As[(kk + lc) * SLD + wm + i * 8 + lr];
+      const double v2 = As[(kk + 4 + lc) * SLD + wm + i * 8 + lr];
       a[i] = NEG ? -v : v;
+      a2[i] = NEG ? -v2 : v2;
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) b[j] = Bs[(kk + lc) * SLD + wn + j * 8 + lr];
+    for (int j = 0; j < 2; ++j) {
+      b[j] = Bs[(kk + lc) * SLD + wn + j * 8 + lr];
+      b2[j] = Bs[(kk + 4 + lc) * SLD + wn + j * 8 + lr];
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      for (int j = 0; j < 2; ++j) {
+        dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        dmma_m8n8k4(acc2[i][j][0], acc2[i][j][1], a2[i], b2[j]);
+      }
   }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      acc[i][j][0] += acc2[i][j][0];
+      acc[i][j][1] += acc2[i][j][1];
+    }
 }
 
 // fragment <-> block coordinates of tile64_mma
@@ -215,96 +238,112 @@ __device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double*
 // NOTE: none of the shared-memory pointers below may be __restrict__: they carry data BETWEEN threads across barriers
 // (a restrict-qualified `sfail` let the compiler keep the first half's value in a register across __syncthreads(); the
 // warp that wrote the failure then returned alone and the CTA dead-locked on its next barrier).
+
+// A follower: x <- x L^-T over the 32 columns [cbase, cbase + 32) of the factor under construction, four columns at a
+// time as they are announced by chol32_warp_pair.
+template <typename Emit>
+__device__ __forceinline__ void solve_follow(double (&x)[32], double* LT, double* rd, int cbase, volatile int* prog,
+                                             Emit&& emit) {
+#pragma unroll 1
+  for (int kb = 0; kb < 32; kb += 4) {
+    while (*prog < kb + 4) __nanosleep(64);  // a tight poll would queue shared-memory loads in front of the factoring warp's
+    __threadfence_block();
+    solve_steps_rot<32, 4, 4, true>(x, LT, rd, cbase + kb, emit);
+  }
+}
+
 // Factor the 64 x 64 diagonal block held in `blk` ([c*SLD + r], lower part meaningful) and build the packet
 // M[m*SLD + j] = (L^-1)[j][m] in `Minv`.  LT (transposed factor, [c*LTS + r]) lives in `LT`.  Returns 0 or the 1-based
-// index of the failing pivot.  All CTHREADS threads call.
-__device__ __forceinline__ int factor_diag64(double* blk, double* LT,
-                                             double* Minv, double* colbuf,
-                                             double* rd, volatile int* sfail, const CoopParams& P,
-                                             int tbase) {
+// index of the failing pivot.  All CTHREADS threads call.  Warp 0 factors; warp 1 (inverse of the diagonal 32-blocks)
+// and warp 2 (rows 32..63 of the first half) trail it column by column.
+__device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Minv, double* cb, double* rd,
+                                             volatile int* sfail, volatile int* prog, const CoopParams& P, int tbase) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * LTS + NB; e += CTHREADS) LT[e] = 0.0;
-  for (int e = tid; e < 256; e += CTHREADS) colbuf[e] = 0.0;
+  for (int e = tid; e < 256; e += CTHREADS) cb[e] = 0.0;
   for (int e = tid; e < BLK; e += CTHREADS) Minv[e] = 0.0;
+  if (tid == 0) *prog = 0;
   __syncthreads();
   if (warp == 0) {
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[c * SLD + lane] : 0.0;
-    const int f = chol32_warp_pair(a, lane, colbuf, LT, rd, 0);
+    const int f = chol32_warp_pipe(a, lane, cb, LT, rd, 0, prog);
     if (lane == 0) *sfail = f;
-  }
-  __syncthreads();
-  trace_mark(P, tbase + 1);
-  if (*sfail) return *sfail;
-  if (warp == 0) {
-    // L21 = A21 L11^-T: lane r solves row 32 + r
-    double x[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) x[c] = blk[c * SLD + 32 + lane];
-    solve_steps_rot<32, 32, 4, true>(x, LT, rd, 0, [&](int k, double v) {
-      blk[k * SLD + 32 + lane] = v;
-      LT[k * LTS + 32 + lane] = v;
-    });
   } else if (warp == 1) {
     // column `lane` of L11^-1 = row `lane` of L11^-T: e_lane L11^-T
     double x[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
-    solve_steps_rot<32, 32, 4, true>(x, LT, rd, 0, [&](int k, double v) { Minv[lane * SLD + k] = v; });
+    solve_follow(x, LT, rd, 0, prog, [&](int k, double v) { Minv[lane * SLD + k] = v; });
+  } else if (warp == 2) {
+    // L21 = A21 L11^-T: lane r solves row 32 + r
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = blk[c * SLD + 32 + lane];
+    solve_follow(x, LT, rd, 0, prog, [&](int k, double v) {
+      blk[k * SLD + 32 + lane] = v;
+      LT[k * LTS + 32 + lane] = v;
+    });
   }
   __syncthreads();
-  trace_mark(P, tbase + 2);
+  trace_mark(P, tbase + 1);
+  if (*sfail) return *sfail;
   {
     // A22 -= L21 L21^T: warp w owns columns 2w, 2w+1; lane r row 32 + r
-    double acc[2];
+    double acc[2][4];  // four partial sums per output: the 32-term dot product is a dependent chain otherwise
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) acc[cc] = blk[(32 + warp * 2 + cc) * SLD + 32 + lane];
-#pragma unroll 8
+    for (int cc = 0; cc < 2; ++cc) {
+      acc[cc][0] = blk[(32 + warp * 2 + cc) * SLD + 32 + lane];
+      acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0;
+    }
+#pragma unroll
     for (int k = 0; k < 32; ++k) {
       const double xr = blk[k * SLD + 32 + lane];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) acc[cc] = fma(-xr, LT[k * LTS + 32 + warp * 2 + cc], acc[cc]);
+      for (int cc = 0; cc < 2; ++cc) acc[cc][k & 3] = fma(-xr, LT[k * LTS + 32 + warp * 2 + cc], acc[cc][k & 3]);
     }
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) blk[(32 + warp * 2 + cc) * SLD + 32 + lane] = acc[cc];
+    for (int cc = 0; cc < 2; ++cc)
+      blk[(32 + warp * 2 + cc) * SLD + 32 + lane] = (acc[cc][0] + acc[cc][1]) + (acc[cc][2] + acc[cc][3]);
+    if (tid == 0) *prog = 0;
   }
   __syncthreads();
+  trace_mark(P, tbase + 2);
   if (warp == 0) {
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[(32 + c) * SLD + 32 + lane] : 0.0;
-    const int f = chol32_warp_pair(a, lane, colbuf, LT, rd, 32);
+    const int f = chol32_warp_pipe(a, lane, cb, LT, rd, 32, prog);
     if (lane == 0) *sfail = f ? 32 + f : 0;
+  } else if (warp == 1) {
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
+    solve_follow(x, LT, rd, 32, prog, [&](int k, double v) { Minv[(32 + lane) * SLD + k] = v; });
   } else {
-    // Y = L21 * L11^-1 (32 x 32) while warp 0 factors A22: thread -> (i = lane, t); parked in the lower-left block
-    for (int t = warp - 1; t < 32; t += CTHREADS / 32 - 1) {
-      double y = 0.0;
-#pragma unroll 8
-      for (int m = 0; m < 32; ++m) y = fma(LT[m * LTS + 32 + lane], Minv[t * SLD + m], y);
-      Minv[t * SLD + 32 + lane] = y;
+    // Y = L21 * L11^-1 (32 x 32) meanwhile: thread -> (i = lane, t); parked in the lower-left block
+    for (int t = warp - 2; t < 32; t += CTHREADS / 32 - 2) {
+      double y[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int m = 0; m < 32; ++m) y[m & 3] = fma(LT[m * LTS + 32 + lane], Minv[t * SLD + m], y[m & 3]);
+      Minv[t * SLD + 32 + lane] = (y[0] + y[1]) + (y[2] + y[3]);
     }
   }
   __syncthreads();
   trace_mark(P, tbase + 3);
   if (*sfail) return *sfail;
-  if (warp == 1) {
-    double x[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
-    solve_steps_rot<32, 32, 4, true>(x, LT, rd, 32, [&](int k, double v) { Minv[(32 + lane) * SLD + k] = v; });
-  }
-  __syncthreads();
   {
     // Z = -L22^-1 * Y: Z[i][t] = -sum_{m <= i} Inv22[i][m] Y[m][t]; two (i, t) pairs per thread
     double z[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int t = warp + 16 * u;
-      double s = 0.0;
-#pragma unroll 8
-      for (int m = 0; m < 32; ++m) s = fma(Minv[(32 + m) * SLD + 32 + lane], Minv[t * SLD + 32 + m], s);
-      z[u] = -s;
+      double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int m = 0; m < 32; ++m)
+        sacc[m & 3] = fma(Minv[(32 + m) * SLD + 32 + lane], Minv[t * SLD + 32 + m], sacc[m & 3]);
+      z[u] = -((sacc[0] + sacc[1]) + (sacc[2] + sacc[3]));
     }
     __syncthreads();
 #pragma unroll
@@ -319,7 +358,8 @@ __device__ __forceinline__ int factor_diag64(double* blk, double* LT,
 // Panel chain of row block r (64 rows) of the panel [p0, p0 + pw).
 // --------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopParams& P, double* buf, uint64_t* pbar,
-                                           uint32_t& pphase, double* colbuf, double* rd, volatile int* sfail, volatile int* sflag) {
+                                           uint32_t& pphase, double* colbuf, double* rd, volatile int* sfail, volatile int* sflag,
+                                       volatile int* prog) {
   const int tid = threadIdx.x;
   const int r = blockIdx.x;
   const int nkk = (P.pw + NB - 1) / NB;
@@ -363,7 +403,7 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
       }
       __syncthreads();
       trace_mark(P, 32 + kk * 6 + 0);
-      const int failed = factor_diag64(blkk, stageM, stageL, colbuf, rd, sfail, P, 32 + kk * 6);
+      const int failed = factor_diag64(blkk, stageM, stageL, colbuf, rd, sfail, prog, P, 32 + kk * 6);
       if (failed) {
         if (tid == 0) {
           *P.flag = k0 + failed;
@@ -371,11 +411,7 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         }
         return;
       }
-      double* Ab = P.A + static_cast<size_t>(k0) * P.lda + k0;
-      for (int e = tid; e < NB * NB; e += CTHREADS) {
-        const int rr = e & (NB - 1), c = e >> 6;
-        if (rr >= c && rr < nb && c < nb) Ab[static_cast<size_t>(c) * P.lda + rr] = stageM[c * LTS + rr];
-      }
+      // publish the inverse first (the chain waits for it), the factor tile itself afterwards
       double* G = P.scratch + kk * BLK;
       for (int e = tid; e < BLK; e += CTHREADS) G[e] = stageL[e];
       __threadfence();
@@ -383,6 +419,11 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
       if (tid == 0) {
         fence_proxy_async();
         st_release(F + kk, 1);
+      }
+      double* Ab = P.A + static_cast<size_t>(k0) * P.lda + k0;
+      for (int e = tid; e < NB * NB; e += CTHREADS) {
+        const int rr = e & (NB - 1), c = e >> 6;
+        if (rr >= c && rr < nb && c < nb) Ab[static_cast<size_t>(c) * P.lda + rr] = stageM[c * LTS + rr];
       }
       trace_mark(P, 32 + kk * 6 + 5);
       return;
@@ -412,14 +453,25 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         blkk[col * SLD + row] = acc[i][j][h];
         if (rows0 + row < P.n && col < nb) Ag[static_cast<size_t>(col) * P.lda + row] = acc[i][j][h];
       })
-      if (r < nkk) __threadfence();
-      __syncthreads();
-      if (r < nkk && tid == 0) {
-        fence_proxy_async();
-        st_release(X + r * 4 + kk, 1);
-      }
+      __syncthreads();  // X (shared-memory copy) visible to every warp: it is an operand of the updates below
       trace_mark(P, 8 + kk * 6 + 3);
     }
+    // the X tiles of the rows inside the panel are operands of everybody's updates: publish them (stores are already in
+    // flight).  The CTA that factors next (r == kk + 1) first updates its own diagonal block, so the fence drains in
+    // the shadow of that product instead of on the chain.
+    bool published = !(r < nkk);
+    auto publish = [&]() {
+      if (!published) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          fence_proxy_async();
+          st_release(X + r * 4 + kk, 1);
+        }
+        published = true;
+      }
+    };
+    if (r != kk + 1) publish();
     // ---- apply to the columns to the right (inside the panel) ----
     for (int jb = kk + 1; jb <= jmax; ++jb) {
       const double* Bs = blkk;
@@ -437,11 +489,12 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
       double* blkj = buf + jb * BLK;
       double acc[2][2][2];
       CMOE_FRAG_LOOP({ acc[i][j][h] = blkj[col * SLD + row]; })
-      tile64_mma<true, false>(acc, blkk, Bs);
+      tile64_mma<true, false>(acc, blkk, Bs, jb == r);
       CMOE_FRAG_LOOP({ blkj[col * SLD + row] = acc[i][j][h]; })
       __syncthreads();  // stageL is reused by the next column block; blkj complete before it becomes an operand
       trace_mark(P, 8 + kk * 6 + 4);
     }
+    publish();
   }
   trace_mark(P, 60);
 }
@@ -456,7 +509,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   __shared__ __align__(8) uint64_t pbar;
   __shared__ double colbuf[256];
   __shared__ double rd[NB];
-  __shared__ int s_tile, sfail, sflag;
+  __shared__ int s_tile, sfail, sflag, prog;
   trace_mark(P, 0);
   if (ld_volatile(P.flag) != 0) return;
   const int tid = threadIdx.x;
@@ -490,28 +543,37 @@ __global__ void __launch_bounds__(CTHREADS, 1)
       total = num_a;
     }
   }
-  int* counter = P.sync;
+  // two tile counters: a CTA with pending panel work only ever claims (a) tiles — claiming a (b) tile before the chain
+  // would park that tile for the whole chain (seen in the trace: +40 us per panel)
+  int* counter_a = P.sync;
+  int* counter_b = P.sync + 21;
   int* rowready = P.sync + 32;
+  bool a_done = (num_a == 0);
   for (;;) {
     if (tid == 0) {
-      int t;
-      if (is_p && !p_done && ld_volatile(counter) >= num_a) {
-        t = -2;
-      } else {
-        t = atomicAdd(counter, 1);
+      int t = -2;
+      if (!a_done) {
+        t = atomicAdd(counter_a, 1);
+        if (t >= num_a) t = -3;  // (a) tiles exhausted
+      }
+      if (t < 0 && (!is_p || p_done)) {
+        t = num_a + atomicAdd(counter_b, 1);
       }
       s_tile = t;
     }
     __syncthreads();
     const int t = s_tile;
     __syncthreads();
-    if (t == -2 || (is_p && !p_done && t >= num_a)) {
-      // (a race can hand a (b) tile to a CTA whose panel work is still pending: the chain goes first)
-      panel_role(&mapBlk, P, buf, &pbar, pphase, colbuf, rd, &sfail, &sflag);
-      p_done = true;
-      __syncthreads();
+    if (t < 0) {
+      a_done = true;
+      if (is_p && !p_done) {
+        panel_role(&mapBlk, P, buf, &pbar, pphase, colbuf, rd, &sfail, &sflag, &prog);
+        p_done = true;
+        __syncthreads();
+      }
+      continue;
     }
-    if (t == -2) continue;
+    if (t >= num_a) a_done = true;
     if (t >= total) break;
     trace_mark(P, t < num_a ? 4 : 61);
     if (t < num_a) {

@@ -10,6 +10,9 @@
 //     four 32 x 32 register inversions, then the 64- and 128-level off-diagonal blocks), prefetches the tile of the
 //     LAST dependency into registers, and, once that x_j arrives, needs one 128 x 128 register product, the partial sums
 //     and one 128 x 128 product with the inverse: ~2 us per block on the critical path instead of ~13 us.
+// Hand-overs carry no flags: the solution vector and the helpers' partial sums start out as a sentinel bit pattern
+// (all ones — a NaN no arithmetic produces) and every consumer thread polls the very word it needs (L1-bypassing loads)
+// until it is a number.  One L2 round trip per hand-over instead of fence + flag store + flag poll + data load.
 // Fixed combination order (helper 0, 1, ..., then the owner's tile): results are bit-identical run to run.
 #include "device_math.cuh"
 #include "internal.cuh"
@@ -24,16 +27,23 @@ constexpr int kMaxHelpers = 3;
 
 __device__ __forceinline__ int ldv(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
-__device__ __forceinline__ bool wait_ge(const int* f, int target, int* abort_flag) {
-  for (unsigned spins = 0; ld_acquire(f) < target; ++spins) {
-    if ((spins & 63u) == 63u && ldv(abort_flag) != 0) return false;
+constexpr unsigned long long kSentinel = ~0ull;  // the host fills hand-over buffers with 0xFF bytes
+
+// spins until *p holds a number; false when the bound is hit or another CTA gave up (~1 s: far beyond any wait)
+__device__ __forceinline__ bool poll_value(const double* p, double& v, int* abort_flag) {
+  const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(p);
+  for (unsigned spins = 0;; ++spins) {
+    const unsigned long long bits = *q;
+    if (bits != kSentinel) {
+      v = __longlong_as_double(static_cast<long long>(bits));
+      return true;
+    }
+    if ((spins & 255u) == 255u && ldv(abort_flag) != 0) return false;
     if (spins > (1u << 23)) {
       atomicExch(abort_flag, 1);
       return false;
     }
-    __nanosleep(20);
   }
-  return true;
 }
 
 // In-place inversion of the lower-triangular 128 x 128 block M ([c*VB + r], r >= c meaningful, upper part ignored and
@@ -120,10 +130,8 @@ struct TrsvParams {
   const double* L;
   int n;
   const double* rhs;
-  double* x;         // out (distinct from rhs)
-  double* partial;   // [nblk][kMaxHelpers][VB]
-  int* ready;        // [nblk]   x_b published
-  int* part_ready;   // [nblk]   helpers that have delivered
+  double* x;         // out (distinct from rhs), sentinel until its block is solved
+  double* partial;   // [nblk][kMaxHelpers][VB], sentinel until a helper delivers
   int* abort_flag;
   int nblk, S;       // CTAs per block row (1 owner + S-1 helpers)
 };
@@ -198,7 +206,6 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
   __shared__ double part[4 * VB];
   __shared__ double sum[VB];
   __shared__ double vv[VB];
-  __shared__ int s_ok;
   const int t = threadIdx.x;
   const int S = P.S;
   const int slot = static_cast<int>(blockIdx.x) / S, role = static_cast<int>(blockIdx.x) % S;  // role 0 = owner
@@ -206,13 +213,14 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
   const int n = P.n, b0 = b * VB, nb = min(VB, n - b0);
   const int ndep = slot;                              // blocks this row depends on
   auto dep_block = [&](int k) { return TRANS ? (P.nblk - 1 - k) : k; };  // k-th dependency in publication order
-  auto wait_x = [&](int blk) -> bool {
-    if (t == 0) s_ok = wait_ge(P.ready + blk, 1, P.abort_flag) ? 1 : 0;
-    __syncthreads();
-    const bool ok = s_ok != 0;
-    if (ok && t < VB) xs[t] = (blk * VB + t < n) ? __ldcg(P.x + blk * VB + t) : 0.0;
-    __syncthreads();
-    return ok;
+  auto wait_x = [&](int blk) -> bool {  // block `blk` of the solution -> xs[], polled element-wise
+    bool ok = true;
+    if (t < VB) {
+      double val = 0.0;
+      if (blk * VB + t < n) ok = poll_value(P.x + blk * VB + t, val, P.abort_flag);
+      xs[t] = val;
+    }
+    return __syncthreads_and(ok ? 1 : 0) != 0;
   };
   double acc[8];
 #pragma unroll
@@ -230,9 +238,6 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
     }
     reduce_acc<TRANS>(acc, part, sum);
     if (t < VB) P.partial[(static_cast<size_t>(b) * kMaxHelpers + (role - 1)) * VB + t] = sum[t];
-    __threadfence();
-    __syncthreads();
-    if (t == 0) atomicAdd(P.part_ready + b, 1);
     return;
   }
 
@@ -257,17 +262,20 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
     apply_tile<TRANS>(v, xs, acc);
   }
   reduce_acc<TRANS>(acc, part, sum);
-  if (S > 1 && ndep > 1) {
-    const int helpers = S - 1;
-    if (t == 0) s_ok = wait_ge(P.part_ready + b, helpers, P.abort_flag) ? 1 : 0;
-    __syncthreads();
-    if (!s_ok) return;
-  }
-  if (t < VB) {
-    double tot = 0.0;
-    if (S > 1 && ndep > 1)
-      for (int h = 0; h < S - 1; ++h) tot += __ldcg(P.partial + (static_cast<size_t>(b) * kMaxHelpers + h) * VB + t);
-    vv[t] = my_rhs - (tot + sum[t]);
+  {
+    bool ok = true;
+    if (t < VB) {
+      double tot = 0.0;
+      if (S > 1 && ndep > 1) {
+        for (int h = 0; h < S - 1 && ok; ++h) {
+          double ph = 0.0;
+          ok = poll_value(P.partial + (static_cast<size_t>(b) * kMaxHelpers + h) * VB + t, ph, P.abort_flag);
+          tot += ph;
+        }
+      }
+      vv[t] = my_rhs - (tot + sum[t]);
+    }
+    if (!__syncthreads_and(ok ? 1 : 0)) return;
   }
   __syncthreads();
   // x_b = L_bb^-1 v (forward: sum over c <= r) or L_bb^-T v (backward: sum over r >= c)
@@ -291,10 +299,7 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
     }
   }
   reduce_acc<TRANS>(acc, part, sum);
-  if (t < nb) P.x[b0 + t] = sum[t];
-  __threadfence();
-  __syncthreads();
-  if (t == 0) st_release(P.ready + b, 1);
+  if (t < nb) P.x[b0 + t] = sum[t];  // the store IS the signal
 }
 
 }  // namespace
@@ -311,16 +316,18 @@ bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(VB) * VB * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(trsv_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CMOE_CUDA(cudaFuncSetAttribute(trsv_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  DevBuf<int> flags(2 * static_cast<size_t>(nblk) + 1);
+  DevBuf<int> flags(1);
   DevBuf<double> out(n), partial(static_cast<size_t>(nblk) * kMaxHelpers * VB);
-  CMOE_CUDA(cudaMemsetAsync(flags.p, 0, flags.count * sizeof(int), s));
-  TrsvParams P{L, n, x, out.p, partial.p, flags.p, flags.p + nblk, flags.p + 2 * nblk, nblk, S};
+  CMOE_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), s));
+  CMOE_CUDA(cudaMemsetAsync(out.p, 0xFF, static_cast<size_t>(n) * sizeof(double), s));                 // sentinel
+  CMOE_CUDA(cudaMemsetAsync(partial.p, 0xFF, partial.count * sizeof(double), s));
+  TrsvParams P{L, n, x, out.p, partial.p, flags.p, nblk, S};
   void* args[] = {&P};
   void* fn = trans ? reinterpret_cast<void*>(trsv_coop_kernel<true>) : reinterpret_cast<void*>(trsv_coop_kernel<false>);
   CMOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nblk * S), dim3(CT), args, smem, s));
   count_launch();
   int aborted = 0;
-  CMOE_CUDA(cudaMemcpyAsync(&aborted, flags.p + 2 * nblk, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaMemcpyAsync(&aborted, flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CMOE_CUDA(cudaStreamSynchronize(s));
   if (aborted) return false;
   CMOE_CUDA(cudaMemcpyAsync(x, out.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));

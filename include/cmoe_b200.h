@@ -322,6 +322,8 @@ int cmoe_bench_fp64_peaks(int device, double* tflops);
 /* tflops[0] = total FP64 TFLOP/s when every warp interleaves DFMA and DMMA 1:1 by flops (do the vector pipe and the
  * tensor sub-pipe overlap?). */
 int cmoe_bench_fp64_mixed(int device, double* tflops);
+/* latency microbenchmarks behind the Cholesky pivot chain: out[11] (cycles), see microbench_chain.cu */
+int cmoe_bench_chain_latencies(int device, double* out);
 /* In-place lower Cholesky of a host matrix through the device path (ComputeCholeskyFactorL, gpp_linear_algebra.cpp:109). */
 int cmoe_cholesky(int n, double* a, int device, int* info);
 /* Solve (L L^T) X = B for nrhs right-hand sides (CholeskyFactorLMatrixMatrixSolve, gpp_linear_algebra.hpp:247). */

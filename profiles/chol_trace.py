@@ -10,7 +10,7 @@ for line in open(sys.argv[1]):
         print(line.strip())
         continue
     p, c, last = int(m.group(1)), int(m.group(2)), int(m.group(3))
-    st = {int(k): int(v) for k, v in (tok.split(":") for tok in m.group(4).split())}
+    st = {int(k): int(v.split("[")[0]) for k, v in (tok.split(":") for tok in m.group(4).split())}
     rows[p][c] = (last, st)
 panels = [int(a) for a in sys.argv[2:]] or sorted(rows)[:3]
 for p in panels:
