@@ -346,6 +346,11 @@ class KGPlan:
         except Exception:
             pass
 
+    def set_stale_union(self, points):
+        """Reference-driver compatibility (cmoe_kg_plan_set_stale_union): the discretisation set keeps these q points."""
+        pts = _f64(points).reshape(self.q, self.dim) if points is not None else None
+        _check(lib().cmoe_kg_plan_set_stale_union(self.h, _d(pts)))
+
     def upload(self, candidates):
         cand = _f64(candidates).reshape(-1, self.q, self.dim)
         self.nc = cand.shape[0]
@@ -383,7 +388,8 @@ def _gd_args(gp, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_fi
 class MultistartOpts(ctypes.Structure):
     _fields_ = [("normals_table", ctypes.POINTER(ctypes.c_double)), ("table_len", ctypes.c_size_t),
                 ("devices", ctypes.POINTER(ctypes.c_int)), ("num_devices", ctypes.c_int),
-                ("domain_type", ctypes.c_int)]
+                ("domain_type", ctypes.c_int), ("fresh_discretisation", ctypes.c_int),
+                ("stale_union", ctypes.POINTER(ctypes.c_double))]
 
 
 TENSOR_PRODUCT, SIMPLEX = 0, 1
@@ -398,19 +404,24 @@ def limit_update(domain_type, bounds, mrc, x, upd):
     return upd
 
 
-def _multistart_opts(table, devices, domain_type=0):
+def _multistart_opts(table, devices, domain_type=0, fresh=False, stale=None):
     """(opts struct or None, keep-alive tuple) for cmoe_multistart_{kg,ei}_ex."""
-    if table is None and not devices and not domain_type:
+    if table is None and not devices and not domain_type and not fresh and stale is None:
         return None, ()
     t = _f64(table).ravel() if table is not None else None
     dv = _i32(devices) if devices else None
     o = MultistartOpts(_d(t) if t is not None else None, t.size if t is not None else 0,
-                       _i(dv) if dv is not None else None, dv.size if dv is not None else 0, int(domain_type))
-    return o, (t, dv)
+                       _i(dv) if dv is not None else None, dv.size if dv is not None else 0, int(domain_type),
+                       int(bool(fresh)), None)
+    st = None
+    if stale is not None:
+        st = _f64(stale).ravel()
+        o.stale_union = _d(st)
+    return o, (t, dv, st)
 
 
 def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
-                  num_fidelity=0, seed=0, table=None, devices=None):
+                  num_fidelity=0, seed=0, table=None, devices=None, fresh_discretisation=False, stale_union=None):
     """cmoe_multistart_kg(_ex): returns (best_point [q, dim], best_value, found_flag, start_values).
     table: normals replayed by every evaluation (NormalRNGSimulator semantics); devices: GPUs to shard the starts over."""
     starts = _f64(starts)
@@ -422,7 +433,7 @@ def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_boun
     bv = ctypes.c_double()
     found = ctypes.c_int()
     info = ctypes.c_int()
-    opts, keep = _multistart_opts(table, devices)
+    opts, keep = _multistart_opts(table, devices, 0, fresh_discretisation, stale_union)
     rc = lib().cmoe_multistart_kg_ex(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db), _d(ib),
                                      _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0], int(num_mc),
                                      ctypes.c_double(best_so_far), ctypes.c_uint64(seed),
@@ -456,7 +467,7 @@ def multistart_ei(gp, starts, Xp, num_mc, best_so_far, outer, domain_bounds, see
 
 
 def kg_gradient_descent(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds, discrete_pts,
-                        num_fidelity=0, seed=0):
+                        num_fidelity=0, seed=0, stale_union=None):
     starts = _f64(starts)
     ns, q, dim = starts.shape
     Xp = _f64(Xp).reshape(-1, dim) if Xp is not None and len(Xp) else np.zeros((0, dim))
@@ -464,10 +475,11 @@ def kg_gradient_descent(gp, starts, Xp, num_mc, best_so_far, outer, inner, domai
     vals = np.empty(ns)
     pts = np.empty((ns, q, dim))
     info = ctypes.c_int()
-    rc = lib().cmoe_kg_gradient_descent(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db),
-                                        _d(ib), _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0],
-                                        int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(vals),
-                                        _d(pts), ctypes.byref(info))
+    st = _f64(stale_union).ravel() if stale_union is not None else None
+    rc = lib().cmoe_kg_gradient_descent_ex(gp.h, int(num_fidelity), ctypes.byref(outer), ctypes.byref(inner), _d(db),
+                                           _d(ib), _d(disc), disc.shape[0], _d(starts), ns, q, _d(Xp), Xp.shape[0],
+                                           int(num_mc), ctypes.c_double(best_so_far), ctypes.c_uint64(seed), _d(st),
+                                           _d(vals), _d(pts), ctypes.byref(info))
     _check(rc, info.value)
     return vals, pts
 

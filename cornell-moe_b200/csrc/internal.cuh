@@ -47,6 +47,7 @@ template <class F>
 int guarded(int* info, F&& f) {
   try {
     if (info) *info = 0;
+    cudaGetLastError();  // a non-sticky error left behind by an earlier, unrelated call must not fail this one
     f();
     return CMOE_OK;
   } catch (const Error& e) {

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ Ke
                                                       const double* __restrict__ B, const double* __restrict__ P,
                                                       const double* __restrict__ D, double* __restrict__ Pk,
                                                       double* __restrict__ Xu, double* __restrict__ A,
-                                                      double* __restrict__ Afull) {
+                                                      double* __restrict__ Afull, const double* __restrict__ stale,
+                                                      int q) {
   const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, b1 = 1 + spec.g, n = N * b1, Q = U * b1;
   const bool se = spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL;
   const double lna = log(spec.alpha);
@@ -96,7 +97,11 @@ __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ Ke
     const int j = e / DIMP, d = e % DIMP;
     double v = 0.0;
     if (d < ps) {
-      v = (j < U) ? Pc[j * dim + d] : D[static_cast<size_t>(j - U) * dim + d];
+      // `stale`: the reference's multistart drivers reuse ONE state whose discretisation set keeps the q points it was
+      // constructed with (SetCurrentPoint does not refresh discretized_set,
+      // gpp_knowledge_gradient_optimization.cpp:233-243, 259-261) — those points stand in for the current ones here
+      v = (j < U) ? ((stale != nullptr && j < q) ? stale[j * dim + d] : Pc[j * dim + d])
+                  : D[static_cast<size_t>(j - U) * dim + d];
     } else if (d < dim) {
       v = 1.0;
     }
@@ -437,7 +442,7 @@ struct cmoe_kg_plan {
   double rmax_static = 0.0;   // max scaled norm of training / pending / discrete points (see kFastPathRadius)
   int chunk = 0;
   // static device data
-  DevBuf<double> dXt, dD, dKD, dMuD, dAlpha0, dTable, dXp, dCand;
+  DevBuf<double> dXt, dD, dKD, dMuD, dAlpha0, dTable, dXp, dCand, dStale;
   KgMcParams mcp{};
   // per-batch device scratch
   PosteriorBatch pb;
@@ -480,7 +485,8 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   CMOE_CUDA(cudaMemcpyAsync(pl.dFailAll.p + c0, pb.fail.p, nb * sizeof(int), cudaMemcpyDeviceToDevice, s));
 
   kg_pack_kernel<<<nb, 256, 0, s>>>(spec, N, U, pl.ps, pl.num_pts, DIMP, QP, pl.stride, pl.dXt.p, gp.dKinvY.p, pb.B.p, pb.P.p,
-                                    pl.dD.p, pl.dPk.p, pl.dXu.p, pl.dA.p, pl.dAfull.p);
+                                    pl.dD.p, pl.dPk.p, pl.dXu.p, pl.dA.p, pl.dAfull.p,
+                                    pl.dStale.count ? pl.dStale.p : nullptr, q);
   count_launch();
   // K(X, A_union) for all candidates of the batch (value rows only)
   build_mix_covariance(spec, gp.dX.p, N, pl.dAfull.p, nb * U, nullptr, 0, pl.dKAu.p, s);
@@ -756,6 +762,18 @@ int cmoe_kg_plan_set_table(cmoe_kg_plan* plan, const double* table, int table_le
     const int need = ((plan->num_mc + 1) / 2) * plan->Q;
     CMOE_REQUIRE(table_len >= need, CMOE_ERR_INVALID_VALUE, "All random numbers stored in the RNG have been used up!");
     plan->dTable.upload(table, table_len, plan->gp->stream);
+    CMOE_CUDA(cudaStreamSynchronize(plan->gp->stream));
+  });
+}
+
+int cmoe_kg_plan_set_stale_union(cmoe_kg_plan* plan, const double* points_to_sample) {
+  return guarded(nullptr, [&] {
+    require_device(plan->gp->device);
+    if (points_to_sample == nullptr) {
+      plan->dStale.release();
+      return;
+    }
+    plan->dStale.upload(points_to_sample, static_cast<size_t>(plan->q) * plan->gp->spec.dim, plan->gp->stream);
     CMOE_CUDA(cudaStreamSynchronize(plan->gp->stream));
   });
 }

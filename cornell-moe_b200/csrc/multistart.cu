@@ -229,11 +229,15 @@ struct KgEvaluator {
 void make_kg_evaluator(KgEvaluator& ev, const cmoe_gp* gp, int nf, const cmoe_gd_params* inner,
                        const double* inner_bounds, const double* discrete_pts, int num_pts, int max_value_cands,
                        int max_grad_cands, int q, const double* Xp, int p, int num_mc, double best_so_far,
-                       uint64_t seed) {
+                       uint64_t seed, const double* stale_union = nullptr) {
   KgEvaluator::check(cmoe_kg_plan_create(gp, nf, inner, inner_bounds, discrete_pts, num_pts, max_value_cands, q, Xp, p,
                                          num_mc, best_so_far, seed, 0, &ev.vplan));
   KgEvaluator::check(cmoe_kg_plan_create(gp, nf, inner, inner_bounds, discrete_pts, num_pts, max_grad_cands, q, Xp, p,
                                          num_mc, best_so_far, seed, 1, &ev.gplan));
+  if (stale_union) {
+    KgEvaluator::check(cmoe_kg_plan_set_stale_union(ev.vplan, stale_union));
+    KgEvaluator::check(cmoe_kg_plan_set_stale_union(ev.gplan, stale_union));
+  }
 }
 
 // analytic one-point EI and gradient (gpp_math.cpp:2196-2253) from device posterior quantities
@@ -533,8 +537,13 @@ int cmoe_multistart_kg_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_par
       sh.workers.emplace_back(new DeviceWorker());
       DeviceWorker& w = *sh.workers.back();
       w.gp = replica_on(gp, devs[d]);
+      // reference-driver behaviour: the discretisation set keeps the first start's points (cmoe_kg_plan_set_stale_union)
+      const double* stale = (opts && opts->fresh_discretisation) ? nullptr
+                            : (opts && opts->stale_union)        ? opts->stale_union
+                                                                 : starts;
       make_kg_evaluator(w.kg, w.gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, (num_starts + G - 1) / G,
-                        (std::min(kTopK, num_starts) + G - 1) / G, q, points_being_sampled, p, num_mc, best_so_far, seed);
+                        (std::min(kTopK, num_starts) + G - 1) / G, q, points_being_sampled, p, num_mc, best_so_far, seed,
+                        stale);
       if (opts && opts->normals_table) {
         KgEvaluator::check(cmoe_kg_plan_set_table(w.kg.vplan, opts->normals_table, static_cast<int>(opts->table_len)));
         KgEvaluator::check(cmoe_kg_plan_set_table(w.kg.gplan, opts->normals_table, static_cast<int>(opts->table_len)));
@@ -603,21 +612,32 @@ int cmoe_multistart_ei(const cmoe_gp* gp, const cmoe_gd_params* outer, const dou
                                best_so_far, seed, nullptr, start_values, best_point, best_value, found_flag, info);
 }
 
-int cmoe_kg_gradient_descent(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,
-                             const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
-                             const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
-                             const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
-                             double* values_out, double* points_out, int* info) {
+int cmoe_kg_gradient_descent_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,
+                                const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                                const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                                const double* points_being_sampled, int p, int num_mc, double best_so_far,
+                                uint64_t seed, const double* stale_union, double* values_out, double* points_out,
+                                int* info) {
   return guarded(info, [&] {
     CMOE_REQUIRE(num_starts >= 1, CMOE_ERR_BOUNDS, "num_multistarts must be > 1");
     require_device(gp->device);
     validate_bounds(domain_bounds, gp->spec.dim);
     KgEvaluator ev;
     make_kg_evaluator(ev, gp, num_fidelity, inner, inner_bounds, discrete_pts, num_pts, num_starts, num_starts, q,
-                      points_being_sampled, p, num_mc, best_so_far, seed);
+                      points_being_sampled, p, num_mc, best_so_far, seed, stale_union);
     BatchEval f = std::ref(ev);
     gradient_descent_batch(f, *outer, domain_bounds, q, gp->spec.dim, starts, num_starts, values_out, points_out);
   });
+}
+
+int cmoe_kg_gradient_descent(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,
+                             const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                             const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                             const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
+                             double* values_out, double* points_out, int* info) {
+  return cmoe_kg_gradient_descent_ex(gp, num_fidelity, outer, inner, domain_bounds, inner_bounds, discrete_pts, num_pts,
+                                     starts, num_starts, q, points_being_sampled, p, num_mc, best_so_far, seed, nullptr,
+                                     values_out, points_out, info);
 }
 
 int cmoe_ei_gradient_descent(const cmoe_gp* gp, const cmoe_gd_params* outer, const double* domain_bounds,

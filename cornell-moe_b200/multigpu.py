@@ -117,13 +117,26 @@ def multistart_kg(gp, starts, Xp, num_mc, best_so_far, outer, inner, domain_boun
     """multistart_knowledge_gradient_optimization sharded over the ranks of `group` (each rank passes its own `gp`)."""
     from . import capi
 
+    # the reference driver's state keeps the FIRST start's points in the inner optimiser's discretisation set
+    # (cmoe_kg_plan_set_stale_union); every rank uses the global first start so that the shards reproduce the one-process
+    # driver bit for bit
+    starts = np.asarray(starts, dtype=np.float64)
+    stale = starts[0]
+    rank, world = world_info(group)
+    share = max(1, -(-starts.shape[0] // world))
+    plan = capi.KGPlan(gp, num_mc, best_so_far, inner, inner_bounds, discrete_pts, share, starts.shape[1], Xp=Xp,
+                       num_fidelity=num_fidelity, seed=seed, want_grad=False)
+    plan.set_stale_union(stale)
+
     def evaluate(sub):
-        return gp.kg(sub, Xp, num_mc, best_so_far, inner, inner_bounds, discrete_pts, num_fidelity=num_fidelity,
-                     seed=seed)
+        plan.upload(sub)
+        plan.run()
+        plan.sync()
+        return plan.download()[0]
 
     def descend(sub):
         return capi.kg_gradient_descent(gp, sub, Xp, num_mc, best_so_far, outer, inner, domain_bounds, inner_bounds,
-                                        discrete_pts, num_fidelity=num_fidelity, seed=seed)
+                                        discrete_pts, num_fidelity=num_fidelity, seed=seed, stale_union=stale)
 
     return sharded_multistart(evaluate, descend, starts, -np.inf, device, group)
 

@@ -168,6 +168,12 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
 void cmoe_kg_plan_destroy(cmoe_kg_plan* plan);
 /* Optional table replay (NormalRNGSimulator semantics): ((num_mc+1)/2)*(q+p) normals; replaces the Philox stream. */
 int cmoe_kg_plan_set_table(cmoe_kg_plan* plan, const double* normals_table, int table_len);
+/* Reference-driver compatibility: the multistart drivers of the reference evaluate every start and every descent step
+ * through ONE KnowledgeGradientState per thread, constructed with the first start; SetCurrentPoint refreshes the GP
+ * quantities but NOT discretized_set (gpp_knowledge_gradient_optimization.cpp:233-243 vs :259-261), so the set the
+ * per-sample inner optimiser starts from keeps the FIRST start's q points instead of the current ones.  Passing those
+ * q points here ([q][dim]; NULL clears) makes a plan evaluate exactly that; cmoe_multistart_kg(_ex) does it itself. */
+int cmoe_kg_plan_set_stale_union(cmoe_kg_plan* plan, const double* points_to_sample);
 int cmoe_kg_plan_upload(cmoe_kg_plan* plan, const double* candidates, int num_candidates);
 int cmoe_kg_plan_run(cmoe_kg_plan* plan);
 int cmoe_kg_plan_sync(cmoe_kg_plan* plan, int* info);
@@ -213,6 +219,11 @@ typedef struct cmoe_multistart_opts {
   const int* devices;
   int num_devices;
   int domain_type; /* CMOE_DOMAIN_TENSOR_PRODUCT (0) or CMOE_DOMAIN_SIMPLEX (1): the outer optimiser's domain */
+  /* q-KG only.  0 (default): bug-compatible with the reference driver — the inner optimiser's discretisation set keeps
+   * the q points of `stale_union` (NULL = the first start), see cmoe_kg_plan_set_stale_union.  1: every evaluation uses
+   * its own current points (what a freshly constructed state, e.g. compute_knowledge_gradient, does). */
+  int fresh_discretisation;
+  const double* stale_union; /* [q][dim] or NULL */
 } cmoe_multistart_opts;
 /* DomainTypes, gpp_python_common.cpp:201-240.  CMOE_DOMAIN_SIMPLEX = unit simplex intersected with the box
  * (SimplexIntersectTensorProductDomain, gpp_domain.cpp:107-289): implemented for the q-EI drivers; q-KG needs the same
@@ -236,11 +247,19 @@ int cmoe_multistart_ei_ex(const cmoe_gp* gp, const cmoe_gd_params* outer, const 
 
 /* Restarted gradient descent from given starts only (the second half of the multistart drivers); used by the
  * multi-GPU host layer after the global top-20 has been agreed on.  values_out[num_starts], points_out[num_starts][q*dim]. */
+/* (cmoe_kg_gradient_descent_ex: same, `stale_union` ([q][dim] or NULL) as in cmoe_multistart_opts — the sharded host
+ * layer passes the global first start so that every rank reproduces the one-process driver.) */
 int cmoe_kg_gradient_descent(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,
                              const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
                              const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
                              const double* points_being_sampled, int p, int num_mc, double best_so_far, uint64_t seed,
                              double* values_out, double* points_out, int* info);
+int cmoe_kg_gradient_descent_ex(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_params* outer,
+                                const cmoe_gd_params* inner, const double* domain_bounds, const double* inner_bounds,
+                                const double* discrete_pts, int num_pts, const double* starts, int num_starts, int q,
+                                const double* points_being_sampled, int p, int num_mc, double best_so_far,
+                                uint64_t seed, const double* stale_union, double* values_out, double* points_out,
+                                int* info);
 int cmoe_ei_gradient_descent(const cmoe_gp* gp, const cmoe_gd_params* outer, const double* domain_bounds,
                              const double* starts, int num_starts, int q, const double* points_being_sampled, int p,
                              int num_mc, double best_so_far, uint64_t seed, double* values_out, double* points_out,

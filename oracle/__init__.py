@@ -139,6 +139,24 @@ class CpuGP:
         return res[0] if len(res) == 1 else tuple(res)
 
 
+    def kg_reused_state(self, Xfirst, Xq, Xp, num_mc, best_so_far, table, gd, inner_bounds, discrete_pts, num_fidelity=0,
+                        grad=False):
+        """q-KG at Xq through a state that was constructed with Xfirst (reference back end only): what one evaluation
+        inside the reference's multistart drivers computes — the inner optimiser's start set keeps Xfirst."""
+        Xq = _f64(Xq).reshape(-1, self.dim)
+        Xf = _f64(Xfirst).reshape(-1, self.dim)
+        Xp = _f64(Xp).reshape(-1, self.dim) if Xp is not None and len(Xp) else np.zeros((0, self.dim))
+        table = _f64(table).ravel()
+        discrete_pts = _f64(discrete_pts).reshape(-1, self.dim - num_fidelity)
+        g = np.empty(Xq.size) if grad else None
+        f = self.b._fn("kg_reused_state")
+        f.restype = ctypes.c_double
+        v = f(self.h, int(num_fidelity), _d(_f64(gd)), _d(_f64(inner_bounds).ravel()), _d(discrete_pts),
+              discrete_pts.shape[0], _d(Xf), _d(Xq), _d(Xp), Xq.shape[0], Xp.shape[0], int(num_mc),
+              ctypes.c_double(best_so_far), _d(table), table.size, _d(g))
+        return (v, g.reshape(Xq.shape)) if grad else v
+
+
 class CpuBackend:
     def __init__(self, path, prefix, name):
         self.lib = ctypes.CDLL(path)

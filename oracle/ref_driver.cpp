@@ -176,6 +176,27 @@ double ref_kg(void* h, int num_fidelity, const double* gd, const double* inner_b
   return v;
 }
 
+// q-KG through a REUSED state, as the multistart drivers evaluate it: the state is constructed with `Xfirst` and then
+// moved to `Xq` by SetCurrentPoint — which refreshes the GP quantities but not discretized_set
+// (gpp_knowledge_gradient_optimization.cpp:233-243 vs :259-261), so the inner optimiser's start set keeps Xfirst.
+double ref_kg_reused_state(void* h, int num_fidelity, const double* gd, const double* inner_bounds,
+                           const double* discrete_pts, int num_pts, const double* Xfirst, const double* Xq,
+                           const double* Xp, int q, int p, int num_mc, double best_so_far, const double* table,
+                           int table_len, double* grad) {
+  auto* gp = static_cast<GaussianProcess*>(h);
+  std::vector<double> tab(table, table + table_len);
+  NormalRNGSimulator rng(tab);
+  TensorProductDomain dom = MakeDomain(inner_bounds, gp->dim() - num_fidelity);
+  GradientDescentParameters inner = MakeGD(gd);
+  KnowledgeGradientEvaluator<TensorProductDomain> ev(*gp, num_fidelity, discrete_pts, num_pts, num_mc, dom, inner,
+                                                     best_so_far);
+  std::vector<int> derivs(gp->derivatives());
+  KnowledgeGradientEvaluator<TensorProductDomain>::StateType st(ev, Xfirst, Xp, q, p, num_mc, derivs.data(),
+                                                                gp->num_derivatives(), true, &rng);
+  st.SetCurrentPoint(ev, Xq);
+  return grad ? ev.ComputeGradKnowledgeGradient(&st, grad) : ev.ComputeKnowledgeGradient(&st);
+}
+
 // ---- the reference's own parallel path, for CPU baselines ----
 // EvaluateKGAtPointList (NullOptimizer + OpenMP static schedule), one NormalRNG per thread seeded seed+t.
 void ref_evaluate_kg_at_point_list(void* h, int num_fidelity, const double* gd, const double* bounds,

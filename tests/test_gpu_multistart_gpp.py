@@ -79,11 +79,20 @@ def test_multistart_kg_selects_strict_argmax_of_top20(capi):
     bp, bv, found, sv = capi.multistart_kg(gp, starts, None, mc, best, outer, EXAMPLE_INNER_GD, unit_bounds(2),
                                            unit_bounds(2), disc, seed=seed)
     assert found and np.isfinite(bv)
-    np.testing.assert_allclose(sv, gp.kg(starts, None, mc, best, EXAMPLE_INNER_GD, unit_bounds(2), disc, seed=seed), rtol=0, atol=0)
+    # the driver evaluates through the reference's reused state: the discretisation set keeps the FIRST start's points
+    plan = capi.KGPlan(gp, mc, best, EXAMPLE_INNER_GD, unit_bounds(2), disc, len(starts), q, seed=seed, want_grad=False)
+    plan.set_stale_union(starts[0])
+    plan.upload(starts)
+    plan.run()
+    plan.sync()
+    np.testing.assert_array_equal(sv, plan.download()[0])
+    fresh = capi.multistart_kg(gp, starts, None, mc, best, outer, EXAMPLE_INNER_GD, unit_bounds(2), unit_bounds(2), disc,
+                               seed=seed, fresh_discretisation=True)[3]
+    np.testing.assert_array_equal(fresh, gp.kg(starts, None, mc, best, EXAMPLE_INNER_GD, unit_bounds(2), disc, seed=seed))
     from cornell_moe_b200 import multigpu
     top = multigpu.top_k_indices(sv)
     vals, pts = capi.kg_gradient_descent(gp, starts[top], None, mc, best, outer, EXAMPLE_INNER_GD, unit_bounds(2),
-                                         unit_bounds(2), disc, seed=seed)
+                                         unit_bounds(2), disc, seed=seed, stale_union=starts[0])
     k = int(np.argmax(vals))  # numpy argmax = first maximiser = the strict-< update in slot order
     assert bv == vals[k]
     np.testing.assert_array_equal(bp, pts[k])

@@ -62,12 +62,17 @@ def test_multistart_kg_matches_reference_driver(capi, kernel):
     bp_ref, found_ref = orc.ref_multistart_kg(ref, starts, None, mc, best, outer1, EXAMPLE_INNER_GD, b3, b3, disc, seed)
     bp, bv, found, sv = capi.multistart_kg(gp, starts, None, mc, best, outer1, EXAMPLE_INNER_GD, b3, b3, disc, seed=1,
                                            table=table)
-    for i in (0, 7, 19, 39):  # the screening values the driver ranks the starts by
-        v = ref.kg(starts[i], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc)
+    for i in (0, 7, 19, 39):  # the screening values the driver ranks the starts by: ONE state, built with start 0
+        v = ref.kg_reused_state(starts[0], starts[i], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc)
         np.testing.assert_allclose(sv[i], v, rtol=1e-6, atol=1e-9)
+    # ... which is not what a freshly constructed state gives (the reference quirk the drivers reproduce)
+    fresh = capi.multistart_kg(gp, starts, None, mc, best, outer1, EXAMPLE_INNER_GD, b3, b3, disc, seed=1, table=table,
+                               fresh_discretisation=True)[3]
+    np.testing.assert_allclose(fresh[7], ref.kg(starts[7], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc), rtol=1e-6,
+                               atol=1e-9)
     assert found == found_ref
     np.testing.assert_allclose(bp, bp_ref, rtol=0, atol=1e-9)
-    v_ref = ref.kg(bp_ref, None, mc, best, table, EXAMPLE_INNER_GD, b3, disc)
+    v_ref = ref.kg_reused_state(starts[0], bp_ref, None, mc, best, table, EXAMPLE_INNER_GD, b3, disc)
     np.testing.assert_allclose(bv, v_ref, rtol=1e-7, atol=1e-10)
     # restarted descent, one start per driver call on both sides
     outer = [1, 3, 1, 0, 0.7, 0.4, 0.2, 1e-7]

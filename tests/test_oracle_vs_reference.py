@@ -352,3 +352,38 @@ def test_simplex_limit_update_host_logic():
         np.testing.assert_allclose(box, ref_box if ref_box is not None else box, rtol=1e-14, atol=0)
         hit_face += (x + box).sum() > 1.0 + 1e-9  # the box-limited step would leave the simplex: the face clip fires
     assert hit_face > 20
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="compiled reference not built")
+def test_reference_driver_state_reuse_quirk():
+    """KnowledgeGradientState::SetCurrentPoint does not refresh discretized_set (…optimization.cpp:233-243 vs :259-261):
+    an evaluation through a state constructed with other points differs from a fresh one, and the multistart driver —
+    which reuses one state built with the first start — ranks its starts by those values.  The device drivers
+    reproduce this (cmoe_kg_plan_set_stale_union); this pins the reference side of it."""
+    from synth import EXAMPLE_INNER_GD, make_problem, unit_bounds
+    ref = orc.load_reference()
+    prob = make_problem(30, 3, seed=3, noise=0.05)
+    gp, lm = ref.gp(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    rng = np.random.default_rng(4)
+    starts = rng.uniform(0.05, 0.95, size=(40, 2, 3))
+    disc = rng.uniform(size=(8, 3))
+    q, mc, seed = 2, 64, 4242
+    best = float(gp.mean_additional(disc).min())
+    b3 = unit_bounds(3)
+    table = orc.normal_draws(seed, (mc // 2) * q)
+    same = gp.kg_reused_state(starts[2], starts[2], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc)
+    assert same == gp.kg(starts[2], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc)
+    pick = [0, 5, 18, 34, 26, 25, 31]
+    reused = [gp.kg_reused_state(starts[0], starts[i], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc) for i in pick]
+    fresh = [gp.kg(starts[i], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc) for i in pick]
+    assert reused[0] == fresh[0]
+    assert any(abs(a - b) > 1e-6 for a, b in zip(reused[1:], fresh[1:]))
+    # one descent step from a single start: the driver's result is start + limited step computed with the start's own
+    # (then still fresh) state — and the final value is evaluated through the reused state
+    outer1 = [1, 1, 1, 0, 0.7, 0.4, 0.2, 1e-7]
+    bp, found = orc.ref_multistart_kg(gp, starts[3:4], None, mc, best, outer1, EXAMPLE_INNER_GD, b3, b3, disc, seed)
+    v, g = gp.kg(starts[3], None, mc, best, table, EXAMPLE_INNER_GD, b3, disc, grad=True)
+    step = 0.4 * g
+    for k in range(q):
+        step[k] = ref.limit_update(b3, 0.2, starts[3][k], step[k])
+    np.testing.assert_allclose(bp, starts[3] + step, rtol=0, atol=1e-14)
