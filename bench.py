@@ -31,6 +31,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the output is ONE JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

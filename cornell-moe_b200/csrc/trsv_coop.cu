@@ -253,30 +253,43 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
   invert_lower128(Minv);
   const double my_rhs = (t < VB && t < nb) ? P.rhs[b0 + t] : 0.0;
   // with helpers the owner only multiplies the tile of the LAST dependency (prefetched: it does not depend on x);
-  // without them (S == 1: more than #SMs / 2 block rows) it walks all dependencies itself
-#pragma unroll 1
-  for (int k = (S == 1) ? 0 : max(0, ndep - 1); k < ndep; ++k) {
-    const int j = dep_block(k), j0 = j * VB, jn = min(VB, n - j0);
+  // without them (S == 1: more than #SMs / 2 block rows) it walks all dependencies itself.  The helpers' partial sums
+  // depend on earlier blocks only: they are collected BEFORE the wait for the last x_j, off the chain.
+  const bool last_only = (S > 1);
+  if (ndep > 0 && last_only) {
+    const int j = dep_block(ndep - 1), j0 = j * VB, jn = min(VB, n - j0);
     load_tile<TRANS>(v, P.L, n, b0, nb, j0, jn);
-    if (!wait_x(j)) return;
-    apply_tile<TRANS>(v, xs, acc);
   }
-  reduce_acc<TRANS>(acc, part, sum);
+  double base = my_rhs;
   {
     bool ok = true;
-    if (t < VB) {
+    if (t < VB && S > 1 && ndep > 1) {
       double tot = 0.0;
-      if (S > 1 && ndep > 1) {
-        for (int h = 0; h < S - 1 && ok; ++h) {
-          double ph = 0.0;
-          ok = poll_value(P.partial + (static_cast<size_t>(b) * kMaxHelpers + h) * VB + t, ph, P.abort_flag);
-          tot += ph;
-        }
+      for (int h = 0; h < S - 1 && ok; ++h) {
+        double ph = 0.0;
+        ok = poll_value(P.partial + (static_cast<size_t>(b) * kMaxHelpers + h) * VB + t, ph, P.abort_flag);
+        tot += ph;
       }
-      vv[t] = my_rhs - (tot + sum[t]);
+      base = my_rhs - tot;
     }
     if (!__syncthreads_and(ok ? 1 : 0)) return;
   }
+  if (last_only) {
+    if (ndep > 0) {
+      if (!wait_x(dep_block(ndep - 1))) return;
+      apply_tile<TRANS>(v, xs, acc);
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < ndep; ++k) {
+      const int j = dep_block(k), j0 = j * VB, jn = min(VB, n - j0);
+      load_tile<TRANS>(v, P.L, n, b0, nb, j0, jn);
+      if (!wait_x(j)) return;
+      apply_tile<TRANS>(v, xs, acc);
+    }
+  }
+  reduce_acc<TRANS>(acc, part, sum);
+  if (t < VB) vv[t] = base - sum[t];
   __syncthreads();
   // x_b = L_bb^-1 v (forward: sum over c <= r) or L_bb^-T v (backward: sum over r >= c)
 #pragma unroll
@@ -316,11 +329,28 @@ bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(VB) * VB * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(trsv_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CMOE_CUDA(cudaFuncSetAttribute(trsv_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  DevBuf<int> flags(1);
-  DevBuf<double> out(n), partial(static_cast<size_t>(nblk) * kMaxHelpers * VB);
+  // workspace kept per host thread and device: cudaMalloc / cudaFree per call cost more than the solve itself
+  struct Workspace {
+    int device = -1;
+    DevBuf<int> flags;
+    DevBuf<double> out, partial;
+  };
+  static thread_local Workspace ws;
+  if (ws.device != dev) {
+    ws.flags.release();
+    ws.out.release();
+    ws.partial.release();
+    ws.device = dev;
+  }
+  if (ws.flags.count == 0) ws.flags.alloc(1);
+  ws.out.ensure(n);
+  ws.partial.ensure(static_cast<size_t>(nblk) * kMaxHelpers * VB);
+  DevBuf<int>& flags = ws.flags;
+  DevBuf<double>& out = ws.out;
+  DevBuf<double>& partial = ws.partial;
   CMOE_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), s));
   CMOE_CUDA(cudaMemsetAsync(out.p, 0xFF, static_cast<size_t>(n) * sizeof(double), s));                 // sentinel
-  CMOE_CUDA(cudaMemsetAsync(partial.p, 0xFF, partial.count * sizeof(double), s));
+  CMOE_CUDA(cudaMemsetAsync(partial.p, 0xFF, static_cast<size_t>(nblk) * kMaxHelpers * VB * sizeof(double), s));
   TrsvParams P{L, n, x, out.p, partial.p, flags.p, nblk, S};
   void* args[] = {&P};
   void* fn = trans ? reinterpret_cast<void*>(trsv_coop_kernel<true>) : reinterpret_cast<void*>(trsv_coop_kernel<false>);
@@ -331,7 +361,7 @@ bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s) {
   CMOE_CUDA(cudaStreamSynchronize(s));
   if (aborted) return false;
   CMOE_CUDA(cudaMemcpyAsync(x, out.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  CMOE_CUDA(cudaStreamSynchronize(s));  // scratch is freed on return
+  CMOE_CUDA(cudaStreamSynchronize(s));  // the cached workspace may be reused from another stream of this thread
   return true;
 }
 
