@@ -251,12 +251,19 @@ def fit_extra(capi, device, fp64_dmma, with_cpu):
     del gpl  # first fit of the process = kernel loading; the reported fit is the second one
     gpl = mk()
     t_cov = gpl.bench_cov_build(20)
+    capi.set_option("cov_tma", 1)  # the TMA / DMMA variant (tensor-map tile stores), off by default: slower at d = 10
+    try:
+        t_cov_tma = gpl.bench_cov_build(20)
+    finally:
+        capi.set_option("cov_tma", 0)
     t_chol = gpl.bench_cholesky(5)
     fit = [float(x) for x in gpl.fit_timings_usec()]
     cov_bytes = 4.0 * Nl * (Nl + 1) + 8.0 * Nl * dl
     out = {
         "cov_build_N5000_d10": {"bound": "hbm", "usec": t_cov, "achieved": cov_bytes / t_cov * 1e-3, "peak": hbm,
-                                "unit": "GB/s", "frac": cov_bytes / t_cov * 1e-3 / hbm, "peak_source": src},
+                                "unit": "GB/s", "frac": cov_bytes / t_cov * 1e-3 / hbm, "peak_source": src,
+                                "kernel": "cov_build_g0_kernel (LDGSTS, default)",
+                                "tma_variant_usec": t_cov_tma, "tma_variant_frac": cov_bytes / t_cov_tma * 1e-3 / hbm},
         "cholesky_N5000": {"bound": "tensor (FP64 DMMA)", "usec": t_chol, "achieved": Nl ** 3 / 3.0 / t_chol * 1e-6,
                            "peak": fp64_dmma, "unit": "TFLOP/s", "frac": Nl ** 3 / 3.0 / t_chol * 1e-6 / fp64_dmma,
                            "frac_of_nominal_40": Nl ** 3 / 3.0 / t_chol * 1e-6 / 40.0,

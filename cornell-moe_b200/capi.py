@@ -106,6 +106,11 @@ def _i(a):
     return None if a is None else a.ctypes.data_as(_ip)
 
 
+def set_option(name, value):
+    """cmoe_set_option: 'legacy_linalg' / 'cov_tma' (0 or 1)."""
+    _check(lib().cmoe_set_option(name.encode(), int(value)))
+
+
 def device_count():
     return lib().cmoe_device_count()
 

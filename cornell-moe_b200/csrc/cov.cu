@@ -368,7 +368,7 @@ __global__ void philox_table_kernel(uint64_t seed, uint64_t first_draw, int num_
 
 void build_covariance(const KernelSpec& spec, const double* X, const double* Xs, int N, const double* noise,
                       double* K, cudaStream_t s) {
-  if (!legacy_linalg() && spec.g == 0 && N >= 256 && (N & 1) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
+  if (cov_tma_enabled() && spec.g == 0 && N >= 256 && (N & 1) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(Xs) & 15) == 0) {
     CUtensorMap mapK;
     if (make_tensor_map_2d(&mapK, K, N, N, N, TR, TCW)) {

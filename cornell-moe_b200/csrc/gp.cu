@@ -351,6 +351,12 @@ void cmoe_gp_destroy(cmoe_gp* gp) {
   delete gp;
 }
 
+int cmoe_set_option(const char* name, int value) {
+  return guarded(nullptr, [&] {
+    CMOE_REQUIRE(set_option(name, value) == 0, CMOE_ERR_INVALID_VALUE, "unknown option name");
+  });
+}
+
 int cmoe_gp_dim(const cmoe_gp* gp) { return gp->spec.dim; }
 int cmoe_gp_device(const cmoe_gp* gp) { return gp->device; }
 int cmoe_gp_num_sampled(const cmoe_gp* gp) { return gp->N; }

@@ -11,6 +11,7 @@
 // Layout: column-major, only the lower triangle of the factor is defined (as in the reference).
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "device_math.cuh"
@@ -715,12 +716,36 @@ void trsv_blocked(const double* L, int n, double* x, bool trans, cudaStream_t s)
 }  // namespace
 
 int launches_issued() { return g_launches; }
-bool legacy_linalg() {
-  static const bool on = [] {
+// run-time switches (initialised from the environment, changeable through cmoe_set_option — the tests flip them to
+// cover both paths in one process)
+namespace {
+int& opt_legacy() {
+  static int v = [] {
     const char* e = std::getenv("CMOE_LEGACY_LINALG");
-    return e && e[0] == '1';
+    return (e && e[0] == '1') ? 1 : 0;
   }();
-  return on;
+  return v;
+}
+int& opt_cov_tma() {
+  static int v = [] {
+    const char* e = std::getenv("CMOE_COV_TMA");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  return v;
+}
+}  // namespace
+bool legacy_linalg() { return opt_legacy() != 0; }
+bool cov_tma_enabled() { return opt_cov_tma() != 0; }
+int set_option(const char* name, int value) {
+  const std::string n(name ? name : "");
+  if (n == "legacy_linalg") {
+    opt_legacy() = value ? 1 : 0;
+  } else if (n == "cov_tma") {
+    opt_cov_tma() = value ? 1 : 0;
+  } else {
+    return -1;
+  }
+  return 0;
 }
 void count_launch(int n) { g_launches += n; }
 

@@ -103,6 +103,10 @@ int cmoe_grad_log_marginal_likelihood(int kernel, double alpha, const double* le
                                       const double* points_sampled_value, const double* noise_variance,
                                       const int* derivatives, int num_derivatives, int dim, int num_sampled, int device,
                                       double* grad, int* info);
+/* Run-time switches between kernel generations (also read once from the environment: CMOE_LEGACY_LINALG, CMOE_COV_TMA):
+ *   "legacy_linalg" 1 = round-1 launch-per-step Cholesky / chained trsv for large n (default 0: cooperative kernels);
+ *   "cov_tma"       1 = TMA / DMMA covariance build with tensor-map tile stores (default 0: LDGSTS kernel, faster at d ~ 10). */
+int cmoe_set_option(const char* name, int value);
 void cmoe_gp_destroy(cmoe_gp* gp);
 int cmoe_gp_dim(const cmoe_gp* gp);
 int cmoe_gp_device(const cmoe_gp* gp);

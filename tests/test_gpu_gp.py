@@ -151,19 +151,44 @@ def test_gp_singular_on_tma_cov_path(capi, kernel):
     prob["noise"][:] = 0.0
     _, lm = checker().gp(kernel, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
     assert lm == 218
-    with pytest.raises(capi.SingularMatrixError) as e:
-        capi.GaussianProcess(kernel, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    capi.set_option("cov_tma", 1)
+    try:
+        with pytest.raises(capi.SingularMatrixError) as e:
+            capi.GaussianProcess(kernel, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+    finally:
+        capi.set_option("cov_tma", 0)
     assert e.value.info == lm
 
 
 def test_gp_cov_build_tma_matches_checker(capi):
     # K itself (not only its factor): a huge noise term keeps the factor's first column ~ K[:, 0] / sqrt(K00)
-    for N, dim in [(256, 3), (386, 10), (1000, 7)]:
+    for N, dim, tma in [(256, 3, 1), (386, 10, 1), (1000, 7, 1), (1000, 7, 0)]:
         prob = make_problem(N, dim, seed=N)
-        gp = capi.GaussianProcess(0, 1.7, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+        capi.set_option("cov_tma", tma)
+        try:
+            gp = capi.GaussianProcess(0, 1.7, prob["lengths"], prob["X"], prob["y"], prob["noise"])
+        finally:
+            capi.set_option("cov_tma", 0)
         ref, lm = checker().gp(0, 1.7, prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
         assert lm == 0
         tril_close(gp.state()[0], ref.state()[0], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("legacy,tma", [(1, 0), (0, 1)])
+def test_gp_large_fit_other_kernel_generations(capi, legacy, tma):
+    """The round-1 launch-per-step factorisation / chained solve and the TMA covariance build stay selectable at run
+    time (cmoe_set_option); both must give the same fit as the defaults to rounding."""
+    prob = make_problem(1500, 6, seed=15)
+    ref_fit = capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"]).state()
+    capi.set_option("legacy_linalg", legacy)
+    capi.set_option("cov_tma", tma)
+    try:
+        other = capi.GaussianProcess(0, 1.0, prob["lengths"], prob["X"], prob["y"], prob["noise"]).state()
+    finally:
+        capi.set_option("legacy_linalg", 0)
+        capi.set_option("cov_tma", 0)
+    tril_close(other[0], ref_fit[0], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(other[1], ref_fit[1], rtol=1e-6, atol=1e-7)
 
 
 def test_gp_large_fit_residual(capi):
