@@ -48,7 +48,8 @@ constexpr int SLD = NB + 4;            // leading dimension of slab / staging bl
 constexpr int BLK = SLD * NB;          // doubles per 64-column block buffer (34 816 B, a multiple of 128)
 constexpr int OPBOX = KC * OLD;        // doubles per operand box
 constexpr int NBUF = 6;                // 4 slab blocks + 2 staging buffers
-constexpr int kSyncPerPanel = 160;     // ints: [0] tile counter, [1..4] F, [5..20] X[j][kk], [32..] row-tile arrivals
+constexpr int kSyncPerPanel = 160;     // ints: [0] (a) counter, [1..4] F, [5..20] X[j][kk], [21] (b) counter, [22..25] arrivals of
+                                       // the diagonal block's 64 x 64 tiles, [32..] row-tile arrivals
 constexpr int kTraceSlots = 64;
 constexpr size_t kCoopSmem = static_cast<size_t>(NBUF) * BLK * sizeof(double) + 128;
 static_assert(STAGES * 2 * OPBOX <= NBUF * BLK, "operand ring must fit into the slab buffers");
@@ -96,14 +97,15 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
 // --------------------------------------------------------------------------------------------------------------
 // Trailing-update tile:  C(128 x TN) -= A[row0.., q0..q0+255] * A[col0.., q0..q0+255]^T
 // --------------------------------------------------------------------------------------------------------------
-template <int TN>
+template <int TMR, int TN>
 __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring, uint64_t* full, uint64_t* empty,
                                           uint32_t& gchunk, double* __restrict__ A, int lda, int n, int row0, int col0,
                                           int q0) {
-  constexpr int NF = TN / 32;  // 8-column fragments per warp
+  constexpr int MF = TMR / 32;  // 8-row fragments per warp (4 x 4 warps)
+  constexpr int NF = TN / 32;   // 8-column fragments per warp
   constexpr int NCH = CW / KC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * (TN / 4);
+  const int wm = (warp & 3) * (TMR / 4), wn = (warp >> 2) * (TN / 4);
   const int lr = lane >> 2, lc = lane & 3;
   const uint32_t g0 = gchunk;
   auto issue = [&](int c) {
@@ -119,10 +121,10 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring
     for (int c = 0; c < PREFETCH; ++c) issue(c);
   }
   // accumulators start as C: D = (-A) B + C, so the epilogue is a plain store
-  double acc[4][NF][2];
+  double acc[MF][NF][2];
   double* Cg = A + static_cast<size_t>(col0) * lda + row0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MF; ++i) {
     const int r = wm + i * 8 + lr;
 #pragma unroll
     for (int j = 0; j < NF; ++j)
@@ -142,13 +144,13 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring
     const double* bs = as + OPBOX;
 #pragma unroll
     for (int kk = 0; kk < KC; kk += 4) {
-      double a[4], b[NF];
+      double a[MF], b[NF];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = -as[(kk + lc) * OLD + wm + i * 8 + lr];
+      for (int i = 0; i < MF; ++i) a[i] = -as[(kk + lc) * OLD + wm + i * 8 + lr];
 #pragma unroll
       for (int j = 0; j < NF; ++j) b[j] = bs[(kk + lc) * OLD + wn + j * 8 + lr];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MF; ++i)
 #pragma unroll
         for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
@@ -157,7 +159,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring
   }
   gchunk = g0 + NCH;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MF; ++i) {
     const int r = wm + i * 8 + lr;
 #pragma unroll
     for (int j = 0; j < NF; ++j)
@@ -377,9 +379,10 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
   };
   trace_mark(P, 1);
   if (P.p0 > 0) {
-    const int ti = r >> 1;
-    const int expect = (ti == 0) ? min(nkk, 2) : nkk;
-    if (!bcast_wait(rowready + ti, expect)) return;
+    // rows of the diagonal block: their own 64 x 64 tiles; rows below: the 128 x 64 tiles of their row pair
+    const int* ready = (r < 4) ? P.sync + 22 + r : rowready + (r >> 1);
+    const int expect = (r < 4) ? min(r, nkk - 1) + 1 : nkk;
+    if (!bcast_wait(ready, expect)) return;
   }
   if (tid == 0) {
     fence_proxy_async();
@@ -528,14 +531,19 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   bool p_done = false;
   uint32_t gchunk = 0, pphase = 0;
   // trailing update with the previous panel
-  int num_a = 0, total = 0, nct_a = 0, count0 = 0, nbt = 0;
+  int num_a = 0, total = 0, nct_a = 0, nbt = 0;
   const int q0 = p0 - CW;
   const int tb0 = p0 + CW;  // origin of the (b) tile grid
+  // (a) tiles = update of panel p's own columns.  The rows of the panel's diagonal block (the first four 64-row blocks,
+  // whose CTAs carry the chain) are cut into 64 x 64 tiles that are handed out FIRST: the chain starts after ~half the
+  // time of a regular 128 x 64 tile.  Row block r needs its lower tiles (r, 0..min(r, nct_a-1)).
+  int num_small = 0, small_rows = 0;
   if (p0 > 0) {
     const int nrt = (n - p0 + TM - 1) / TM;
     nct_a = (P.pw + NB - 1) / NB;
-    count0 = min(nct_a, 2);
-    num_a = count0 + (nrt - 1) * nct_a;
+    small_rows = min(4, nrb);
+    for (int r = 0; r < small_rows; ++r) num_small += min(r, nct_a - 1) + 1;
+    num_a = num_small + max(0, nrt - 2) * nct_a;
     if (n > tb0) {
       nbt = (n - tb0 + TM - 1) / TM;
       total = num_a + nbt * (nbt + 1) / 2;
@@ -548,7 +556,9 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   int* counter_a = P.sync;
   int* counter_b = P.sync + 21;
   int* rowready = P.sync + 32;
-  bool a_done = (num_a == 0);
+  // the four chain CTAs never pick up (a) tiles: nothing may delay the start of the chain
+  bool a_done = (num_a == 0) || static_cast<int>(blockIdx.x) < small_rows;
+  int* small_ready = P.sync + 22;
   for (;;) {
     if (tid == 0) {
       int t = -2;
@@ -576,16 +586,20 @@ __global__ void __launch_bounds__(CTHREADS, 1)
     if (t >= num_a) a_done = true;
     if (t >= total) break;
     trace_mark(P, t < num_a ? 4 : 61);
-    if (t < num_a) {
-      int ti, tj;
-      if (t < count0) {
-        ti = 0;
-        tj = t;
-      } else {
-        ti = 1 + (t - count0) / nct_a;
-        tj = (t - count0) % nct_a;
+    if (t < num_small) {
+      int r = 0, rem = t;
+      while (rem >= min(r, nct_a - 1) + 1) {
+        rem -= min(r, nct_a - 1) + 1;
+        ++r;
       }
-      gemm_tile<64>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, p0 + ti * TM, p0 + tj * NB, q0);
+      gemm_tile<64, 64>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, p0 + r * NB, p0 + rem * NB, q0);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(small_ready + r, 1);
+      trace_mark(P, 5);
+    } else if (t < num_a) {
+      const int ti = 2 + (t - num_small) / nct_a, tj = (t - num_small) % nct_a;
+      gemm_tile<128, 64>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, p0 + ti * TM, p0 + tj * NB, q0);
       __threadfence();
       __syncthreads();
       if (tid == 0) atomicAdd(rowready + ti, 1);
@@ -597,7 +611,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
         ++tj;
       }
       const int ti = tj + rem;
-      gemm_tile<128>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, tb0 + ti * TM, tb0 + tj * TM, q0);
+      gemm_tile<128, 128>(&mapOp, buf, full, empty, gchunk, P.A, P.lda, n, tb0 + ti * TM, tb0 + tj * TM, q0);
     }
     trace_mark(P, 6);
   }
