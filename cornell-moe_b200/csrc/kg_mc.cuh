@@ -314,6 +314,105 @@ __device__ __forceinline__ void eval_line(const double* __restrict__ Xt, const d
   }
 }
 
+// Batched backtracking for the Matern-5/2 kernel.  No factorisation along the line here, but the trial points
+// x + a_k g share everything that depends on the training point only: with r0^2 = |x~ - X~_j|^2 and
+// p_j = g~ . (X~_j - x~),   |x~ + a g~ - X~_j|^2 = r0^2 - 2 a p_j + a^2 |g~|^2 ,
+// so the operand loads, the two dot products and the Q weight FMAs are paid once per step and each trial costs one
+// sqrt, one exp and a handful of FMAs, value only (a one-at-a-time trial also accumulates the DIM gradient sums it
+// almost never uses).  S[k] <-> a_k = a0 2^-k, k < KB.
+#ifndef CMOE_LINE_BATCH_M
+#define CMOE_LINE_BATCH_M 6
+#endif
+constexpr int kLineBatchM = CMOE_LINE_BATCH_M;
+static_assert(kLineBatchM <= kLineBatch, "S is sized for the SquareExponential batch");
+
+// sqrt(p) for a normal p > 0: MUFU.RSQ64H seed + two coupled Goldschmidt steps (seven FP64 operations, no special-case
+// branch; within ~1 ulp)
+__device__ __forceinline__ double sqrt_seeded(double p) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(p));
+  double g = p * y0, h = 0.5 * y0;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  return fma(g, r, g);
+}
+
+template <int DIM, int QP, bool SMEM>
+__device__ __forceinline__ void eval_line_matern(const double* __restrict__ Xt, const double* __restrict__ Pk,
+                                                 const double* __restrict__ Xu, int N, int U, double alpha,
+                                                 const double (&xb)[DIM], const double (&gt)[DIM],
+                                                 const double (&c)[QP], double a0, double (&S)[kLineBatch]) {
+  constexpr int KB = kLineBatchM;
+  double nq = 0.0, xg = 0.0, gg = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    nq = fma(xb[d], xb[d], nq);
+    xg = fma(xb[d], gt[d], xg);
+    gg = fma(gt[d], gt[d], gg);
+  }
+  const double hq = -0.5 * nq;
+  double m2a[KB], aag[KB];
+  {
+    double ak = a0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      m2a[k] = -2.0 * ak;
+      aag[k] = ak * ak * gg;
+      ak *= 0.5;
+      S[k] = 0.0;
+    }
+  }
+  auto trials = [&](double r2b, double pj, double w) {
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      // clamped away from 0 for the seed (Matern-5/2 is flat at r = 0: the value is unchanged to the last bit) and,
+      // on the table-exp path, from above so that the argument stays inside the table exp's range contract
+      const double r2 = fmax(1.0e-280, fma(m2a[k], pj, r2b) + aag[k]);
+      double ar = kSqrt5 * sqrt_seeded(r2);
+      if (SMEM) ar = fmin(ar, 1.0e6);
+      const double we = w * exp_sel<SMEM>(-ar);
+      S[k] = fma(we, fma(5.0 / 3.0, r2, 1.0 + ar), S[k]);
+    }
+  };
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    const double* xj = Xt + j * DIM;
+    const double* pk = Pk + j * (QP + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<SMEM>(xj + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    const double2 h = ld2<SMEM>(pk);  // (|X~_j|^2, beta_j)
+    const double dot = dot_dim<DIM>(xb, xv, 0.0);
+    const double pj = dot_dim<DIM>(gt, xv, -xg);
+    const double a = weight_row<QP, SMEM>(pk, h.y, c);
+    trials(fmax(0.0, h.x - 2.0 * (hq + dot)), pj, a * alpha);
+  }
+  for (int u = 0; u < U; ++u) {
+    const double* xu = Xu + u * (DIM + 2);
+    double xv[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d += 2) {
+      const double2 v = ld2<SMEM>(xu + d);
+      xv[d] = v.x;
+      xv[d + 1] = v.y;
+    }
+    const double2 h = ld2<SMEM>(xu + DIM);
+    const double dot = dot_dim<DIM>(xb, xv, 0.0);
+    const double pj = dot_dim<DIM>(gt, xv, -xg);
+    double cu = 0.0;
+#pragma unroll
+    for (int v = 0; v < QP; ++v)
+      if (v == u) cu = c[v];
+    trials(fmax(0.0, h.x - 2.0 * (hq + dot)), pj, cu * alpha);
+  }
+}
+
 // Kernel pieces for the general path: kv = k(x, X_j) (value row), kb = factor of the first-derivative rows,
 // kc = factor of d kb / d x  (SE: all three equal k; Matern-5/2: cov0, first_derivative_part, alpha_exp_part of
 // gpp_covariance.cpp:353-355).
@@ -599,7 +698,9 @@ template <int KERNEL, int DIM, int QP, bool SMEM, bool GEN>
 __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* __restrict__ Xt,
                                            const double* __restrict__ Pk, const double* __restrict__ Xu, int cand,
                                            int s_begin, int s_end, int* next_sample) {
-  constexpr bool LINE = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL);
+  constexpr bool SE = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL);
+  constexpr bool LINE = SE || !GEN;  // Matern-5/2 batches its trials too (eval_line_matern) unless derivative rows exist
+  constexpr int KB = SE ? kLineBatch : kLineBatchM;  // trial step sizes per LINE round
   constexpr int ST_SEARCH = LINE ? ST_LINE : ST_TRIAL;  // how a step's backtracking starts
   const int N = prm.N, U = prm.U;
   const double* A = prm.A + static_cast<size_t>(cand) * prm.M * DIM;
@@ -678,9 +779,12 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         gt[d] = gb[d] * prm.inv_len[d];
         gg = fma(gt[d], gt[d], gg);
       }
-      constexpr double kTop = static_cast<double>(1 << (kLineBatch - 1));
+      constexpr double kTop = static_cast<double>(1 << (KB - 1));
       double T[GEN ? kLineBatch : 1];
-      if (GEN) {
+      if (!SE) {
+        pmax_hi = 0;  // no factor can leave the double range on this path
+        eval_line_matern<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xt, gt, c, alpha_n, S);
+      } else if (GEN) {
         eval_line_gen<DIM, QP>(prm, Xt, Pk, Xu, xt, gt, c, cl, alpha_n * (1.0 / kTop), S,
                                reinterpret_cast<double (&)[kLineBatch]>(T), pmax_hi);
       } else {
@@ -698,9 +802,9 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
           int kacc = -1;
           double ak = alpha_n, a_acc = alpha_n;
 #pragma unroll
-          for (int k = 0; k < kLineBatch; ++k) {
+          for (int k = 0; k < KB; ++k) {
             const double sk = GEN ? fma(ak, T[GEN ? k : 0], S[k]) : S[k];
-            const double fq = -(prm.mean + exp_fast(-0.5 * ak * ak * gg) * sk);
+            const double fq = SE ? -(prm.mean + exp_fast(-0.5 * ak * ak * gg) * sk) : -(prm.mean + sk);
             // Armijo-type test of the reference: f(x + a g) - f(x) > 0.5 a |g|^2   (gpp_optimization.hpp:758)
             const bool ok = (search + k < 30) && ((fq - fb) > 0.5 * ak * gnorm);
             if (kacc < 0 && ok) {
@@ -715,8 +819,8 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
             alpha_n = a_acc;
             state = ST_LIMIT;  // value and gradient at the domain-limited point decide the step (:767-781)
           } else {
-            n_evals += min(kLineBatch, 30 - search);
-            search += kLineBatch;
+            n_evals += min(KB, 30 - search);
+            search += KB;
             alpha_n *= 1.0 / (2.0 * kTop);
             if (search >= 30) finish_run = true;  // exhausted: reject and stop this run (:778-781)
           }
