@@ -48,9 +48,10 @@ __global__ void pack_xt_kernel(const __grid_constant__ KernelSpec spec, const do
   Xt[e] = (d < spec.dim) ? X[static_cast<size_t>(j) * spec.dim + d] * spec.inv_len[d] : 0.0;
 }
 
-// per-candidate operand packs for the MC kernel.  Training point j owns rows (j, m), m = 0..g; the pack row is
-//   [ e_j | beta_(j,0), B_(j,0),0..QP-1 | beta~_(j,1), B~_(j,1),: | ... ]   (~ = divided by l_t, t = derivs[m-1])
-// so that derivative rows multiply plain scaled coordinate differences in the kernel.  stride = 1 + (1+g)(QP+1) (even).
+// per-candidate operand packs for the MC kernel.  g == 0: the pack row of training point j is [ e_j | beta_j, B_j,0..QP-1 ]
+// (stride QP + 2).  g > 0: training point j owns rows r = (j, m), m = 0..g; the pack row is [ e_j | 0 ] and the weights go
+// to the table Wt[1+QP][N(1+g)]: Wt[0][r] = beta~_r, Wt[1+u][r] = B~_(r,u)  (~ = divided by l_t, t = derivs[m-1], so
+// that derivative rows multiply plain scaled coordinate differences in the kernel).
 __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int ps,
                                                       int num_pts, int DIMP, int QP, int stride,
                                                       const double* __restrict__ Xt, const double* __restrict__ beta,
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ Ke
                                                       const double* __restrict__ D, double* __restrict__ Pk,
                                                       double* __restrict__ Xu, double* __restrict__ A,
                                                       double* __restrict__ Afull, const double* __restrict__ stale,
-                                                      int q) {
+                                                      int q, double* __restrict__ Wt) {
   const int c = blockIdx.x, tid = threadIdx.x, dim = spec.dim, b1 = 1 + spec.g, n = N * b1, Q = U * b1;
   const bool se = spec.kernel == CMOE_KERNEL_SQUARE_EXPONENTIAL;
   const double lna = log(spec.alpha);
@@ -69,13 +70,20 @@ __global__ void __launch_bounds__(256) kg_pack_kernel(const __grid_constant__ Ke
     for (int d = 0; d < DIMP; ++d) nrm = fma(Xt[j * DIMP + d], Xt[j * DIMP + d], nrm);
     double* o = pk + static_cast<size_t>(j) * stride;
     o[0] = se ? (lna - 0.5 * nrm) : nrm;
-    for (int m = 0; m < b1; ++m) {
-      const double sc = m ? spec.inv_len[spec.derivs[m - 1]] : 1.0;
-      double* row = o + 1 + m * (QP + 1);
-      row[0] = beta[j * b1 + m] * sc;
-      for (int u = 0; u < QP; ++u) row[1 + u] = (u < Q) ? Bc[static_cast<size_t>(u) * n + j * b1 + m] * sc : 0.0;
+    if (spec.g == 0) {
+      o[1] = beta[j];
+      for (int u = 0; u < QP; ++u) o[2 + u] = (u < Q) ? Bc[static_cast<size_t>(u) * n + j] : 0.0;
+    } else {
+      o[1] = 0.0;
     }
-    for (int e = 1 + b1 * (QP + 1); e < stride; ++e) o[e] = 0.0;
+  }
+  if (spec.g > 0) {
+    double* wt = Wt + static_cast<size_t>(c) * (1 + QP) * n;
+    for (int e = tid; e < (1 + QP) * n; e += blockDim.x) {
+      const int u = e / n - 1, r = e % n, m = r % b1;
+      const double sc = m ? spec.inv_len[spec.derivs[m - 1]] : 1.0;
+      wt[e] = (u < 0) ? beta[r] * sc : ((u < Q) ? Bc[static_cast<size_t>(u) * n + r] * sc : 0.0);
+    }
   }
   const double* Pc = P + static_cast<size_t>(c) * U * dim;
   double* xu = Xu + static_cast<size_t>(c) * U * (DIMP + 2);
@@ -274,57 +282,44 @@ __global__ void __launch_bounds__(256) kg_tprime_kernel(int n, int Q, int QP, co
   }
 }
 
-// General (derivative-observation) version of the phase-2 accumulation: one thread per row of [X rows ; Xu rows],
-//   R[a][row] = sum_i c_ia K(row, x*_i)      in fixed sample order.
-__global__ void __launch_bounds__(128) kg_acc_gen_kernel(const __grid_constant__ KernelSpec spec, int N, int U, int QP,
-                                                         int DIMP, int num_mc, const double* __restrict__ X,
-                                                         const double* __restrict__ P,
-                                                         const double* __restrict__ recC,
-                                                         const double* __restrict__ outX, double* __restrict__ R) {
-  const int cand = blockIdx.y, dim = spec.dim, b1 = 1 + spec.g, n = N * b1, Q = U * b1;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n + Q) return;
-  const bool is_u = row >= n;
-  const int pt = is_u ? (row - n) / b1 : row / b1;
-  const int ty = row_type(is_u ? (row - n) % b1 : row % b1, spec.derivs);
-  const double* xr = is_u ? (P + (static_cast<size_t>(cand) * U + pt) * dim) : (X + static_cast<size_t>(pt) * dim);
-  double acc[kMaxQ];
-  for (int a = 0; a < Q; ++a) acc[a] = 0.0;
-  const double* xs = outX + static_cast<size_t>(cand) * num_mc * DIMP;
-  const double* cs = recC + static_cast<size_t>(cand) * num_mc * QP;
-  for (int i = 0; i < num_mc; ++i) {
-    double xi[CMOE_MAX_DIM];
-    for (int d = 0; d < dim; ++d) xi[d] = xs[static_cast<size_t>(i) * DIMP + d] / spec.inv_len[d];
-    const KParts kp = kernel_parts(spec, weighted_sqdist(spec, xr, xi));
-    const double kval = cov_entry(spec, kp, xr, xi, ty, -1);
-    const double* ci = cs + static_cast<size_t>(i) * QP;
-    for (int a = 0; a < Q; ++a) acc[a] = fma(ci[a], kval, acc[a]);
-  }
-  double* Rc = R + static_cast<size_t>(cand) * QP * (n + Q);
-  for (int a = 0; a < Q; ++a) Rc[static_cast<size_t>(a) * (n + Q) + row] = acc[a];
-}
-
-// G1[p][d] = sum_i sum_m c_i,(p,m) d K(Xu_p row m, x*_i) / d Xu_p,d     (fixed sample order); grid nc, thread per (p, d)
-__global__ void __launch_bounds__(128) kg_g1_kernel(const __grid_constant__ KernelSpec spec, int U, int q, int QP,
+// G1[p][d] = sum_i sum_m c_i,(p,m) d K(Xu_p row m, x*_i) / d Xu_p,d ; grid nc.  Every output (p, d) is summed by
+// kG1Split threads over the samples i = t, t + kG1Split, ... and the partial sums are combined in a fixed order, so the
+// result does not depend on scheduling.
+constexpr int kG1Split = 16;
+__global__ void __launch_bounds__(256) kg_g1_kernel(const __grid_constant__ KernelSpec spec, int U, int q, int QP,
                                                     int DIMP, int num_mc, const double* __restrict__ P,
                                                     const double* __restrict__ recC, const double* __restrict__ outX,
                                                     double* __restrict__ G1) {
+  __shared__ double part[256];
   const int cand = blockIdx.x, dim = spec.dim, bs = 1 + spec.g;
   const double* xs = outX + static_cast<size_t>(cand) * num_mc * DIMP;
   const double* cs = recC + static_cast<size_t>(cand) * num_mc * QP;
-  for (int o = threadIdx.x; o < q * dim; o += blockDim.x) {
-    const int p = o / dim, d = o % dim;
-    const double* pp = P + (static_cast<size_t>(cand) * U + p) * dim;
+  double len[CMOE_MAX_DIM];
+  for (int e = 0; e < dim; ++e) len[e] = 1.0 / spec.inv_len[e];
+  const int outs_per_pass = blockDim.x / kG1Split;
+  for (int o0 = 0; o0 < q * dim; o0 += outs_per_pass) {
+    const int o = o0 + threadIdx.x / kG1Split, t = threadIdx.x % kG1Split;
     double acc = 0.0;
-    for (int i = 0; i < num_mc; ++i) {
-      double xi[CMOE_MAX_DIM];
-      for (int e = 0; e < dim; ++e) xi[e] = xs[static_cast<size_t>(i) * DIMP + e] / spec.inv_len[e];
-      const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pp, xi));
-      const double* ci = cs + static_cast<size_t>(i) * QP;
-      for (int m = 0; m < bs; ++m)
-        acc = fma(ci[p * bs + m], grad_cov_entry(spec, kp, pp, xi, row_type(m, spec.derivs), -1, d), acc);
+    if (o < q * dim) {
+      const int p = o / dim, d = o % dim;
+      const double* pp = P + (static_cast<size_t>(cand) * U + p) * dim;
+      for (int i = t; i < num_mc; i += kG1Split) {
+        double xi[CMOE_MAX_DIM];
+        for (int e = 0; e < dim; ++e) xi[e] = xs[static_cast<size_t>(i) * DIMP + e] * len[e];
+        const KParts kp = kernel_parts(spec, weighted_sqdist(spec, pp, xi));
+        const double* ci = cs + static_cast<size_t>(i) * QP;
+        for (int m = 0; m < bs; ++m)
+          acc = fma(ci[p * bs + m], grad_cov_entry(spec, kp, pp, xi, row_type(m, spec.derivs), -1, d), acc);
+      }
     }
-    G1[(static_cast<size_t>(cand) * q + p) * dim + d] = acc;
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (t == 0 && o < q * dim) {
+      double tot = 0.0;
+      for (int k = 0; k < kG1Split; ++k) tot += part[threadIdx.x + k];
+      G1[static_cast<size_t>(cand) * q * dim + o] = tot;
+    }
+    __syncthreads();
   }
 }
 
@@ -447,7 +442,9 @@ struct cmoe_kg_plan {
   // per-batch device scratch
   PosteriorBatch pb;
   DevBuf<double> dPk, dXu, dA, dAfull, dKAu, dW, dMuA, dBestPost, dRecC, dOutVal, dOutX, dOutH, dR, dGu, dGkB, dTp, dG1;
-  DevBuf<int> dWinner, dRecStart;
+  DevBuf<int> dWinner, dRecStart, dWork;
+  DevBuf<double> dWt, dAw;  // general path: weight table per candidate, per-lane weight columns per resident CTA
+  int aw_slots = 0;
   DevBuf<unsigned long long> dStats;
   // results
   DevBuf<double> dKG, dGrad;
@@ -486,7 +483,7 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
 
   kg_pack_kernel<<<nb, 256, 0, s>>>(spec, N, U, pl.ps, pl.num_pts, DIMP, QP, pl.stride, pl.dXt.p, gp.dKinvY.p, pb.B.p, pb.P.p,
                                     pl.dD.p, pl.dPk.p, pl.dXu.p, pl.dA.p, pl.dAfull.p,
-                                    pl.dStale.count ? pl.dStale.p : nullptr, q);
+                                    pl.dStale.count ? pl.dStale.p : nullptr, q, gen ? pl.dWt.p : nullptr);
   count_launch();
   // K(X, A_union) for all candidates of the batch (value rows only)
   build_mix_covariance(spec, gp.dX.p, N, pl.dAfull.p, nb * U, nullptr, 0, pl.dKAu.p, s);
@@ -517,6 +514,15 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
   prm.stats = pl.dStats.p;
   const int chunks = (mc + pl.chunk - 1) / pl.chunk;
   const size_t smem_mc = (!gen && pl.use_smem) ? pl.entry->smem_bytes(N, U) : 0;
+  if (gen) {
+    prm.Wt = pl.dWt.p;
+    prm.aw = pl.dAw.p;
+    prm.work = pl.dWork.p;
+    prm.aw_slots = pl.aw_slots;
+    prm.chunks = chunks;
+    prm.work_total = chunks * nb;
+    CMOE_CUDA(cudaMemsetAsync(pl.dWork.p, 0, sizeof(int), s));
+  }
   cudaEventRecord(pl.mc_events[ev_idx].first, s);
   if (gen) {
     pl.entry->mc_gen(prm, dim3(chunks, nb), 0, s);
@@ -546,9 +552,12 @@ void plan_run_batch(cmoe_kg_plan& pl, int c0, int nb, size_t ev_idx) {
     ap.GkB = pl.dGkB.p;
     CMOE_CUDA(cudaMemsetAsync(pl.dR.p, 0, static_cast<size_t>(nb) * QP * (n + Q) * sizeof(double), s));
     if (gen) {
-      kg_acc_gen_kernel<<<dim3((n + Q + 127) / 128, nb), 128, 0, s>>>(spec, N, U, QP, DIMP, mc, gp.dX.p, pb.P.p,
-                                                                     pl.dRecC.p, pl.dOutX.p, pl.dR.p);
-      kg_g1_kernel<<<nb, 128, 0, s>>>(spec, U, q, QP, DIMP, mc, pb.P.p, pl.dRecC.p, pl.dOutX.p, pl.dG1.p);
+      ap.g = spec.g;
+      for (int k = 0; k < 8; ++k) ap.derivs[k] = (k < spec.g) ? spec.derivs[k] : 0;
+      for (int d = 0; d < CMOE_MAX_DIM; ++d) ap.inv_len[d] = (d < dim) ? spec.inv_len[d] : 0.0;
+      ap.fast_exp = 0;
+      pl.entry->acc_gen(ap, dim3((n + Q + 127) / 128, nb), s);
+      kg_g1_kernel<<<nb, 256, 0, s>>>(spec, U, q, QP, DIMP, mc, pb.P.p, pl.dRecC.p, pl.dOutX.p, pl.dG1.p);
       count_launch();
     } else {
       pl.entry->acc(ap, dim3((N + U + 127) / 128, nb), s);
@@ -614,7 +623,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->DIMP = pl->entry->dim;
     pl->QP = pl->entry->qp;
     const int DIMP = pl->DIMP, QP = pl->QP, Q = pl->Q;
-    pl->stride = (1 + (1 + spec.g) * (QP + 1) + 1) / 2 * 2;
+    pl->stride = spec.g > 0 ? 2 : QP + 2;
     cudaStream_t s = gp->stream;
 
     // static data: scaled training points, discrete set (full dim, fidelity coords = 1), K(X, D), mu_n(D)
@@ -697,6 +706,15 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->dOutX.alloc(static_cast<size_t>(B) * num_mc * DIMP);
     pl->dOutH.alloc(static_cast<size_t>(B) * num_mc);
     pl->dStats.alloc(4);
+    if (spec.g > 0) {
+      // one scratch slot (N(1+g) rows x kMcThreads lanes) per resident CTA, at most 3 per SM and ~6 GiB in total
+      const size_t slot = static_cast<size_t>(n) * kMcThreads;
+      pl->aw_slots = static_cast<int>(std::max<size_t>(1, std::min<size_t>(3 * static_cast<size_t>(sms),
+                                                                            (size_t(6) << 30) / (slot * sizeof(double)))));
+      pl->dAw.alloc(slot * pl->aw_slots);
+      pl->dWt.alloc(static_cast<size_t>(B) * (1 + QP) * n);
+      pl->dWork.alloc(1);
+    }
     if (pl->want_grad) {
       pl->dR.alloc(static_cast<size_t>(B) * QP * (n + Q));
       pl->dGu.alloc(static_cast<size_t>(B) * U * DIMP);

@@ -16,6 +16,8 @@
 // kind of round, see kg_mc_body.
 #pragma once
 
+#include <algorithm>
+
 #include "device_math.cuh"
 #include "internal.cuh"
 
@@ -28,6 +30,14 @@ namespace cmoe {
 // union, discrete points, inner-domain corners) lies within kFastPathRadius of the origin; a query point farther than
 // kFarRadius is then at least kFarRadius - kFastPathRadius = 2000 length scales from every operand, so all its kernel
 // values are exactly 0 and the evaluation is short-circuited; any other query point has |t| <= 6000^2 / 2 = 1.8e7.
+#ifndef CMOE_MC_THREADS
+#define CMOE_MC_THREADS 128
+#endif
+#ifndef CMOE_MC_MINBLOCKS
+#define CMOE_MC_MINBLOCKS 3
+#endif
+constexpr int kMcThreads = CMOE_MC_THREADS;
+
 constexpr double kFastPathRadius = 2000.0;
 constexpr double kFarRadius = 4000.0;
 
@@ -57,12 +67,22 @@ struct KgMcParams {
   double* outX;          // [nc][num_mc][DIM] scaled minimiser
   double* outH;          // [nc][num_mc]      -|scaled minimiser|^2 / 2 (consumed by kg_acc_kernel)
   unsigned long long* stats;  // [4]: posterior evaluations, accepted steps, point rounds, line batches (per lane)
+  // general path (derivative observations): per-candidate weight table and the per-lane weight columns
+  const double* Wt;  // [nc][1 + QP][N * (1+g)]: row 0 = beta~, row 1+u = B~[:, u]  (~: derivative rows divided by l_t)
+  double* aw;        // [aw_slots][N * (1+g)][kMcThreads]: a = beta~ - B~ c of the sample each lane is working on
+  int* work;         // work-item counter of the persistent grid (zeroed before the launch)
+  int aw_slots;      // resident CTAs the scratch was sized for
+  int chunks;        // work items per candidate
+  int work_total;    // chunks * candidates of this launch
   double lo[CMOE_MAX_DIM], hi[CMOE_MAX_DIM], inv_len[CMOE_MAX_DIM], len[CMOE_MAX_DIM];
 };
 
 struct KgAccParams {
   int N, U, dim, num_mc;
   int fast_exp;  // 1: the range contract of the table exp holds (see kFastPathRadius)
+  int g;          // derivative observations per point (general path: rows = (N + U) * (1 + g))
+  int derivs[8];
+  double inv_len[CMOE_MAX_DIM];
   double alpha;
   const double* Xt;     // [N][DIM]
   const double* Xu;     // [nc][U][DIM+2]
@@ -434,6 +454,48 @@ __device__ __forceinline__ void kernel_triple(double dot, double pk0, double hq,
 }
 
 constexpr int kMaxG = 8;
+// points per trip of the general path's row loops: the loop body is one long dependent chain per point (weight loads
+// from L2/HBM, dot, exp), so independent points are interleaved to cover the latencies
+#ifndef CMOE_GEN_UNROLL
+#define CMOE_GEN_UNROLL 4
+#endif
+constexpr int kGenUnroll = CMOE_GEN_UNROLL;
+
+// Weight stream of the general path.  Each lane re-reads its weight column (N(1+g) doubles, global memory) on every
+// evaluation; a plain load loop leaves the warp waiting on L2/HBM for most of its time (ncu: 74 % of the issue
+// slots stalled on the long scoreboard with 8 warps per SM).  The column is therefore pulled through a per-lane ring in
+// shared memory with LDGSTS (cp.async, 8 bytes per lane = 256 bytes per warp and row), kRingDepth stages of `P` points
+// deep, and the arithmetic reads the ring.  Every lane copies and reads only its own slots, so cp.async.wait_group is
+// the only synchronisation.  body(j, w): w[m * kMcThreads] is weight m of point j.
+constexpr int kRingRows = 80;   // ring slots per lane (rows of the weight column)
+constexpr int kRingDepth = 8;   // stages in flight
+template <typename F>
+__device__ __forceinline__ void stream_point_weights(const double* aw, double* ring, int N, int b1, F&& body) {
+  constexpr int T = kMcThreads;
+  const int P = max(1, kRingRows / (kRingDepth * b1));  // points per stage
+  const int SR = P * b1, R = N * b1;
+  const int nst = (N + P - 1) / P;
+  auto issue = [&](int st) {
+    if (st < nst) {
+      const int r0 = st * SR;
+      const int cnt = min(SR, R - r0);
+      double* dst = ring + (st & (kRingDepth - 1)) * SR * T;
+      const double* src = aw + static_cast<size_t>(r0) * T;
+      for (int k = 0; k < cnt; ++k) cp_async8(dst + k * T, src + static_cast<size_t>(k) * T, true);
+    }
+    cp_async_commit();
+  };
+  for (int st = 0; st < kRingDepth - 1; ++st) issue(st);
+  for (int st = 0; st < nst; ++st) {
+    issue(st + kRingDepth - 1);  // refills the slot consumed in the previous trip
+    cp_async_wait<kRingDepth - 1>();
+    const double* w = ring + (st & (kRingDepth - 1)) * SR * T;
+    const int j1 = min(N, (st + 1) * P);
+#pragma unroll 2
+    for (int j = st * P; j < j1; ++j, w += b1 * T) body(j, w);
+  }
+  cp_async_wait<0>();
+}
 
 // General evaluation with derivative observations (d-KG): every training point owns 1+g rows
 //   K((j,0), x) = kv ,  K((j,m), x) = kb (x~_t - X~_jt) / l_t   (t = derivs[m-1]; the 1/l_t is folded into the pack)
@@ -443,7 +505,7 @@ constexpr int kMaxG = 8;
 template <int KERNEL, int DIM, int QP>
 __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const double* __restrict__ Xt,
                                                    const double* __restrict__ Pk, const double* __restrict__ Xu,
-                                                   const double (&xq)[DIM], const double (&c)[QP],
+                                                   const double (&xq)[DIM], const double* aw, double* ring,
                                                    const double* __restrict__ cl, double& S0, double& SB,
                                                    double (&s)[DIM], double (&em)[kMaxG]) {
   const int N = prm.N, U = prm.U, g = prm.g, stride = prm.pk_stride;
@@ -467,7 +529,7 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
   SB = 0.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) s[d] = 0.0;
-  for (int j = 0; j < N; ++j) {
+  stream_point_weights(aw, ring, N, 1 + g, [&](int j, const double* aj) {
     const double* xj = Xt + static_cast<size_t>(j) * DIM;
     const double* pk = Pk + static_cast<size_t>(j) * stride;
     double xv[DIM];
@@ -482,17 +544,12 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
     for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
     double kv, kb, kc;
     kernel_triple<KERNEL>(dot, __ldg(pk), hq, prm.alpha, kv, kb, kc);
-    double a0 = __ldg(pk + 1);
-#pragma unroll
-    for (int u = 0; u < QP; ++u) a0 = fma(-__ldg(pk + 2 + u), c[u], a0);
+    const double a0 = aj[0];  // this lane's weights of point j (ring slots)
     double wsum = 0.0;
 #pragma unroll
     for (int m = 0; m < kMaxG; ++m) {
       if (m < g) {
-        const double* row = pk + 1 + (m + 1) * (QP + 1);
-        double am = __ldg(row);
-#pragma unroll
-        for (int u = 0; u < QP; ++u) am = fma(-__ldg(row + 1 + u), c[u], am);
+        const double am = aj[(m + 1) * kMcThreads];
         wsum = fma(am, xm[m] - __ldg(xj + prm.derivs[m]), wsum);
         em[m] = fma(kb, am, em[m]);
       }
@@ -503,7 +560,7 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
     SB += wb;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) s[d] = fma(wb, xv[d], s[d]);
-  }
+  });
   const int bs = 1 + g;
   for (int u = 0; u < U; ++u) {
     const double* xu = Xu + static_cast<size_t>(u) * (DIM + 2);
@@ -546,8 +603,8 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
 template <int DIM, int QP>
 __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const double* __restrict__ Xt,
                                               const double* __restrict__ Pk, const double* __restrict__ Xu,
-                                              const double (&xb)[DIM], const double (&gt)[DIM], const double (&c)[QP],
-                                              const double* __restrict__ cl, double alpha_min,
+                                              const double (&xb)[DIM], const double (&gt)[DIM], const double* aw,
+                                              double* ring, const double* __restrict__ cl, double alpha_min,
                                               double (&S)[kLineBatch], double (&T)[kLineBatch], int& pmax_hi) {
   const int N = prm.N, U = prm.U, g = prm.g, stride = prm.pk_stride;
   double nq = 0.0, xg = 0.0;
@@ -579,7 +636,7 @@ __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const doubl
 #pragma unroll
   for (int k = 0; k < kLineBatch; ++k) S[k] = T[k] = 0.0;
   pmax_hi = 0;
-  for (int j = 0; j < N; ++j) {
+  stream_point_weights(aw, ring, N, 1 + g, [&](int j, const double* aj) {
     const double* xj = Xt + static_cast<size_t>(j) * DIM;
     const double* pk = Pk + static_cast<size_t>(j) * stride;
     double xv[DIM];
@@ -595,17 +652,12 @@ __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const doubl
       dot = fma(xb[d], xv[d], dot);
       pj = fma(ga[d], xv[d], pj);
     }
-    double a0 = __ldg(pk + 1);
-#pragma unroll
-    for (int u = 0; u < QP; ++u) a0 = fma(-__ldg(pk + 2 + u), c[u], a0);
+    const double a0 = aj[0];
     double us = 0.0, vs = 0.0;
 #pragma unroll
     for (int m = 0; m < kMaxG; ++m) {
       if (m < g) {
-        const double* row = pk + 1 + (m + 1) * (QP + 1);
-        double am = __ldg(row);
-#pragma unroll
-        for (int u = 0; u < QP; ++u) am = fma(-__ldg(row + 1 + u), c[u], am);
+        const double am = aj[(m + 1) * kMcThreads];
         us = fma(am, xm[m] - __ldg(xj + prm.derivs[m]), us);
         vs = fma(am, gm[m], vs);
       }
@@ -620,7 +672,7 @@ __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const doubl
       T[k] = fma(wv, G, T[k]);
       if (k > 0) G *= G;
     }
-  }
+  });
   const int bs = 1 + g;
   for (int u = 0; u < U; ++u) {
     const double* xu = Xu + static_cast<size_t>(u) * (DIM + 2);
@@ -677,15 +729,51 @@ __device__ __forceinline__ double limit_step(double step, double x, double lo, d
   return step;
 }
 
+// General path: the weights a = beta~ - B~ c depend on the sample only, not on the query point, so they are formed once
+// when a lane takes a new sample and parked in that lane's column of the CTA's scratch (global memory, streamed back
+// with L2-only loads by every evaluation of the sample: (1+g) loads per training point instead of (1+g)(Q+1) loads
+// and (1+g) Q FMAs).  The warp fills the column of each requesting lane together, rows strided over the lanes, so the
+// table reads are coalesced; the FMA order per row (beta first, then u ascending) is the one the per-evaluation code had.
+template <int QP>
+__device__ __forceinline__ void fill_sample_weights(const double* __restrict__ Wt, int R,
+                                                    const double* __restrict__ recC, double* aw_warp, unsigned want,
+                                                    int sample, int lane) {
+  while (want) {
+    const int b = __ffs(want) - 1;
+    want &= want - 1;
+    const int sb = __shfl_sync(0xffffffffu, sample, b);
+    double cb[QP];
+#pragma unroll
+    for (int u = 0; u < QP; ++u) cb[u] = __ldg(recC + static_cast<size_t>(sb) * QP + u);
+    double* col = aw_warp + b;
+#pragma unroll 4
+    for (int r = lane; r < R; r += 32) {
+      double a = __ldg(Wt + r);
+#pragma unroll
+      for (int u = 0; u < QP; ++u) a = fma(-__ldg(Wt + static_cast<size_t>(1 + u) * R + r), cb[u], a);
+      col[static_cast<size_t>(r) * kMcThreads] = a;
+    }
+  }
+  __syncwarp();
+}
+
+// The same column formed by its own lane (table loads are warp-uniform).  Costs R Q FMAs per lane however many lanes
+// take part, so it is used when at least kOwnFillLanes do; a lone lane is served by the whole warp instead.
+constexpr int kOwnFillLanes = 6;
+template <int QP>
+__device__ __forceinline__ void fill_own_weights(const double* __restrict__ Wt, int R, const double (&c)[QP],
+                                                 double* aw) {
+#pragma unroll 4
+  for (int r = 0; r < R; ++r) {
+    double a = __ldg(Wt + r);
+#pragma unroll
+    for (int u = 0; u < QP; ++u) a = fma(-__ldg(Wt + static_cast<size_t>(1 + u) * R + r), c[u], a);
+    aw[static_cast<size_t>(r) * kMcThreads] = a;
+  }
+}
+
 enum : int { ST_FETCH = 0, ST_INIT = 1, ST_TRIAL = 2, ST_LIMIT = 3, ST_DONE = 4, ST_LINE = 5 };
 
-#ifndef CMOE_MC_THREADS
-#define CMOE_MC_THREADS 128
-#endif
-#ifndef CMOE_MC_MINBLOCKS
-#define CMOE_MC_MINBLOCKS 3
-#endif
-constexpr int kMcThreads = CMOE_MC_THREADS;
 
 // The per-lane line-search state machine.  Live across evaluations: c, the base point xb with f and grad f there,
 // the step size and a few counters; the start point of the current restart run is parked in the sample's output slot.
@@ -697,7 +785,8 @@ constexpr int kMcThreads = CMOE_MC_THREADS;
 template <int KERNEL, int DIM, int QP, bool SMEM, bool GEN>
 __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* __restrict__ Xt,
                                            const double* __restrict__ Pk, const double* __restrict__ Xu, int cand,
-                                           int s_begin, int s_end, int* next_sample) {
+                                           int s_begin, int s_end, int* next_sample, double* aw = nullptr,
+                                           const double* __restrict__ Wt = nullptr, double* ring = nullptr) {
   constexpr bool SE = (KERNEL == CMOE_KERNEL_SQUARE_EXPONENTIAL);
   constexpr bool LINE = SE || !GEN;  // Matern-5/2 batches its trials too (eval_line_matern) unless derivative rows exist
   constexpr int KB = SE ? kLineBatch : kLineBatchM;  // trial step sizes per LINE round
@@ -723,9 +812,11 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
   for (int u = 0; u < QP; ++u) c[u] = 0.0;
 
   while (true) {
+    bool took_sample = false;
     if (state == ST_FETCH) {
       if (sample < s_end) {
         if (prm.max_restarts > 0) {
+          took_sample = true;
 #pragma unroll
           for (int u = 0; u < QP; ++u) c[u] = recC[static_cast<size_t>(sample) * QP + u];
           if (GEN) {
@@ -759,6 +850,18 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
       }
     }
     if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+    if (GEN) {
+      const unsigned want = __ballot_sync(0xffffffffu, took_sample);
+      if (__popc(want) >= kOwnFillLanes) {
+        // many lanes at once (samples with equal round counts keep a warp's lanes in cohorts): every requesting lane
+        // forms its own column from warp-uniform (broadcast) table loads; the column stores are full lines
+        if (took_sample) fill_own_weights<QP>(Wt, prm.N * (1 + prm.g), c, aw);
+        __syncwarp();
+      } else if (want) {
+        fill_sample_weights<QP>(Wt, prm.N * (1 + prm.g), recC, aw - (threadIdx.x & 31), want, sample,
+                                threadIdx.x & 31);
+      }
+    }
 
     bool line_round = false;
     if (LINE) {
@@ -785,7 +888,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         pmax_hi = 0;  // no factor can leave the double range on this path
         eval_line_matern<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xt, gt, c, alpha_n, S);
       } else if (GEN) {
-        eval_line_gen<DIM, QP>(prm, Xt, Pk, Xu, xt, gt, c, cl, alpha_n * (1.0 / kTop), S,
+        eval_line_gen<DIM, QP>(prm, Xt, Pk, Xu, xt, gt, aw, ring, cl, alpha_n * (1.0 / kTop), S,
                                reinterpret_cast<double (&)[kLineBatch]>(T), pmax_hi);
       } else {
         eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax_hi);
@@ -841,7 +944,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
       double S0, SB, s[DIM];
       double em[kMaxG];
       if (GEN) {
-        eval_posterior_gen<KERNEL, DIM, QP>(prm, Xt, Pk, Xu, xq, c, cl, S0, SB, s, em);
+        eval_posterior_gen<KERNEL, DIM, QP>(prm, Xt, Pk, Xu, xq, aw, ring, cl, S0, SB, s, em);
         // kb a~_jm lands on coordinate derivs[m]: fold it into s so that the common gradient formula below holds
         // (grad_d = inv_len_d (s_d - x~_d SB)), using compile-time register indices only
 #pragma unroll
@@ -1018,18 +1121,37 @@ __global__ void __launch_bounds__(kMcThreads, CMOE_MC_MINBLOCKS) kg_mc_kernel(co
   }
 }
 
-// General-path kernel (derivative observations): same state machine, operands read through the read-only path.
+// General-path kernel (derivative observations): same state machine; the per-point operands are read through the
+// read-only path and the per-sample weights from the lane's scratch column (fill_sample_weights).  Persistent grid: one
+// CTA per scratch slot, work items (candidate, sample chunk) handed out by an atomic counter.
+#ifndef CMOE_MC_GEN_MINBLOCKS
+#define CMOE_MC_GEN_MINBLOCKS 2
+#endif
 template <int KERNEL, int DIM, int QP>
-__global__ void __launch_bounds__(kMcThreads, 2) kg_mc_gen_kernel(const __grid_constant__ KgMcParams prm) {
+__global__ void __launch_bounds__(kMcThreads, CMOE_MC_GEN_MINBLOCKS)
+    kg_mc_gen_kernel(const __grid_constant__ KgMcParams prm) {
+  extern __shared__ __align__(16) double gen_ring[];  // [kRingRows][kMcThreads]
   __shared__ int next_sample;
-  const int cand = blockIdx.y;
-  const int s_begin = blockIdx.x * prm.chunk;
-  const int s_end = min(prm.num_mc, s_begin + prm.chunk);
-  if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
-  __syncthreads();
-  const double* gPk = prm.Pk + static_cast<size_t>(cand) * prm.N * prm.pk_stride;
-  const double* gXu = prm.Xu + static_cast<size_t>(cand) * prm.U * (DIM + 2);
-  kg_mc_body<KERNEL, DIM, QP, false, true>(prm, prm.Xt, gPk, gXu, cand, s_begin, s_end, &next_sample);
+  __shared__ int work_item;
+  const int R = prm.N * (1 + prm.g);
+  double* aw = prm.aw + static_cast<size_t>(blockIdx.x) * R * kMcThreads + threadIdx.x;
+  while (true) {
+    if (threadIdx.x == 0) work_item = atomicAdd(prm.work, 1);
+    __syncthreads();
+    const int w = work_item;
+    if (w >= prm.work_total) break;
+    const int cand = w / prm.chunks;
+    const int s_begin = (w % prm.chunks) * prm.chunk;
+    const int s_end = min(prm.num_mc, s_begin + prm.chunk);
+    if (threadIdx.x == 0) next_sample = s_begin + blockDim.x;
+    __syncthreads();
+    const double* gPk = prm.Pk + static_cast<size_t>(cand) * prm.N * prm.pk_stride;
+    const double* gXu = prm.Xu + static_cast<size_t>(cand) * prm.U * (DIM + 2);
+    const double* gWt = prm.Wt + static_cast<size_t>(cand) * (1 + QP) * R;
+    kg_mc_body<KERNEL, DIM, QP, false, true>(prm, prm.Xt, gPk, gXu, cand, s_begin, s_end, &next_sample, aw, gWt,
+                                             gen_ring + threadIdx.x);
+    __syncthreads();  // next_sample / work_item are rewritten by thread 0
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1043,13 +1165,25 @@ constexpr int kAccTile = 64;  // samples per shared-memory tile of kg_acc_kernel
 // One thread per row of [training points; union points]; the samples' records (minimiser, c, -|x*|^2/2) stream through
 // shared memory in double-buffered tiles (LDGSTS, 16-byte chunks) and are read back as warp-broadcast LDS.128.
 // TAB selects the table exp under the fast path's range contract (kFastPathRadius).
-template <int KERNEL, int DIM, int QP, bool TAB>
+// GEN (derivative observations): the rows are (point, m), m = 0..g, training rows first; row (p, m > 0) is the
+// derivative of k(p, x*) with respect to coordinate t = derivs[m-1] of p:  kb (x~*_t - p~_t) / l_t.  The union rows'
+// own-point gradient sums (Gu, GkB) are only produced for g == 0 (kg_g1_kernel does that part otherwise).
+template <int KERNEL, int DIM, int QP, bool TAB, bool GEN = false>
 __device__ __forceinline__ void kg_acc_body(const KgAccParams& prm, double* __restrict__ sbuf) {
   const int cand = blockIdx.y;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  const int N = prm.N, U = prm.U;
-  const bool active = row < N + U;
-  const bool is_u = row >= N;
+  const int grow = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b1 = GEN ? 1 + prm.g : 1;
+  const int N = prm.N, U = prm.U, nrows = (N + U) * b1;
+  const bool active = grow < nrows;
+  const bool is_u = grow >= N * b1;
+  const int row = GEN ? (is_u ? N + (grow - N * b1) / b1 : grow / b1) : grow;  // index into [training ; union] points
+  const int mrow = GEN ? (is_u ? (grow - N * b1) % b1 : grow % b1) : 0;
+  int tcoord = 0;
+  double tscale = 0.0;  // 1 / l_t of a derivative row
+  if (GEN && mrow > 0) {
+    tcoord = prm.derivs[mrow - 1];
+    tscale = prm.inv_len[tcoord];
+  }
   double xr[DIM];
   double pk0 = 0.0;
   if (active) {
@@ -1079,6 +1213,12 @@ __device__ __forceinline__ void kg_acc_body(const KgAccParams& prm, double* __re
   const double* cs = prm.recC + static_cast<size_t>(cand) * prm.num_mc * QP;
   const double* hs = prm.outH + static_cast<size_t>(cand) * prm.num_mc;
   const int uu = is_u ? (row - N) : 0;
+  double xrt = 0.0;  // own coordinate along the derivative direction
+  if (GEN) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+      if (d == tcoord) xrt = xr[d];
+  }
   constexpr int TS = kAccTile;
   constexpr int kBuf = TS * (DIM + QP + 1);  // doubles per buffer: [TS][DIM] | [TS][QP] | [TS]
   const int num_mc = prm.num_mc;
@@ -1133,9 +1273,10 @@ __device__ __forceinline__ void kg_acc_body(const KgAccParams& prm, double* __re
       for (int d = 0; d < DIM; ++d) dot = fma(xi[d], xr[d], dot);
       double kv, kb;
       kernel_pair<KERNEL, TAB>(dot, pk0, sh[i], prm.alpha, kv, kb);
+      if (GEN && mrow > 0) kv = kb * (sx[i * DIM + tcoord] - xrt) * tscale;
 #pragma unroll
       for (int a = 0; a < QP; ++a) acc[a] = fma(ci[a], kv, acc[a]);
-      if (is_u) {
+      if (!GEN && is_u) {
         double cu = 0.0;
 #pragma unroll
         for (int a = 0; a < QP; ++a)
@@ -1149,10 +1290,10 @@ __device__ __forceinline__ void kg_acc_body(const KgAccParams& prm, double* __re
     __syncthreads();  // the buffer is refilled two tiles later
   }
   if (!active) return;
-  double* R = prm.R + static_cast<size_t>(cand) * QP * (N + U);
+  double* R = prm.R + static_cast<size_t>(cand) * QP * nrows;
 #pragma unroll
-  for (int a = 0; a < QP; ++a) R[static_cast<size_t>(a) * (N + U) + row] = acc[a];
-  if (is_u) {
+  for (int a = 0; a < QP; ++a) R[static_cast<size_t>(a) * nrows + grow] = acc[a];
+  if (!GEN && is_u) {
     prm.GkB[static_cast<size_t>(cand) * U + uu] = gkb;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) prm.Gu[(static_cast<size_t>(cand) * U + uu) * DIM + d] = gu[d];
@@ -1170,6 +1311,17 @@ __global__ void __launch_bounds__(128) kg_acc_kernel(const __grid_constant__ KgA
   kg_acc_body<KERNEL, DIM, QP, false>(prm, acc_smem);
 }
 
+template <int KERNEL, int DIM, int QP>
+__global__ void __launch_bounds__(128) kg_acc_gen_kernel(const __grid_constant__ KgAccParams prm) {
+  extern __shared__ __align__(16) double acc_smem[];
+  if (prm.fast_exp) {
+    exp_table_stage();
+    kg_acc_body<KERNEL, DIM, QP, true, true>(prm, acc_smem);
+    return;
+  }
+  kg_acc_body<KERNEL, DIM, QP, false, true>(prm, acc_smem);
+}
+
 // launchers instantiated per (DIM) translation unit
 using KgMcLaunch = void (*)(const KgMcParams&, dim3 grid, size_t smem, cudaStream_t s);
 using KgAccLaunch = void (*)(const KgAccParams&, dim3 grid, cudaStream_t s);
@@ -1178,6 +1330,7 @@ struct KgDispatchEntry {
   KgMcLaunch mc;      // g == 0 fast path (TMA-staged operands)
   KgMcLaunch mc_gen;  // general path (derivative observations); may be null
   KgAccLaunch acc;
+  KgAccLaunch acc_gen;  // general path; null where mc_gen is
   size_t (*smem_bytes)(int N, int U);
 };
 void register_kg_entries(const KgDispatchEntry* entries, int count);
@@ -1190,8 +1343,16 @@ void launch_kg_mc(const KgMcParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   kg_mc_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, smem, s>>>(p);
 }
 template <int KERNEL, int DIM, int QP>
-void launch_kg_mc_gen(const KgMcParams& p, dim3 grid, size_t, cudaStream_t s) {
-  kg_mc_gen_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, 0, s>>>(p);
+void launch_kg_mc_gen(const KgMcParams& p, dim3, size_t, cudaStream_t s) {
+  int dev = 0, sms = 1, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  constexpr size_t ring_bytes = static_cast<size_t>(kRingRows + kRingDepth) * kMcThreads * sizeof(double);
+  cudaFuncSetAttribute(kg_mc_gen_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(ring_bytes));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kg_mc_gen_kernel<KERNEL, DIM, QP>, kMcThreads, ring_bytes);
+  const int grid = std::max(1, std::min(std::min(p.aw_slots, p.work_total), sms * std::max(1, per_sm)));
+  kg_mc_gen_kernel<KERNEL, DIM, QP><<<grid, kMcThreads, ring_bytes, s>>>(p);
 }
 template <int KERNEL, int DIM, int QP>
 void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {
@@ -1199,15 +1360,24 @@ void launch_kg_acc(const KgAccParams& p, dim3 grid, cudaStream_t s) {
   cudaFuncSetAttribute(kg_acc_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   kg_acc_kernel<KERNEL, DIM, QP><<<grid, 128, smem, s>>>(p);
 }
+template <int KERNEL, int DIM, int QP>
+void launch_kg_acc_gen(const KgAccParams& p, dim3 grid, cudaStream_t s) {
+  const size_t smem = 2 * static_cast<size_t>(kAccTile) * (DIM + QP + 1) * sizeof(double);
+  cudaFuncSetAttribute(kg_acc_gen_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  kg_acc_gen_kernel<KERNEL, DIM, QP><<<grid, 128, smem, s>>>(p);
+}
 template <int DIM, int QP>
 size_t kg_smem_bytes(int N, int U) {
   return (static_cast<size_t>(N) * (DIM + QP + 2) + static_cast<size_t>(U) * (DIM + 2)) * sizeof(double);
 }
 
 #define CMOE_KG_ENTRY(K, D, Q) \
-  { K, D, Q, &launch_kg_mc<K, D, Q>, nullptr, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
-#define CMOE_KG_ENTRY_GEN(K, D, Q) \
-  { K, D, Q, &launch_kg_mc<K, D, Q>, &launch_kg_mc_gen<K, D, Q>, &launch_kg_acc<K, D, Q>, &kg_smem_bytes<D, Q> }
+  { K, D, Q, &launch_kg_mc<K, D, Q>, nullptr, &launch_kg_acc<K, D, Q>, nullptr, &kg_smem_bytes<D, Q> }
+#define CMOE_KG_ENTRY_GEN(K, D, Q)                                                                                \
+  {                                                                                                               \
+    K, D, Q, &launch_kg_mc<K, D, Q>, &launch_kg_mc_gen<K, D, Q>, &launch_kg_acc<K, D, Q>, &launch_kg_acc_gen<K, D, Q>, \
+        &kg_smem_bytes<D, Q>                                                                                       \
+  }
 // union-row counts: 2, 4, 8, 16, 24, 32 (24 serves config 4: q = 4 with 4 derivative observations -> 20 rows; the
 // 32-wide instantiation spilled ~1.5 KB per thread there)
 #define CMOE_KG_ENTRIES_FOR_DIM(D)                                                                              \
