@@ -62,6 +62,8 @@ struct CoopParams {
   int* sync;         // this launch's sync area
   double* scratch;   // [4][BLK] published inverses
   int* abort_flag;   // set when a wait gives up
+  int gate;          // >= 0: CTAs of the rows below the diagonal block keep taking trailing tiles until diagonal block
+                     // `gate` has been factored (see chol_step_kernel); -1: they join the chain at once
   unsigned long long* trace;  // optional [gridDim][kTraceSlots] time stamps (CMOE_CHOL_TRACE), else NULL
 };
 
@@ -361,9 +363,8 @@ __device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Mi
 // --------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopParams& P, double* buf, uint64_t* pbar,
                                            uint32_t& pphase, double* colbuf, double* rd, volatile int* sfail, volatile int* sflag,
-                                       volatile int* prog) {
+                                       volatile int* prog, int r) {
   const int tid = threadIdx.x;
-  const int r = blockIdx.x;
   const int nkk = (P.pw + NB - 1) / NB;
   const int rows0 = P.p0 + NB * r;
   const int jmax = min(r, nkk - 1);
@@ -527,7 +528,12 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   __syncthreads();
   const int n = P.n, p0 = P.p0;
   const int nrb = (n - p0 + NB - 1) / NB;        // panel row blocks
+  // CTA r < nrb owns row block r of the panel.  A row block below the diagonal block spends most of the chain waiting
+  // for the next diagonal block (its own share of a step is a few microseconds of a ~30 us step).  While the trailing
+  // update is the bottleneck of the launch (P.gate >= 0) such a CTA therefore keeps taking trailing tiles until diagonal
+  // block `gate` is done and runs through its steps afterwards, every earlier flag already set.
   const bool is_p = static_cast<int>(blockIdx.x) < nrb;
+  const bool gated = is_p && P.gate >= 0 && static_cast<int>(blockIdx.x) >= 4;
   bool p_done = false;
   uint32_t gchunk = 0, pphase = 0;
   // trailing update with the previous panel
@@ -559,6 +565,8 @@ __global__ void __launch_bounds__(CTHREADS, 1)
   // the four chain CTAs never pick up (a) tiles: nothing may delay the start of the chain
   bool a_done = (num_a == 0) || static_cast<int>(blockIdx.x) < small_rows;
   int* small_ready = P.sync + 22;
+  const int* gate_flag = P.sync + 1 + max(0, P.gate);  // F flag of diagonal block `gate`
+  bool b_left = true;  // thread 0's view of the (b) tile pool
   for (;;) {
     if (tid == 0) {
       int t = -2;
@@ -566,8 +574,17 @@ __global__ void __launch_bounds__(CTHREADS, 1)
         t = atomicAdd(counter_a, 1);
         if (t >= num_a) t = -3;  // (a) tiles exhausted
       }
-      if (t < 0 && (!is_p || p_done)) {
-        t = num_a + atomicAdd(counter_b, 1);
+      if (t < 0) {
+        const bool hold_rows = gated && !p_done && b_left && ld_acquire(gate_flag) == 0;
+        if (!is_p || p_done || hold_rows) {
+          const int tb = num_a + atomicAdd(counter_b, 1);
+          if (tb < total) {
+            t = tb;
+          } else {
+            b_left = false;
+            t = (is_p && !p_done) ? -3 : total;  // nothing left to fill the wait with: join the chain / leave
+          }
+        }
       }
       s_tile = t;
     }
@@ -577,7 +594,7 @@ __global__ void __launch_bounds__(CTHREADS, 1)
     if (t < 0) {
       a_done = true;
       if (is_p && !p_done) {
-        panel_role(&mapBlk, P, buf, &pbar, pphase, colbuf, rd, &sfail, &sflag, &prog);
+        panel_role(&mapBlk, P, buf, &pbar, pphase, colbuf, rd, &sfail, &sflag, &prog, blockIdx.x);
         p_done = true;
         __syncthreads();
       }
@@ -662,9 +679,24 @@ bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
   CMOE_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(kCoopSmem)));
   const int npanels = (n + CW - 1) / CW;
-  DevBuf<int> sync(static_cast<size_t>(npanels) * kSyncPerPanel + 1);
-  DevBuf<double> scratch(static_cast<size_t>(4) * BLK);
-  CMOE_CUDA(cudaMemsetAsync(sync.p, 0, sync.count * sizeof(int), s));
+  // workspace kept per host thread and device: cudaMalloc / cudaFree inside the timed factorisation cost up to
+  // milliseconds on a loaded host (seen as 3.4 -> 5.6 ms on one box with identical device-side spans)
+  struct Workspace {
+    int device = -1;
+    DevBuf<int> sync;
+    DevBuf<double> scratch;
+  };
+  static thread_local Workspace ws;
+  if (ws.device != dev) {
+    ws.sync.release();
+    ws.scratch.release();
+    ws.device = dev;
+  }
+  ws.sync.ensure(static_cast<size_t>(npanels) * kSyncPerPanel + 1);
+  ws.scratch.ensure(static_cast<size_t>(4) * BLK);
+  DevBuf<int>& sync = ws.sync;
+  DevBuf<double>& scratch = ws.scratch;
+  CMOE_CUDA(cudaMemsetAsync(sync.p, 0, (static_cast<size_t>(npanels) * kSyncPerPanel + 1) * sizeof(int), s));
   CMOE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
   int* abort_flag = sync.p + static_cast<size_t>(npanels) * kSyncPerPanel;
   // CMOE_CHOL_TRACE=<file>: %globaltimer stamps of thread 0 of every CTA at the role / step boundaries of every panel
@@ -675,9 +707,18 @@ bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
     trace.alloc(per_panel * npanels);
     CMOE_CUDA(cudaMemsetAsync(trace.p, 0, trace.count * sizeof(unsigned long long), s));
   }
+  // trailing row tiles (128 rows) from which a panel counts as update-bound (the chain takes ~130 us, a 128 x 128 tile
+  // ~40 us on one SM) and the diagonal block the lower rows wait for; CMOE_CHOL_GATE="<tiles>,<block>" overrides (a huge
+  // tile count disables)
+  int gate_min_tiles = 22, gate_block = 1;
+  if (const char* e = std::getenv("CMOE_CHOL_GATE")) std::sscanf(e, "%d,%d", &gate_min_tiles, &gate_block);
+  gate_block = std::max(0, std::min(gate_block, 3));
   for (int p0 = 0, pi = 0; p0 < n; p0 += CW, ++pi) {
+    // hold the rows below the diagonal block back while the trailing update, not the chain, bounds the launch
+    const int nbt = n > p0 + CW ? (n - p0 - CW + TM - 1) / TM : 0;
+    const int gate = (p0 > 0 && p0 + CW < n && nbt >= gate_min_tiles) ? gate_block : -1;
     CoopParams P{A, n, n, p0, std::min(CW, n - p0), flag, sync.p + static_cast<size_t>(pi) * kSyncPerPanel, scratch.p,
-                 abort_flag, trace_path ? trace.p + per_panel * pi : nullptr};
+                 abort_flag, gate, trace_path ? trace.p + per_panel * pi : nullptr};
     void* args[] = {&mapOp, &mapBlk, &P};
     CMOE_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(chol_step_kernel), dim3(sms), dim3(CTHREADS), args,
                                           kCoopSmem, s));
@@ -713,7 +754,7 @@ bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
   }
   int aborted = 0;
   CMOE_CUDA(cudaMemcpyAsync(&aborted, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CMOE_CUDA(cudaStreamSynchronize(s));  // scratch is freed on return
+  CMOE_CUDA(cudaStreamSynchronize(s));
   CMOE_REQUIRE(!aborted, CMOE_ERR_RUNTIME,
                "cooperative Cholesky: a dependency wait timed out (device shared with another long-running kernel?)");
   return true;

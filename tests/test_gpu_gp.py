@@ -85,6 +85,34 @@ def test_cholesky_cooperative_path(capi, n):
     tril_close(Lo, Lref[: n - 1, : n - 1], rtol=1e-10, atol=1e-11)
 
 
+@pytest.mark.parametrize("n", [1536, 2306])
+@pytest.mark.parametrize("block", [0, 2, 3])
+def test_cholesky_cooperative_gated_rows(capi, n, block, monkeypatch):
+    """Update-bound panels let the CTAs of the rows below the diagonal block keep working on trailing tiles until a
+    given diagonal block of the panel is factored.  That schedule only engages for n >= 3328 by default;
+    CMOE_CHOL_GATE="1,<block>" forces it on every panel with trailing columns, so the small sizes cover it too.  Same
+    matrix, both schedules, bit-identical factors expected (the arithmetic of a row block does not depend on when it
+    runs)."""
+    rng = np.random.default_rng(1234 + n)
+    G = rng.standard_normal((n, n // 2))
+    A = G @ G.T + 0.5 * n * np.eye(n)
+    monkeypatch.setenv("CMOE_CHOL_GATE", "100000,0")
+    L0 = np.tril(capi.cholesky(A))
+    monkeypatch.setenv("CMOE_CHOL_GATE", "1,%d" % block)
+    L1 = np.tril(capi.cholesky(A))
+    np.testing.assert_array_equal(L0, L1)
+    rc, Lref = checker().cholesky(A)
+    assert rc == 0
+    tril_close(L1, Lref, rtol=1e-10, atol=1e-11)
+    # a failed pivot inside the chain while row blocks are still held back
+    bad = 700
+    A[bad, :] = 0.0
+    A[:, bad] = 0.0
+    with pytest.raises(capi.SingularMatrixError) as e:
+        capi.cholesky(A)
+    assert e.value.info == bad + 1
+
+
 @pytest.mark.parametrize("bad", [0, 70, 300, 1279, 1535])
 def test_cholesky_cooperative_failure_index(capi, bad):
     n = 1536
