@@ -550,12 +550,30 @@ def main():
         #   point evaluation (value + gradient at one query point): dot 2d, weights 2qb, exp 1, value 2, scale 1, grad 2d
         #   line batch (all KB = 8 backtracking trials of a step):  two dots 4d, weights 2qb, two exps 2, scale 1,
         #                                                            KB fma 2KB, KB-1 squarings
+        #   Matern-5/2 line batch (KB = 6 value-only trials sharing dots and weights): 4d + 2q + 3, then per trial
+        #                                                            distance 3, sqrt 1, exp 1, polynomial + sum 6
+        #   derivative observations (g > 0): the (1+g) Q weight FMAs per training point are executed ONCE per sample
+        #   (per-lane weight columns), an evaluation then costs per POINT: dot 2d, exp 1, 5 per derivative row, 9 for
+        #   value / gradient weights, grad 2d; a line batch per POINT: 4d, 5 per derivative row, two exps, 3, 5 KB - 1
         b = 1 + len(w["g"])
         rows = w["N"] * b + w["q"] * b
-        KB = 8
-        flops_point = rows * (2 * w["dim"] + 2 * w["q"] * b + 1 + 2 + 1 + 2 * w["dim"])
-        flops_line = rows * (4 * w["dim"] + 2 * w["q"] * b + 2 + 1 + 2 * KB + (KB - 1))
-        executed = stats["point_evals"] * flops_point + stats["line_batches"] * flops_line
+        flops_sample = 0
+        if w["g"]:
+            KB = 8
+            pts = w["N"] + w["q"]
+            flops_point = pts * (4 * w["dim"] + 5 * len(w["g"]) + 10)
+            flops_line = pts * (4 * w["dim"] + 5 * len(w["g"]) + 5 + 5 * KB - 1)
+            flops_sample = 2 * w["N"] * b * (w["q"] * b)
+        elif kernel == 1:
+            KB = 6
+            flops_point = rows * (2 * w["dim"] + 2 * w["q"] + 1 + 1 + 8 + 2 * w["dim"])
+            flops_line = rows * (4 * w["dim"] + 2 * w["q"] + 3 + KB * 11)
+        else:
+            KB = 8
+            flops_point = rows * (2 * w["dim"] + 2 * w["q"] * b + 1 + 2 + 1 + 2 * w["dim"])
+            flops_line = rows * (4 * w["dim"] + 2 * w["q"] * b + 2 + 1 + 2 * KB + (KB - 1))
+        executed = (stats["point_evals"] * flops_point + stats["line_batches"] * flops_line +
+                    stats["mc_samples"] * flops_sample)
         achieved = executed / (mc_ms / args.steps * 1e-3) * 1e-12
         # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write); the
         # capture ran 256 candidates per launch and the traffic is per-sample records: it scales with the candidates
@@ -579,6 +597,7 @@ def main():
             "point_evals_per_sample": stats["point_evals"] / max(1, stats["mc_samples"]),
             "line_batches_per_sample": stats["line_batches"] / max(1, stats["mc_samples"]),
             "flops_per_point_eval": flops_point, "flops_per_line_batch": flops_line,
+            "flops_per_sample_setup": flops_sample,
             "executed_flops_per_sample": executed / max(1, stats["mc_samples"])}
         out["fp64_dmma_peak_tflops"] = fp64_dmma
     else:
