@@ -153,6 +153,27 @@ def test_dkg_derivative_observations_table_fed(capi, kernel, gd, q, p, g_idx):
         np.testing.assert_allclose(grad[c], g, rtol=1e-5, atol=1e-8)
 
 
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("dim,g_idx,q", [(8, tuple(range(8)), 2), (4, (1, 3), 3), (6, (0, 2, 3, 4, 5), 1)])
+def test_dkg_weight_column_paths(capi, kernel, dim, g_idx, q):
+    """The per-sample weight columns of the d-KG kernel on shapes the other tests do not reach: 8 derivative observations
+    (9 rows per point: one point per ring stage), even / odd row counts, and 1024 samples per candidate so that lanes
+    take several samples each — cohorts of lanes (own-lane column fill) as well as stragglers (warp-cooperative fill)."""
+    prob = make_problem(10, dim, g_idx=g_idx, seed=21 + dim, noise=0.1)
+    gp, ref = _pair(capi, kernel, prob)
+    rng = np.random.default_rng(5 + dim)
+    cands = rng.uniform(size=(2, q, dim))
+    disc = rng.uniform(size=(6, dim))
+    mc = 1024
+    Q = q * (1 + len(g_idx))
+    table = rng.standard_normal((mc // 2) * Q)
+    best = float(ref.mean_additional(disc).min())
+    kg, grad = gp.kg(cands, None, mc, best, EXAMPLE_INNER_GD, unit_bounds(dim), disc, table=table, grad=True)
+    v, g = ref.kg(cands[1], None, mc, best, table, EXAMPLE_INNER_GD, unit_bounds(dim), disc, grad=True)
+    np.testing.assert_allclose(kg[1], v, rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(grad[1], g, rtol=1e-5, atol=1e-8)
+
+
 def test_dkg_config4_shape_spot_check(capi):
     """BASELINE.json configs[3] structure: d = 4, all 4 partial derivatives observed, q = 4 (system n = N*5); reduced N
     and num_mc so that the CPU checker finishes in seconds, Philox stream on the device."""
