@@ -178,14 +178,29 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* mapOp, double* ring
 // [k][SLD].  16 warps x (16 x 16).  TRI: B is the transposed inverse of a lower-triangular block (B[k][c] = 0 for
 // k > c), so the K loop of a warp stops at its last column.
 // --------------------------------------------------------------------------------------------------------------
+// Warp -> 16 x 16 sub-tile.  Standard: warp w -> (rows 16 (w % 4), columns 16 (w / 4)).  LOWER (symmetric update of a
+// diagonal block: only the lower triangle is ever read): the ten lower sub-tiles are dealt to warps 0..9 in an order that
+// puts at most three on a scheduler (the standard map leaves four on one), warps 10..15 idle (wm < 0).
+struct WarpTile {
+  int wm, wn;
+};
+__device__ __forceinline__ WarpTile warp_tile(bool lower) {
+  const int warp = threadIdx.x >> 5;
+  if (!lower) return {(warp & 3) * 16, (warp >> 2) * 16};
+  // (row, col) in units of 16, in the order 00 10 11 20 21 22 30 31 32 33
+  if (warp >= 10) return {-1, -1};
+  const int row = (warp >= 6) ? 3 : (warp >= 3) ? 2 : (warp >= 1) ? 1 : 0;
+  return {row * 16, (warp - row * (row + 1) / 2) * 16};
+}
+
 template <bool NEG, bool TRI>
 __device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double* As, const double* Bs,
-                                           bool lower_only = false) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 16;
+                                           const WarpTile wt) {
+  const int lane = threadIdx.x & 31;
+  const int wm = wt.wm, wn = wt.wn;
   const int lr = lane >> 2, lc = lane & 3;
   const int kend = TRI ? wn + 16 : NB;
-  if (lower_only && wn > wm) return;  // symmetric update of a diagonal block: only the lower triangle is ever read
+  if (wm < 0) return;
   // two independent accumulator sets (even / odd k-steps): the product is a chain of dependent DMMAs per accumulator
   // and this routine sits on the panel's critical path — half the chain, summed at the end
   double acc2[2][2][2];
@@ -226,10 +241,10 @@ __device__ __forceinline__ void tile64_mma(double (&acc)[2][2][2], const double*
 }
 
 // fragment <-> block coordinates of tile64_mma
-#define CMOE_FRAG_LOOP(BODY)                                            \
-  {                                                                     \
-    const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;       \
-    const int wm_ = (warp_ & 3) * 16, wn_ = (warp_ >> 2) * 16;          \
+#define CMOE_FRAG_LOOP(WT, BODY)                                        \
+  if ((WT).wm >= 0) {                                                   \
+    const int lane_ = threadIdx.x & 31;                                 \
+    const int wm_ = (WT).wm, wn_ = (WT).wn;                             \
     const int lr_ = lane_ >> 2, lc_ = lane_ & 3;                        \
     _Pragma("unroll") for (int i = 0; i < 2; ++i)                       \
     _Pragma("unroll") for (int j = 0; j < 2; ++j)                       \
@@ -256,6 +271,16 @@ __device__ __forceinline__ void solve_follow(double (&x)[32], double* LT, double
   }
 }
 
+// One 8 x 8 block of a 32 x 32 product on the FP64 tensor pipe: acc (+)= sum_{k0 <= k < k1} A(r, k) B(c, k) for the block
+// rows r = 8 bi .. and columns c = 8 bj ..; a_at / b_at fetch single operand entries (shared memory, any layout).  The
+// SYRK / Y / Z pieces of the diagonal-block factorisation were per-thread dot products before: 96 shared-memory loads
+// per thread and ~1.8 us each on the chain, bound by the load pipe; as 16 warp blocks they are 16 loads + 8 DMMA per warp.
+template <typename FA, typename FB>
+__device__ __forceinline__ void mma_block8(double (&acc)[2], int bi, int bj, int k0, int k1, FA&& a_at, FB&& b_at) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  for (int k = k0; k < k1; k += 4) dmma_m8n8k4(acc[0], acc[1], a_at(bi * 8 + lr, k + lc), b_at(bj * 8 + lr, k + lc));
+}
+
 // Factor the 64 x 64 diagonal block held in `blk` ([c*SLD + r], lower part meaningful) and build the packet
 // M[m*SLD + j] = (L^-1)[j][m] in `Minv`.  LT (transposed factor, [c*LTS + r]) lives in `LT`.  Returns 0 or the 1-based
 // index of the failing pivot.  All CTHREADS threads call.  Warp 0 factors; warp 1 (inverse of the diagonal 32-blocks)
@@ -263,17 +288,32 @@ __device__ __forceinline__ void solve_follow(double (&x)[32], double* LT, double
 __device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Minv, double* cb, double* rd,
                                              volatile int* sfail, volatile int* prog, const CoopParams& P, int tbase) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Nothing but the column buffer needs clearing: LT is only read where it has been written or into window slots that are
+  // never emitted (any finite or non-finite garbage is discarded there); of Minv only the lower-triangular part of the
+  // packet is produced, read (Y, Z) and published — the other half of the packet is zero in global memory for good.
   for (int e = tid; e < NB * LTS + NB; e += CTHREADS) LT[e] = 0.0;
   for (int e = tid; e < 256; e += CTHREADS) cb[e] = 0.0;
   for (int e = tid; e < BLK; e += CTHREADS) Minv[e] = 0.0;
   if (tid == 0) *prog = 0;
   __syncthreads();
+  // the X tile this CTA stored as a consumer of the previous step is announced from here by a warp that idles through
+  // the first half anyway (every thread's stores precede the barrier above; barrier + one thread's fence publishes them)
+  // (block kk >= 1 is factored by the CTA that consumed step kk - 1 as row block kk: its X flag is sync[5 + 4 kk + kk - 1])
+  const int kk_self = (tbase - 32) / 6;
+  if (kk_self > 0 && tid == 3 * 32) {
+    __threadfence();
+    fence_proxy_async();
+    st_release(P.sync + 5 + kk_self * 4 + (kk_self - 1), 1);
+  }
+  const int tfine = tbase - 24;  // the consumer slots of this step are free in the factoring CTA
+  trace_mark(P, tfine + 0);
   if (warp == 0) {
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[c * SLD + lane] : 0.0;
     const int f = chol32_warp_pipe(a, lane, cb, LT, rd, 0, prog);
     if (lane == 0) *sfail = f;
+    trace_mark(P, tfine + 1);
   } else if (warp == 1) {
     // column `lane` of L11^-1 = row `lane` of L11^-T: e_lane L11^-T
     double x[32];
@@ -294,24 +334,28 @@ __device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Mi
   trace_mark(P, tbase + 1);
   if (*sfail) return *sfail;
   {
-    // A22 -= L21 L21^T: warp w owns columns 2w, 2w+1; lane r row 32 + r
-    double acc[2][4];  // four partial sums per output: the 32-term dot product is a dependent chain otherwise
+    // A22 -= L21 L21^T (lower blocks) and Y = L21 * L11^-1 (parked in the lower-left block of Minv): warp w -> block (w / 4, w % 4)
+    const int bi = warp >> 2, bj = warp & 3, lr = lane >> 2, lc = lane & 3;
+    if (bi >= bj) {
+      double acc[2];
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      acc[cc][0] = blk[(32 + warp * 2 + cc) * SLD + 32 + lane];
-      acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0;
+      for (int h = 0; h < 2; ++h) acc[h] = blk[(32 + bj * 8 + lc * 2 + h) * SLD + 32 + bi * 8 + lr];
+      mma_block8(acc, bi, bj, 0, 32, [&](int r, int k) { return -blk[k * SLD + 32 + r]; },
+                 [&](int c, int k) { return blk[k * SLD + 32 + c]; });
+#pragma unroll
+      for (int h = 0; h < 2; ++h) blk[(32 + bj * 8 + lc * 2 + h) * SLD + 32 + bi * 8 + lr] = acc[h];
     }
+    {
+      // Y[i][t] = sum_{m >= t} L21[i][m] I11[m][t]
+      double acc[2] = {0.0, 0.0};
+      mma_block8(acc, bi, bj, bj * 8, 32, [&](int i, int m) { return LT[m * LTS + 32 + i]; },
+                 [&](int t, int m) { return Minv[t * SLD + m]; });
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const double xr = blk[k * SLD + 32 + lane];
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) acc[cc][k & 3] = fma(-xr, LT[k * LTS + 32 + warp * 2 + cc], acc[cc][k & 3]);
+      for (int h = 0; h < 2; ++h) Minv[(bj * 8 + lc * 2 + h) * SLD + 32 + bi * 8 + lr] = acc[h];
     }
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc)
-      blk[(32 + warp * 2 + cc) * SLD + 32 + lane] = (acc[cc][0] + acc[cc][1]) + (acc[cc][2] + acc[cc][3]);
     if (tid == 0) *prog = 0;
   }
+  trace_mark(P, tfine + 2);
   __syncthreads();
   trace_mark(P, tbase + 2);
   if (warp == 0) {
@@ -320,38 +364,26 @@ __device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Mi
     for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? blk[(32 + c) * SLD + 32 + lane] : 0.0;
     const int f = chol32_warp_pipe(a, lane, cb, LT, rd, 32, prog);
     if (lane == 0) *sfail = f ? 32 + f : 0;
+    trace_mark(P, tfine + 3);
   } else if (warp == 1) {
     double x[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) x[c] = (c == lane) ? 1.0 : 0.0;
     solve_follow(x, LT, rd, 32, prog, [&](int k, double v) { Minv[(32 + lane) * SLD + k] = v; });
-  } else {
-    // Y = L21 * L11^-1 (32 x 32) meanwhile: thread -> (i = lane, t); parked in the lower-left block
-    for (int t = warp - 2; t < 32; t += CTHREADS / 32 - 2) {
-      double y[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int m = 0; m < 32; ++m) y[m & 3] = fma(LT[m * LTS + 32 + lane], Minv[t * SLD + m], y[m & 3]);
-      Minv[t * SLD + 32 + lane] = (y[0] + y[1]) + (y[2] + y[3]);
-    }
   }
   __syncthreads();
   trace_mark(P, tbase + 3);
   if (*sfail) return *sfail;
   {
-    // Z = -L22^-1 * Y: Z[i][t] = -sum_{m <= i} Inv22[i][m] Y[m][t]; two (i, t) pairs per thread
-    double z[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = warp + 16 * u;
-      double sacc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int m = 0; m < 32; ++m)
-        sacc[m & 3] = fma(Minv[(32 + m) * SLD + 32 + lane], Minv[t * SLD + 32 + m], sacc[m & 3]);
-      z[u] = -((sacc[0] + sacc[1]) + (sacc[2] + sacc[3]));
-    }
+    // Z = -L22^-1 * Y: Z[i][t] = -sum_{m <= i} Inv22[i][m] Y[m][t], in place over Y (all blocks read before any is written)
+    const int bi = warp >> 2, bj = warp & 3, lr = lane >> 2, lc = lane & 3;
+    double acc[2] = {0.0, 0.0};
+    mma_block8(acc, bi, bj, 0, bi * 8 + 8, [&](int i, int m) { return -Minv[(32 + m) * SLD + 32 + i]; },
+               [&](int t, int m) { return Minv[t * SLD + 32 + m]; });
+    trace_mark(P, tfine + 4);
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 2; ++u) Minv[(warp + 16 * u) * SLD + 32 + lane] = z[u];
+    for (int h = 0; h < 2; ++h) Minv[(bj * 8 + lc * 2 + h) * SLD + 32 + bi * 8 + lr] = acc[h];
   }
   __syncthreads();
   trace_mark(P, tbase + 4);
@@ -415,9 +447,15 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         }
         return;
       }
-      // publish the inverse first (the chain waits for it), the factor tile itself afterwards
+      // publish the inverse first (the chain waits for it), the factor tile itself afterwards.  Packet entry
+      // [m * SLD + j] = (L^-1)[j][m]: only j >= m is non-zero and only that half is ever written (the buffer was cleared
+      // when it was allocated)
       double* G = P.scratch + kk * BLK;
-      for (int e = tid; e < BLK; e += CTHREADS) G[e] = stageL[e];
+      for (int e = tid; e < BLK; e += CTHREADS) {
+        const int m = e / SLD, j = e - m * SLD;
+        if (j >= m && j < NB) G[e] = stageL[e];
+      }
+      trace_mark(P, 8 + kk * 6 + 5);
       __threadfence();
       __syncthreads();
       if (tid == 0) {
@@ -450,10 +488,11 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-      tile64_mma<false, true>(acc, blkk, stageM);
+      const WarpTile wt = warp_tile(false);
+      tile64_mma<false, true>(acc, blkk, stageM, wt);
       __syncthreads();  // every warp has read its A rows
       double* Ag = P.A + static_cast<size_t>(k0) * P.lda + rows0;
-      CMOE_FRAG_LOOP({
+      CMOE_FRAG_LOOP(wt, {
         blkk[col * SLD + row] = acc[i][j][h];
         if (rows0 + row < P.n && col < nb) Ag[static_cast<size_t>(col) * P.lda + row] = acc[i][j][h];
       })
@@ -492,12 +531,17 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
       }
       double* blkj = buf + jb * BLK;
       double acc[2][2][2];
-      CMOE_FRAG_LOOP({ acc[i][j][h] = blkj[col * SLD + row]; })
-      tile64_mma<true, false>(acc, blkk, Bs, jb == r);
-      CMOE_FRAG_LOOP({ blkj[col * SLD + row] = acc[i][j][h]; })
+      WarpTile wt = warp_tile(false);
+      // own diagonal tile: only its lower triangle is ever read.  (The balanced map warp_tile(true) would save ~0.5 us
+      // here but costs the pivot loop of factor_diag64 a spilled loop-carried register with this register budget.)
+      if (jb == r && wt.wn > wt.wm) wt.wm = -1;
+      CMOE_FRAG_LOOP(wt, { acc[i][j][h] = blkj[col * SLD + row]; })
+      tile64_mma<true, false>(acc, blkk, Bs, wt);
+      CMOE_FRAG_LOOP(wt, { blkj[col * SLD + row] = acc[i][j][h]; })
       __syncthreads();  // stageL is reused by the next column block; blkj complete before it becomes an operand
       trace_mark(P, 8 + kk * 6 + 4);
     }
+    if (r == kk + 1 && r < nkk) published = true;  // this CTA factors next: factor_diag64 releases the flag
     publish();
   }
   trace_mark(P, 60);
@@ -693,7 +737,10 @@ bool potrf_lower_coop(double* A, int n, int* flag, cudaStream_t s) {
     ws.device = dev;
   }
   ws.sync.ensure(static_cast<size_t>(npanels) * kSyncPerPanel + 1);
-  ws.scratch.ensure(static_cast<size_t>(4) * BLK);
+  if (ws.scratch.count < static_cast<size_t>(4) * BLK) {
+    ws.scratch.alloc(static_cast<size_t>(4) * BLK);
+    CMOE_CUDA(cudaMemsetAsync(ws.scratch.p, 0, ws.scratch.count * sizeof(double), s));  // the packets' zero halves
+  }
   DevBuf<int>& sync = ws.sync;
   DevBuf<double>& scratch = ws.scratch;
   CMOE_CUDA(cudaMemsetAsync(sync.p, 0, (static_cast<size_t>(npanels) * kSyncPerPanel + 1) * sizeof(int), s));
