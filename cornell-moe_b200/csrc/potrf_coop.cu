@@ -291,9 +291,7 @@ __device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Mi
   // Nothing but the column buffer needs clearing: LT is only read where it has been written or into window slots that are
   // never emitted (any finite or non-finite garbage is discarded there); of Minv only the lower-triangular part of the
   // packet is produced, read (Y, Z) and published — the other half of the packet is zero in global memory for good.
-  for (int e = tid; e < NB * LTS + NB; e += CTHREADS) LT[e] = 0.0;
   for (int e = tid; e < 256; e += CTHREADS) cb[e] = 0.0;
-  for (int e = tid; e < BLK; e += CTHREADS) Minv[e] = 0.0;
   if (tid == 0) *prog = 0;
   __syncthreads();
   // the X tile this CTA stored as a consumer of the previous step is announced from here by a warp that idles through
@@ -456,9 +454,11 @@ __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopPar
         if (j >= m && j < NB) G[e] = stageL[e];
       }
       trace_mark(P, 8 + kk * 6 + 5);
-      __threadfence();
       __syncthreads();
       if (tid == 0) {
+        // barrier, then ONE thread's fence and release: cumulative over the block's stores that precede the barrier (the
+        // pattern of a cooperative-groups grid barrier) — the other 511 threads do not wait for their stores to drain
+        __threadfence();
         fence_proxy_async();
         st_release(F + kk, 1);
       }
