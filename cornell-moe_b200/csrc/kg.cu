@@ -13,6 +13,7 @@
 //   -> fused MC kernel (inner line-search optimisation of every sample)
 //   -> [gradient] accumulate R = sum_i k(X, x*_i) c_i^T, K^-1 R, contraction with dK*, dL  -> KG, grad KG.
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 
@@ -744,6 +745,10 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     m.g = spec.g;
     m.Q = Q;
     m.pk_stride = pl->stride;
+    // general path: park the scaled training points + e_j behind the weight ring when they are small enough to leave room
+    // for two CTAs per SM (2 x (90 KB ring + 20 KB) < 227 KB)
+    m.stage_ops = (spec.g > 0 && static_cast<size_t>(N) * (DIMP + 2) * sizeof(double) <= 20 * 1024) ? 1 : 0;
+    if (const char* e = std::getenv("CMOE_GEN_STAGE")) m.stage_ops = m.stage_ops && std::atoi(e) != 0;
     for (int k = 0; k < 8; ++k) m.derivs[k] = (k < spec.g) ? spec.derivs[k] : 0;
     m.max_steps = inner->max_num_steps;
     m.max_restarts = inner->max_num_restarts;

@@ -74,6 +74,7 @@ struct KgMcParams {
   int aw_slots;      // resident CTAs the scratch was sized for
   int chunks;        // work items per candidate
   int work_total;    // chunks * candidates of this launch
+  int stage_ops;     // general path: scaled training points and e_j fit next to the ring in shared memory
   double lo[CMOE_MAX_DIM], hi[CMOE_MAX_DIM], inv_len[CMOE_MAX_DIM], len[CMOE_MAX_DIM];
 };
 
@@ -154,6 +155,12 @@ __device__ __forceinline__ double2 ld2(const double* p) {
   } else {
     return __ldg(reinterpret_cast<const double2*>(p));
   }
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double ld1(const double* p) {
+  if (SMEM) return *p;
+  return __ldg(p);
 }
 
 // x . y and beta - B . c over the staged operands (one dependent DFMA chain each; splitting them into even / odd
@@ -502,7 +509,7 @@ __device__ __forceinline__ void stream_point_weights(const double* aw, double* r
 //   mu+(x) - m = sum_j [ a_j0 kv + kb sum_m a~_jm (x~_t - X~_jt) ]  with  a_(j,m) = beta_(j,m) - B_(j,m),: . c
 //   d/dx~_d   = (X~_jd - x~_d) (a_j0 kb + kc wsum) + kb a~_jm [d == t]
 // Operands come straight from global memory (read-only path): with g > 0 the pack does not fit in shared memory.
-template <int KERNEL, int DIM, int QP>
+template <int KERNEL, int DIM, int QP, bool XS>
 __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const double* __restrict__ Xt,
                                                    const double* __restrict__ Pk, const double* __restrict__ Xu,
                                                    const double (&xq)[DIM], const double* aw, double* ring,
@@ -535,7 +542,7 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
     double xv[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d += 2) {
-      const double2 v = ld2<false>(xj + d);
+      const double2 v = ld2<XS>(xj + d);
       xv[d] = v.x;
       xv[d + 1] = v.y;
     }
@@ -543,14 +550,14 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
 #pragma unroll
     for (int d = 0; d < DIM; ++d) dot = fma(xq[d], xv[d], dot);
     double kv, kb, kc;
-    kernel_triple<KERNEL>(dot, __ldg(pk), hq, prm.alpha, kv, kb, kc);
+    kernel_triple<KERNEL>(dot, ld1<XS>(pk), hq, prm.alpha, kv, kb, kc);
     const double a0 = aj[0];  // this lane's weights of point j (ring slots)
     double wsum = 0.0;
 #pragma unroll
     for (int m = 0; m < kMaxG; ++m) {
       if (m < g) {
         const double am = aj[(m + 1) * kMcThreads];
-        wsum = fma(am, xm[m] - __ldg(xj + prm.derivs[m]), wsum);
+        wsum = fma(am, xm[m] - ld1<XS>(xj + prm.derivs[m]), wsum);
         em[m] = fma(kb, am, em[m]);
       }
     }
@@ -600,7 +607,7 @@ __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const 
 //     u_j = sum_m a~_jm (x~_t - X~_jt),  v_j = sum_m a~_jm g~_t,  k0_j = k(x, X_j),  G_jk = exp(a_k p_j)
 // the trial values are  E_k [ sum_j k0_j G_jk (a_j0 + u_j) + a_k sum_j k0_j G_jk v_j ]:  S[k] and T[k] below.
 // The (1+g) Q weight FMAs per point — the dominant cost of this path — are paid once per step instead of once per trial.
-template <int DIM, int QP>
+template <int DIM, int QP, bool XS>
 __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const double* __restrict__ Xt,
                                               const double* __restrict__ Pk, const double* __restrict__ Xu,
                                               const double (&xb)[DIM], const double (&gt)[DIM], const double* aw,
@@ -642,7 +649,7 @@ __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const doubl
     double xv[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d += 2) {
-      const double2 v = ld2<false>(xj + d);
+      const double2 v = ld2<XS>(xj + d);
       xv[d] = v.x;
       xv[d + 1] = v.y;
     }
@@ -658,12 +665,12 @@ __device__ __forceinline__ void eval_line_gen(const KgMcParams& prm, const doubl
     for (int m = 0; m < kMaxG; ++m) {
       if (m < g) {
         const double am = aj[(m + 1) * kMcThreads];
-        us = fma(am, xm[m] - __ldg(xj + prm.derivs[m]), us);
+        us = fma(am, xm[m] - ld1<XS>(xj + prm.derivs[m]), us);
         vs = fma(am, gm[m], vs);
       }
     }
     pmax_hi = max(pmax_hi, __double2hiint(pj) & 0x7fffffff);
-    const double k0 = exp_fast(dot + (__ldg(pk) + hq));
+    const double k0 = exp_fast(dot + (ld1<XS>(pk) + hq));
     const double w = k0 * (a0 + us), wv = k0 * vs;
     double G = exp_fast(pj);
 #pragma unroll
@@ -888,7 +895,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
         pmax_hi = 0;  // no factor can leave the double range on this path
         eval_line_matern<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, prm.alpha, xt, gt, c, alpha_n, S);
       } else if (GEN) {
-        eval_line_gen<DIM, QP>(prm, Xt, Pk, Xu, xt, gt, aw, ring, cl, alpha_n * (1.0 / kTop), S,
+        eval_line_gen<DIM, QP, SMEM>(prm, Xt, Pk, Xu, xt, gt, aw, ring, cl, alpha_n * (1.0 / kTop), S,
                                reinterpret_cast<double (&)[kLineBatch]>(T), pmax_hi);
       } else {
         eval_line<DIM, QP, SMEM>(Xt, Pk, Xu, N, U, xt, gt, c, alpha_n * (1.0 / kTop), S, pmax_hi);
@@ -944,7 +951,7 @@ __device__ __forceinline__ void kg_mc_body(const KgMcParams& prm, const double* 
       double S0, SB, s[DIM];
       double em[kMaxG];
       if (GEN) {
-        eval_posterior_gen<KERNEL, DIM, QP>(prm, Xt, Pk, Xu, xq, aw, ring, cl, S0, SB, s, em);
+        eval_posterior_gen<KERNEL, DIM, QP, SMEM>(prm, Xt, Pk, Xu, xq, aw, ring, cl, S0, SB, s, em);
         // kb a~_jm lands on coordinate derivs[m]: fold it into s so that the common gradient formula below holds
         // (grad_d = inv_len_d (s_d - x~_d SB)), using compile-time register indices only
 #pragma unroll
@@ -1135,6 +1142,19 @@ __global__ void __launch_bounds__(kMcThreads, CMOE_MC_GEN_MINBLOCKS)
   __shared__ int work_item;
   const int R = prm.N * (1 + prm.g);
   double* aw = prm.aw + static_cast<size_t>(blockIdx.x) * R * kMcThreads + threadIdx.x;
+  // The weight stream passes through L1 on its way into the ring (8-byte cp.async is .ca only) and evicts everything
+  // else, so the candidate-independent operands of every point — scaled coordinates and e_j — are parked behind the ring
+  // in shared memory when they fit (read as broadcast LDS); e_j is the same for every candidate (candidate 0's pack).
+  double* sX = gen_ring + static_cast<size_t>(kRingRows + kRingDepth) * kMcThreads;
+  double* sE = sX + static_cast<size_t>(prm.N) * DIM;
+  if (prm.stage_ops) {
+    for (int e = threadIdx.x; e < prm.N * DIM; e += blockDim.x) sX[e] = prm.Xt[e];
+    for (int j = threadIdx.x; j < prm.N; j += blockDim.x) {
+      sE[2 * j] = prm.Pk[static_cast<size_t>(j) * prm.pk_stride];
+      sE[2 * j + 1] = 0.0;
+    }
+    __syncthreads();
+  }
   while (true) {
     if (threadIdx.x == 0) work_item = atomicAdd(prm.work, 1);
     __syncthreads();
@@ -1148,8 +1168,13 @@ __global__ void __launch_bounds__(kMcThreads, CMOE_MC_GEN_MINBLOCKS)
     const double* gPk = prm.Pk + static_cast<size_t>(cand) * prm.N * prm.pk_stride;
     const double* gXu = prm.Xu + static_cast<size_t>(cand) * prm.U * (DIM + 2);
     const double* gWt = prm.Wt + static_cast<size_t>(cand) * (1 + QP) * R;
-    kg_mc_body<KERNEL, DIM, QP, false, true>(prm, prm.Xt, gPk, gXu, cand, s_begin, s_end, &next_sample, aw, gWt,
-                                             gen_ring + threadIdx.x);
+    if (prm.stage_ops) {
+      kg_mc_body<KERNEL, DIM, QP, true, true>(prm, sX, sE, gXu, cand, s_begin, s_end, &next_sample, aw, gWt,
+                                              gen_ring + threadIdx.x);
+    } else {
+      kg_mc_body<KERNEL, DIM, QP, false, true>(prm, prm.Xt, gPk, gXu, cand, s_begin, s_end, &next_sample, aw, gWt,
+                                               gen_ring + threadIdx.x);
+    }
     __syncthreads();  // next_sample / work_item are rewritten by thread 0
   }
 }
@@ -1347,7 +1372,8 @@ void launch_kg_mc_gen(const KgMcParams& p, dim3, size_t, cudaStream_t s) {
   int dev = 0, sms = 1, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  constexpr size_t ring_bytes = static_cast<size_t>(kRingRows + kRingDepth) * kMcThreads * sizeof(double);
+  const size_t ring_bytes = static_cast<size_t>(kRingRows + kRingDepth) * kMcThreads * sizeof(double) +
+                            (p.stage_ops ? static_cast<size_t>(p.N) * (DIM + 2) * sizeof(double) : 0);
   cudaFuncSetAttribute(kg_mc_gen_kernel<KERNEL, DIM, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(ring_bytes));
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kg_mc_gen_kernel<KERNEL, DIM, QP>, kMcThreads, ring_bytes);
