@@ -178,6 +178,7 @@ void potrs_lower(const double* L, int n, double* X, int ldx, int nrhs, cudaStrea
 void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans, cudaStream_t s);
 // trsv_coop.cu: one cooperative launch, owner + helper CTAs per 128-unknown block row; false = not applicable / gave up
 bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s);
+bool trsv_coop_pair(const double* L, int n, double* x, cudaStream_t s);
 
 // ---- posterior.cu -------------------------------------------------------------------------------------------
 constexpr int kMaxQ = 96;  // largest (q+p)*(1+num_derivatives) handled by the per-set kernels

@@ -886,6 +886,17 @@ void trsm_lower(const double* L, int n, double* X, int ldx, int nrhs, bool trans
 }
 
 void potrs_lower(const double* L, int n, double* X, int ldx, int nrhs, cudaStream_t s) {
+  if (nrhs <= 4 && n >= 1024 && !legacy_linalg()) {
+    // few right-hand sides on a large factor: both triangular solves of a column back to back (one synchronisation);
+    // a column the cooperative kernel declines (it leaves the right-hand side untouched) takes the two-step path
+    for (int r = 0; r < nrhs; ++r) {
+      double* col = X + static_cast<size_t>(r) * ldx;
+      if (trsv_coop_pair(L, n, col, s)) continue;
+      trsm_lower(L, n, col, ldx, 1, false, s);
+      trsm_lower(L, n, col, ldx, 1, true, s);
+    }
+    return;
+  }
   trsm_lower(L, n, X, ldx, nrhs, false, s);
   trsm_lower(L, n, X, ldx, nrhs, true, s);
 }

@@ -317,8 +317,18 @@ __global__ void __launch_bounds__(CT, 1) trsv_coop_kernel(const TrsvParams P) {
 
 }  // namespace
 
-// false: not applicable (too many block rows for the device, no cooperative launch) or a wait gave up; x untouched
-bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s) {
+namespace {
+
+// workspace kept per host thread and device: cudaMalloc / cudaFree per call cost more than the solve itself
+struct TrsvWorkspace {
+  int device = -1;
+  DevBuf<int> flags;
+  DevBuf<double> out, partial;
+};
+
+// One or two chained solves (forward, then optionally the transposed one on its result) enqueued back to back: one set of
+// sentinel fills, one abort read-back and one host synchronisation for the lot.
+bool trsv_coop_run(const double* L, int n, double* x, bool first_trans, bool both, cudaStream_t s) {
   int dev = 0, sms = 0, coop = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -329,40 +339,47 @@ bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(VB) * VB * sizeof(double);
   CMOE_CUDA(cudaFuncSetAttribute(trsv_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CMOE_CUDA(cudaFuncSetAttribute(trsv_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  // workspace kept per host thread and device: cudaMalloc / cudaFree per call cost more than the solve itself
-  struct Workspace {
-    int device = -1;
-    DevBuf<int> flags;
-    DevBuf<double> out, partial;
-  };
-  static thread_local Workspace ws;
+  static thread_local TrsvWorkspace ws;
   if (ws.device != dev) {
     ws.flags.release();
     ws.out.release();
     ws.partial.release();
     ws.device = dev;
   }
+  const int nsolve = both ? 2 : 1;
+  const size_t np = static_cast<size_t>(nblk) * kMaxHelpers * VB;
   if (ws.flags.count == 0) ws.flags.alloc(1);
-  ws.out.ensure(n);
-  ws.partial.ensure(static_cast<size_t>(nblk) * kMaxHelpers * VB);
-  DevBuf<int>& flags = ws.flags;
-  DevBuf<double>& out = ws.out;
-  DevBuf<double>& partial = ws.partial;
-  CMOE_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), s));
-  CMOE_CUDA(cudaMemsetAsync(out.p, 0xFF, static_cast<size_t>(n) * sizeof(double), s));                 // sentinel
-  CMOE_CUDA(cudaMemsetAsync(partial.p, 0xFF, static_cast<size_t>(nblk) * kMaxHelpers * VB * sizeof(double), s));
-  TrsvParams P{L, n, x, out.p, partial.p, flags.p, nblk, S};
-  void* args[] = {&P};
-  void* fn = trans ? reinterpret_cast<void*>(trsv_coop_kernel<true>) : reinterpret_cast<void*>(trsv_coop_kernel<false>);
-  CMOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nblk * S), dim3(CT), args, smem, s));
-  count_launch();
+  ws.out.ensure(static_cast<size_t>(2) * n);
+  ws.partial.ensure(2 * np);
+  CMOE_CUDA(cudaMemsetAsync(ws.flags.p, 0, sizeof(int), s));
+  CMOE_CUDA(cudaMemsetAsync(ws.out.p, 0xFF, static_cast<size_t>(nsolve) * n * sizeof(double), s));  // sentinel
+  CMOE_CUDA(cudaMemsetAsync(ws.partial.p, 0xFF, nsolve * np * sizeof(double), s));
+  for (int k = 0; k < nsolve; ++k) {
+    const bool trans = (k == 0) ? first_trans : true;
+    TrsvParams P{L, n, k == 0 ? x : ws.out.p, ws.out.p + static_cast<size_t>(k) * n, ws.partial.p + k * np, ws.flags.p, nblk, S};
+    void* args[] = {&P};
+    void* fn = trans ? reinterpret_cast<void*>(trsv_coop_kernel<true>) : reinterpret_cast<void*>(trsv_coop_kernel<false>);
+    CMOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nblk * S), dim3(CT), args, smem, s));
+    count_launch();
+  }
   int aborted = 0;
-  CMOE_CUDA(cudaMemcpyAsync(&aborted, flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CMOE_CUDA(cudaMemcpyAsync(&aborted, ws.flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CMOE_CUDA(cudaStreamSynchronize(s));
   if (aborted) return false;
-  CMOE_CUDA(cudaMemcpyAsync(x, out.p, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CMOE_CUDA(cudaMemcpyAsync(x, ws.out.p + static_cast<size_t>(nsolve - 1) * n, static_cast<size_t>(n) * sizeof(double),
+                            cudaMemcpyDeviceToDevice, s));
   CMOE_CUDA(cudaStreamSynchronize(s));  // the cached workspace may be reused from another stream of this thread
   return true;
 }
+
+}  // namespace
+
+// false: not applicable (too many block rows for the device, no cooperative launch) or a wait gave up; x untouched
+bool trsv_coop(const double* L, int n, double* x, bool trans, cudaStream_t s) {
+  return trsv_coop_run(L, n, x, trans, false, s);
+}
+
+// x <- L^-T L^-1 x in one go (same contract)
+bool trsv_coop_pair(const double* L, int n, double* x, cudaStream_t s) { return trsv_coop_run(L, n, x, false, true, s); }
 
 }  // namespace cmoe
