@@ -181,6 +181,10 @@ def best_so_far_cpu(backend, gp, w, wl):
 def cpu_sample_shape(w, threads):
     # one candidate per thread (OpenMP static over candidates), enough MC samples that the per-candidate set-up
     # (posterior state, Cholesky of the q x q variance) is amortised as it is for the GPU arm
+    # (derivative observations make a CPU sample ~7x dearer — an n = N(1+g) system behind every evaluation: 256 samples
+    # per candidate keep that arm inside the 10-30 s budget)
+    if w["kind"] == "kg" and w["g"]:
+        return threads, 256
     return threads, {"kg": 1024, "ei": 1 << 20}[w["kind"]]
 
 
