@@ -395,6 +395,14 @@ __device__ __forceinline__ int factor_diag64(double* blk, double* LT, double* Mi
 __device__ __noinline__ void panel_role(const CUtensorMap* mapBlk, const CoopParams& P, double* buf, uint64_t* pbar,
                                            uint32_t& pphase, double* colbuf, double* rd, volatile int* sfail, volatile int* sflag,
                                        volatile int* prog, int r) {
+  // out of line: tell the compiler what the caller knew (shared-memory pointers -> LDS / STS instead of generic LD / ST)
+  __builtin_assume(__isShared(buf));
+  __builtin_assume(__isShared(colbuf));
+  __builtin_assume(__isShared(rd));
+  __builtin_assume(__isShared(pbar));
+  __builtin_assume(__isShared(const_cast<const int*>(sfail)));
+  __builtin_assume(__isShared(const_cast<const int*>(sflag)));
+  __builtin_assume(__isShared(const_cast<const int*>(prog)));
   const int tid = threadIdx.x;
   const int nkk = (P.pw + NB - 1) / NB;
   const int rows0 = P.p0 + NB * r;
@@ -553,6 +561,9 @@ __global__ void __launch_bounds__(CTHREADS, 1)
                      const __grid_constant__ CoopParams P) {
   extern __shared__ __align__(128) unsigned char coop_smem_raw[];
   double* buf = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(coop_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  // the round-up hides the address space from the compiler: without this every operand fragment load of the trailing
+  // update is a generic LD.E instead of LDS (seen in the SASS of the DMMA loop)
+  __builtin_assume(__isShared(buf));
   __shared__ __align__(8) uint64_t full[STAGES];
   __shared__ __align__(8) uint64_t empty[STAGES];
   __shared__ __align__(8) uint64_t pbar;
