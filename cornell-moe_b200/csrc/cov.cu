@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
                          const double* __restrict__ Xs, int N, const double* __restrict__ noise, int ntiles) {
   extern __shared__ __align__(128) unsigned char cov_smem_raw[];
   double* stage = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(cov_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  __builtin_assume(__isShared(stage));  // the round-up hides the address space: generic LD / ST instead of LDS / STS otherwise
   const int dim = spec.dim;
   double* slabR = stage + TCW * TR;      // [TR][dim]  rows of Xs as they lie in global memory
   double* slabC = slabR + TR * dim;      // [TCW][dim]

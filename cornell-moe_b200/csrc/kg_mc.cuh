@@ -11,9 +11,11 @@
 // Mapping: one thread per MC sample; grid = (sample chunks, candidates).  Lanes that finish fetch the next sample of
 // the chunk from a shared counter, so a warp only idles at the very end of a chunk although the line search has
 // data-dependent trip counts.  The line search is a per-lane state machine around two warp-uniform routines:
-// "evaluate mu+ and its gradient at my query point" (POINT round) and, for the SquareExponential kernel, "evaluate all
-// backtracking trials of this step along my gradient" (LINE round, eval_line / eval_line_gen); a warp vote picks the
-// kind of round, see kg_mc_body.
+// "evaluate mu+ and its gradient at my query point" (POINT round) and "evaluate all backtracking trials of this step
+// along my gradient" (LINE round: eval_line / eval_line_gen for the SquareExponential kernel, eval_line_matern for
+// Matern-5/2 without derivative observations); a warp vote picks the kind of round, see kg_mc_body.
+// With derivative observations (kg_mc_gen_kernel) the per-sample weights are formed once per sample and streamed back
+// through a per-lane cp.async ring (fill_*_weights, stream_point_weights).
 #pragma once
 
 #include <algorithm>
@@ -52,7 +54,7 @@ struct KgMcParams {
   int use_smem;
   int g;          // derivative observations per point (0 on the fast path)
   int Q;          // rows of the union block = U * (1 + g)
-  int pk_stride;  // doubles per training point in Pk: 1 + (1+g)*(QP+1), rounded up to even
+  int pk_stride;  // doubles per training point in Pk: QP + 2 (g == 0) or 2 (g > 0: e_j only, the weights live in Wt)
   int derivs[8];  // observed partial-derivative indices (g <= 8 on the general path)
   int max_steps, max_restarts;
   double mean, mrc, tol, step_tol, alpha;
@@ -508,7 +510,8 @@ __device__ __forceinline__ void stream_point_weights(const double* aw, double* r
 //   K((j,0), x) = kv ,  K((j,m), x) = kb (x~_t - X~_jt) / l_t   (t = derivs[m-1]; the 1/l_t is folded into the pack)
 //   mu+(x) - m = sum_j [ a_j0 kv + kb sum_m a~_jm (x~_t - X~_jt) ]  with  a_(j,m) = beta_(j,m) - B_(j,m),: . c
 //   d/dx~_d   = (X~_jd - x~_d) (a_j0 kb + kc wsum) + kb a~_jm [d == t]
-// Operands come straight from global memory (read-only path): with g > 0 the pack does not fit in shared memory.
+// The weights a_(j,m) come from this lane's ring slots (aj), the point operands from shared memory when they were
+// parked there (XS) and through the read-only path otherwise.
 template <int KERNEL, int DIM, int QP, bool XS>
 __device__ __forceinline__ void eval_posterior_gen(const KgMcParams& prm, const double* __restrict__ Xt,
                                                    const double* __restrict__ Pk, const double* __restrict__ Xu,
