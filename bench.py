@@ -181,10 +181,11 @@ def best_so_far_cpu(backend, gp, w, wl):
 def cpu_sample_shape(w, threads):
     # one candidate per thread (OpenMP static over candidates), enough MC samples that the per-candidate set-up
     # (posterior state, Cholesky of the q x q variance) is amortised as it is for the GPU arm
-    # (derivative observations make a CPU sample ~7x dearer — an n = N(1+g) system behind every evaluation: 256 samples
-    # per candidate keep that arm inside the 10-30 s budget)
+    # (derivative observations make a CPU sample ~7x dearer — an n = N(1+g) system behind every evaluation; 512 samples per
+    # candidate: ~40 s on 128 threads.  Fewer would leave the per-candidate set-up unamortised — 256 samples measured
+    # 1.0e3 sample-evals/s against 1.9e3 at 1024 — and understate the CPU.)
     if w["kind"] == "kg" and w["g"]:
-        return threads, 256
+        return threads, 512
     return threads, {"kg": 1024, "ei": 1 << 20}[w["kind"]]
 
 
