@@ -583,12 +583,13 @@ def main():
         # DRAM traffic of the same kernel from the committed `ncu --set full` capture (dram__bytes_read + write); the
         # capture ran 256 candidates per launch and the traffic is per-sample records: it scales with the candidates
         traffic, traffic_src = None, None
-        if args.config == "c3" and kernel == 0:
+        cap_file = {"c3": "r1_kg_mc_kernel_ncu.json", "c4": "r2_kg_mc_gen_ncu.json"}.get(args.config)
+        if cap_file and kernel == 0:
             try:
-                with open(os.path.join(ROOT, "profiles", "r1_kg_mc_kernel_ncu.json")) as f:
+                with open(os.path.join(ROOT, "profiles", cap_file)) as f:
                     cap = json.load(f)
                 traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * len(my) / cap["candidates_per_launch"]
-                traffic_src = "profiles/r1_kg_mc_kernel_ncu.json (ncu --set full, scaled by candidates per launch)"
+                traffic_src = f"profiles/{cap_file} (ncu --set full, scaled by candidates per launch)"
             except Exception:
                 pass
         out["roofline"] = {
