@@ -19,11 +19,29 @@ __global__ void center_values_kernel(const double* __restrict__ y, int N, int b,
   out[r] = y[r] - ((r % b == 0) ? mean : 0.0);  // only function-value rows carry the constant prior mean
 }
 
-__global__ void scale_points_kernel(const __grid_constant__ KernelSpec spec, const double* __restrict__ X, int N,
-                                    double* __restrict__ Xs) {
+// Length-scaled coordinates of the fast covariance build, centred first: that kernel forms -r^2/2 as
+// x.y - |x|^2/2 - |y|^2/2, whose absolute error grows with |x|^2 + |y|^2 in length-scale units — a domain far from the
+// origin ([1000, 1010] with l = 1) would otherwise lose ~1e-10 relative on every entry.  The kernels are translation
+// invariant, so any common shift is exact in exact arithmetic; coincident points still map to identical coordinates.
+struct Centre {
+  double c[CMOE_MAX_DIM];
+};
+__global__ void scale_points_kernel(const __grid_constant__ KernelSpec spec, const __grid_constant__ Centre centre,
+                                    const double* __restrict__ X, int N, double* __restrict__ Xs) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * spec.dim) return;
-  Xs[e] = X[e] * spec.inv_len[e % spec.dim];
+  const int d = e % spec.dim;
+  Xs[e] = (X[e] - centre.c[d]) * spec.inv_len[d];
+}
+
+Centre centre_of(const std::vector<double>& hX, int N, int dim) {
+  Centre c{};
+  for (int d = 0; d < dim; ++d) {
+    double m = 0.0;
+    for (int i = 0; i < N; ++i) m += hX[static_cast<size_t>(i) * dim + d];
+    c.c[d] = N > 0 ? m / N : 0.0;
+  }
+  return c;
 }
 
 // ---- incremental append (cmoe_gp_add_sampled_points) --------------------------------------------------------------
@@ -91,7 +109,8 @@ void fit_gp(cmoe_gp* gp, bool mean_change) {
   ensure_scaled_points(gp->dXs, N, spec.dim, s);
   if (gp->dFlag.count == 0) gp->dFlag.alloc(1);
 
-  scale_points_kernel<<<(N * spec.dim + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, N, gp->dXs.p);
+  scale_points_kernel<<<(N * spec.dim + 255) / 256, 256, 0, s>>>(spec, centre_of(gp->hX, N, spec.dim), gp->dX.p, N,
+                                                                 gp->dXs.p);
   count_launch();
   EventTimer t0, t1, t2;
   t0.start(s);
@@ -142,7 +161,7 @@ void append_points(cmoe_gp* gp, const double* new_points, const double* new_valu
   DevBuf<int> dDer(spec.g > 0 ? spec.g : 1), flag(1);
   dXn.upload(new_points, static_cast<size_t>(m) * dim, s);
   if (spec.g > 0) dDer.upload(spec.derivs, spec.g, s);
-  scale_points_kernel<<<(m * dim + 255) / 256, 256, 0, s>>>(spec, dXn.p, m, dXsn.p);
+  scale_points_kernel<<<(m * dim + 255) / 256, 256, 0, s>>>(spec, centre_of(gp->hX, N0, dim), dXn.p, m, dXsn.p);
   // old factor -> top-left block under the new leading dimension
   CMOE_CUDA(cudaMemcpy2DAsync(K1.p, static_cast<size_t>(n1) * sizeof(double), gp->dK.p,
                               static_cast<size_t>(n0) * sizeof(double), static_cast<size_t>(n0) * sizeof(double), n0,
@@ -180,7 +199,8 @@ void append_points(cmoe_gp* gp, const double* new_points, const double* new_valu
   gp->dy.upload(gp->hy.data(), gp->hy.size(), s);
   ensure_scaled_points(gp->dXs, gp->N, dim, s);
   gp->dKinvY.ensure(n1);
-  scale_points_kernel<<<(gp->N * dim + 255) / 256, 256, 0, s>>>(spec, gp->dX.p, gp->N, gp->dXs.p);
+  scale_points_kernel<<<(gp->N * dim + 255) / 256, 256, 0, s>>>(spec, centre_of(gp->hX, gp->N, dim), gp->dX.p, gp->N,
+                                                                gp->dXs.p);
   double mu = 0.0;  // mean_ = average of the function values (gpp_math.cpp:498-504), same summation order
   for (int i = 0; i < gp->N; ++i) mu += gp->hy[static_cast<size_t>(i) * b];
   gp->mean = mu / gp->N;

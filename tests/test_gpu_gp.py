@@ -147,6 +147,27 @@ def test_philox_stream_matches_host(capi):
 
 
 @pytest.mark.parametrize("kernel", [0, 1])
+def test_gp_fit_offset_domain(capi, kernel):
+    """Training points far from the origin relative to the length scale ([1000, 1002]^4, l = 0.5: |x| ~ 4000 length
+    scales).  The fast covariance build forms -r^2/2 as x.y - |x|^2/2 - |y|^2/2; on uncentred coordinates every entry
+    would carry ~eps (|x|^2 + |y|^2) ~ 4e-9 of absolute error in the exponent.  The coordinates are centred before
+    scaling (the kernels are translation invariant), so the factor matches the reference — which differences first —
+    to the same tolerance as a unit-cube problem."""
+    prob = make_problem(200, 4, seed=91)
+    X0 = prob["X"].copy()
+    prob["X"] = 1000.0 + 2.0 * X0
+    prob["lengths"] = np.full(4, 0.5)
+    gp = capi.GaussianProcess(kernel, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"],
+                              prob["derivs"])
+    ref, lm = checker().gp(kernel, prob["alpha"], prob["lengths"], prob["X"], prob["y"], prob["noise"], prob["derivs"])
+    assert lm == 0
+    K, kinvy, mean = gp.state()
+    Kr, kr, mr = ref.state()
+    tril_close(K, Kr, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(kinvy, kr, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
 @pytest.mark.parametrize("N,dim,g_idx", [(50, 2, ()), (24, 3, (0, 2)), (200, 6, ()), (300, 4, (0, 1, 2, 3)), (500, 8, ())])
 def test_gp_fit_matches_checker(capi, kernel, N, dim, g_idx):
     prob = make_problem(N, dim, g_idx=g_idx, seed=N + dim)
