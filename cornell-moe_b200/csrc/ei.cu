@@ -125,7 +125,8 @@ void upload_union_sets(PosteriorBatch& pb, const double* candidates, int nc, int
   CMOE_CUDA(cudaStreamSynchronize(s));  // h goes out of scope
 }
 
-void ei_eval_batch(const cmoe_gp& gp, const double* candidates, int nc, int q, const double* Xp, int p, int num_mc,
+namespace {
+void ei_eval_chunk(const cmoe_gp& gp, const double* candidates, int nc, int q, const double* Xp, int p, int num_mc,
                    double best_so_far, uint64_t seed, const double* dtable, double* ei_host, double* grad_host) {
   cudaStream_t s = gp.stream;
   const int U = q + p, dim = gp.spec.dim;
@@ -155,6 +156,21 @@ void ei_eval_batch(const cmoe_gp& gp, const double* candidates, int nc, int q, c
   if (want_grad) dgrad.download(grad_host, static_cast<size_t>(nc) * q * dim, s);
   CMOE_CUDA(cudaStreamSynchronize(s));
 }
+}  // namespace
+
+// any number of candidates: the per-sample scratch (z, improvement, winner) is bounded to ~2 GiB per chunk — for the C
+// entry point and for the multistart drivers alike
+void ei_eval_batch(const cmoe_gp& gp, const double* candidates, int nc, int q, const double* Xp, int p, int num_mc,
+                   double best_so_far, uint64_t seed, const double* dtable, double* ei_host, double* grad_host) {
+  const int U = q + p, dim = gp.spec.dim;
+  const size_t per_cand = static_cast<size_t>(num_mc) * (U + 2) * sizeof(double);
+  const int batch = static_cast<int>(std::max<size_t>(1, std::min<size_t>(nc, (size_t(2) << 30) / per_cand)));
+  for (int c0 = 0; c0 < nc; c0 += batch) {
+    const int nb = std::min(batch, nc - c0);
+    ei_eval_chunk(gp, candidates + static_cast<size_t>(c0) * q * dim, nb, q, Xp, p, num_mc, best_so_far, seed, dtable,
+                  ei_host + c0, grad_host ? grad_host + static_cast<size_t>(c0) * q * dim : nullptr);
+  }
+}
 
 }  // namespace cmoe
 
@@ -170,14 +186,7 @@ extern "C" int cmoe_ei_eval(const cmoe_gp* gp, const double* candidates, int num
     const int U = q + p;
     DevBuf<double> dtable;
     if (normals_table) dtable.upload(normals_table, static_cast<size_t>(num_mc) * U, gp->stream);
-    // bound scratch (z, improvement, winner per sample) to ~2 GiB per batch of candidates
-    const size_t per_cand = static_cast<size_t>(num_mc) * (U + 2) * sizeof(double);
-    const int batch = static_cast<int>(std::max<size_t>(1, std::min<size_t>(num_candidates, (size_t(2) << 30) / per_cand)));
-    for (int c0 = 0; c0 < num_candidates; c0 += batch) {
-      const int nb = std::min(batch, num_candidates - c0);
-      ei_eval_batch(*gp, candidates + static_cast<size_t>(c0) * q * gp->spec.dim, nb, q, points_being_sampled, p,
-                    num_mc, best_so_far, seed, normals_table ? dtable.p : nullptr, ei + c0,
-                    grad_ei ? grad_ei + static_cast<size_t>(c0) * q * gp->spec.dim : nullptr);
-    }
+    ei_eval_batch(*gp, candidates, num_candidates, q, points_being_sampled, p, num_mc, best_so_far, seed,
+                  normals_table ? dtable.p : nullptr, ei, grad_ei);
   });
 }

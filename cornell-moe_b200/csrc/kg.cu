@@ -620,7 +620,7 @@ int cmoe_kg_plan_create(const cmoe_gp* gp, int num_fidelity, const cmoe_gd_param
     pl->Q = pl->U * (1 + spec.g);
     pl->entry = find_kg_entry(spec.kernel, dim, pl->Q, spec.g > 0);
     CMOE_REQUIRE(pl->entry != nullptr, CMOE_ERR_BOUNDS,
-                 "(q+p)*(1+num_derivatives) or dim exceeds the largest compiled q-KG kernel (32 rows, 8 dims)");
+                 "(q+p)*(1+num_derivatives) or dim exceeds the largest compiled q-KG kernel (32 rows, 32 dims)");
     pl->DIMP = pl->entry->dim;
     pl->QP = pl->entry->qp;
     const int DIMP = pl->DIMP, QP = pl->QP, Q = pl->Q;

@@ -132,7 +132,10 @@ def test_posterior_mean_optimization(capi, kernel, g_idx, nf):
         b, v, found = capi.posterior_mean_optimization(gp, x0, gd, unit_bounds(dim - nf), nf)
         br, vr = ref.posterior_mean_optimization(np.array(x0), gd, unit_bounds(dim - nf), nf)
         assert found
-        np.testing.assert_allclose(b, br, rtol=1e-7, atol=1e-9)
+        # the descent stops once a step is shorter than its 1e-8 tolerance: the end point is defined to ~1e-8 only, and
+        # which iteration stops it depends on last-bit differences of K^-1 y (seen when the covariance build moved to
+        # centred coordinates: 1.6e-8 on one coordinate); the value at the optimum is flat there and keeps its 1e-9
+        np.testing.assert_allclose(b, br, rtol=1e-7, atol=1e-7)
         np.testing.assert_allclose(v, vr, rtol=1e-9)
     # max_num_restarts = 0: the reference returns without touching its outputs
     b, v, found = capi.posterior_mean_optimization(gp, x0, [1, 50, 0, 0, 0.7, 1.0, 0.2, 1e-8], unit_bounds(dim - nf), nf)
